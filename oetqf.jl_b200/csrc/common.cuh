@@ -1,0 +1,122 @@
+// common.cuh -- runtime plumbing shared by the translation units of liboetqf_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/oetqf_b200.h"
+
+namespace oq {
+
+// ---- error reporting (never throw across the ABI) -------------------------------------------
+std::string& last_error();
+int fail(const char* fmt, ...);
+extern std::atomic<int64_t> g_launches;
+int current_device();
+
+#define OQ_CUDA(expr)                                                                          \
+    do {                                                                                       \
+        cudaError_t e__ = (expr);                                                              \
+        if (e__ != cudaSuccess)                                                                \
+            return ::oq::fail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+#define OQ_CHECK(cond, ...)                                   \
+    do {                                                      \
+        if (!(cond)) return ::oq::fail(__VA_ARGS__);          \
+    } while (0)
+
+#define OQ_TRY(expr)                   \
+    do {                               \
+        int rc__ = (expr);             \
+        if (rc__ != 0) return rc__;    \
+    } while (0)
+
+// counts a kernel launch of this library and checks the launch itself
+#define OQ_LAUNCHED()                                   \
+    do {                                                \
+        ::oq::g_launches.fetch_add(1);                  \
+        OQ_CUDA(cudaGetLastError());                    \
+    } while (0)
+
+// Makes sure the calling host thread targets the library's device (Julia tasks migrate between
+// threads; CUDA's current device is per-thread).
+int enter();
+
+// ---- RAII device memory ---------------------------------------------------------------------
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept {
+        if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+        return *this;
+    }
+    ~DevBuf() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    int alloc(size_t count) {
+        release();
+        if (count == 0) return 0;
+        cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+        if (e != cudaSuccess)
+            return fail("cudaMalloc of %zu bytes failed: %s", count * sizeof(T), cudaGetErrorString(e));
+        n = count;
+        return 0;
+    }
+    int upload(const T* host, size_t count) {
+        OQ_TRY(alloc(count));
+        if (count) OQ_CUDA(cudaMemcpy(p, host, count * sizeof(T), cudaMemcpyHostToDevice));
+        return 0;
+    }
+    int zero() {
+        if (n) OQ_CUDA(cudaMemset(p, 0, n * sizeof(T)));
+        return 0;
+    }
+};
+
+struct EventTimer {
+    cudaEvent_t a = nullptr, b = nullptr;
+    ~EventTimer() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+    int start(cudaStream_t s = 0) {
+        if (!a) { OQ_CUDA(cudaEventCreate(&a)); OQ_CUDA(cudaEventCreate(&b)); }
+        OQ_CUDA(cudaEventRecord(a, s));
+        return 0;
+    }
+    int stop(double* ms, cudaStream_t s = 0) {
+        OQ_CUDA(cudaEventRecord(b, s));
+        OQ_CUDA(cudaEventSynchronize(b));
+        float f = 0;
+        OQ_CUDA(cudaEventElapsedTime(&f, a, b));
+        if (ms) *ms = f;
+        return 0;
+    }
+};
+
+inline size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
+
+// sind/cosd on the host with exact values at multiples of 90° (Julia's sincosd)
+void sincosd(double deg, double* s, double* c);
+
+}  // namespace oq
+
+// ---- the opaque handles -----------------------------------------------------------------------
+struct OqMatrix {
+    int row_kind = OQ_ROWS_FAULT;   // how [row_begin,row_end) maps to rows
+    int row_begin = 0, row_end = 0; // fault cells or mantle elements
+    int global_rows = 0;            // nf or 6*ne
+    int local_rows = 0;             // (row_end-row_begin) or 6*(row_end-row_begin)
+    int cols = 0;
+    size_t ld = 0;                  // leading dimension in doubles (multiple of 16)
+    oq::DevBuf<double> d;           // [local_rows * ld], row-major, padding zeroed
+    double kernel_ms = 0.0;         // device time of the assembly kernel(s)
+};

@@ -1,0 +1,757 @@
+// greens.cu -- Green's-function assembly kernels (hot path 1) and the OqMatrix handle.
+//
+// Replaces the four `stress_greens_function` methods of /root/reference/src/BEM/GF.jl (:31,:123,:194,:250).
+// One thread per (receiver, source) pair; element geometry is staged in shared memory; the periodic
+// image loop (GF.jl:47,154), the quadrature loop (GF.jl:146,270) and the stress/traction projections
+// (GF.jl:76-96,163-169) are fused into the kernels.  All device matrices are row-major so that the
+// RHS matvec (rhs.cu) streams each row with coalesced 128-bit loads.
+#include "common.cuh"
+#include "hex8_dev.cuh"
+#include "okada_dev.cuh"
+
+namespace oq {
+
+// ---- device views ---------------------------------------------------------------------------
+struct FaultGeom {
+    const double *x, *ax0, *ax1;            // [nx]
+    const double *y, *z, *axi0, *axi1;      // [nxi]
+    int nx, nxi;
+    double dep;
+};
+
+struct Hex8Geom {
+    const double *cx, *cy, *cz, *qx, *qy, *qz, *dx, *dy, *dz;
+    int n;
+};
+
+struct OkadaParams {
+    OkadaMedium m;
+    double lam, mu;
+    double s1, c1, s2, c2;   // sind(dip), cosd(dip), sind(2dip), cosd(2dip) for the traction projection
+    double lrept;            // image period (GF.jl:38,135)
+    int nrept;
+};
+
+// GF.jl:76-87 on the gradient 9-vector g = u[4..12]
+template <int SLIP>
+__device__ __forceinline__ double shear_traction_grad(const double (&g)[9], const OkadaParams& p)
+{
+    if (SLIP == kStrikeSlip) {
+        const double sxy = p.mu * (g[1] + g[3]);
+        const double sxz = p.mu * (g[2] + g[6]);
+        return -sxy * p.s1 + sxz * p.c1;
+    } else {
+        const double l2m = p.lam + 2.0 * p.mu;
+        const double szz = l2m * g[8] + p.lam * g[0] + p.lam * g[4];
+        const double syy = l2m * g[4] + p.lam * g[0] + p.lam * g[8];
+        const double syz = p.mu * (g[7] + g[5]);
+        return (szz - syy) / 2.0 * p.s2 + syz * p.c2;
+    }
+}
+
+// GF.jl:89-96
+__device__ __forceinline__ double shear_traction_stress(int slip, const double (&s)[6], double s1, double c1,
+                                                        double s2, double c2)
+{
+    return slip == kStrikeSlip ? (-s[1] * s1 + s[2] * c1) : ((s[5] - s[3]) / 2.0 * s2 + s[4] * c2);
+}
+
+// ---- K1: fault -> fault, Toeplitz-unique entries st[i,j,l] (GF.jl:41-58) -------------------------
+// thread t -> (i, j, l) with i fastest: writes are coalesced, the receiver depth (j) and the source
+// row (l) are warp-uniform for nx >= 32 so the EPS / edge branches of the closed form do not diverge.
+template <int SLIP>
+__global__ void __launch_bounds__(128)
+gf_fault_fault_kernel(FaultGeom f, OkadaParams p, double* __restrict__ st)
+{
+    extern __shared__ double sm[];
+    double* sy = sm;
+    double* sz = sy + f.nxi;
+    double* sa0 = sz + f.nxi;
+    double* sa1 = sa0 + f.nxi;
+    for (int k = threadIdx.x; k < f.nxi; k += blockDim.x) {
+        sy[k] = f.y[k]; sz[k] = f.z[k]; sa0[k] = f.axi0[k]; sa1[k] = f.axi1[k];
+    }
+    __syncthreads();
+    const size_t total = (size_t)f.nx * f.nxi * f.nxi;
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int i = (int)(t % f.nx);
+    const int j = (int)((t / f.nx) % f.nxi);
+    const int l = (int)(t / ((size_t)f.nx * f.nxi));
+    const double x = f.x[i], y = sy[j], z = sz[j];
+    const double al1 = f.ax0[0], al2 = f.ax1[0], aw1 = sa0[l], aw2 = sa1[l];
+    double g[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) g[k] = 0.0;
+    for (int r = -p.nrept; r <= p.nrept; ++r) {
+        const double jump = r * p.lrept;
+        okada_gradient<SLIP>(p.m, x, y, z, f.dep, al1 + jump, al2 + jump, aw1, aw2, g);
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) g[k] *= kInv2Pi;
+    st[t] = shear_traction_grad<SLIP>(g, p);
+}
+
+// Dense expansion G[(i,j),(k,l)] = st[|i-k|, j, l] (test/BEM/tests.jl:46-49), rows [r0, r1).
+__global__ void __launch_bounds__(256)
+expand_toeplitz_kernel(const double* __restrict__ st, int nx, int nxi, int r0, int nrows, size_t ld,
+                       double* __restrict__ G)
+{
+    const int nf = nx * nxi;
+    const int row = blockIdx.y;
+    if (row >= nrows) return;
+    const int f = r0 + row;
+    const int i = f % nx, j = f / nx;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < (int)ld; c += gridDim.x * blockDim.x) {
+        double v = 0.0;
+        if (c < nf) {
+            const int k = c % nx, l = c / nx;
+            const int dk = i > k ? i - k : k - i;
+            v = st[dk + (size_t)nx * (j + (size_t)nxi * l)];
+        }
+        G[(size_t)row * ld + c] = v;
+    }
+}
+
+// Strike-wise DFT of the even extension [st; reverse(st[2:end])] of length N = 2nx-1 (GF.jl:60-68).
+// The sequence is real and even, so the transform is the real cosine sum; one thread per output.
+__global__ void __launch_bounds__(256)
+toeplitz_dft_kernel(const double* __restrict__ st, int nx, int npairs, double* __restrict__ out_complex)
+{
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)nx * npairs) return;
+    const int k = (int)(t % nx);
+    const size_t pair = t / nx;
+    const double* s = st + pair * nx;
+    const int N = 2 * nx - 1;
+    double acc = 0.0;
+    for (int m = nx - 1; m >= 1; --m) {
+        // cos(2π k m / N) with exact integer argument reduction
+        const int km = (int)(((long long)k * m) % N);
+        acc += s[m] * cospi(2.0 * (double)km / (double)N);
+    }
+    out_complex[2 * t] = s[0] + 2.0 * acc;
+    out_complex[2 * t + 1] = 0.0;
+}
+
+// ---- K2: fault -> mantle (GF.jl:123-174) -----------------------------------------------------------
+// thread t -> (source fault cell j fastest, receiver element e); writes row-major G[(k*nel+el), j].
+template <int SLIP>
+__global__ void __launch_bounds__(128)
+gf_fault_mantle_kernel(FaultGeom f, Hex8Geom a, OkadaParams p, const double* __restrict__ qc,
+                       const double* __restrict__ qw, int nq, int e_begin, int nel, size_t ld,
+                       double* __restrict__ G)
+{
+    const int nf = f.nx * f.nxi;
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)nf * nel) return;
+    const int j = (int)(t % nf);
+    const int el = (int)(t / nf);
+    const int e = e_begin + el;
+    const int q1 = j % f.nx, q2 = j / f.nx;
+    const double al1 = f.ax0[q1], al2 = f.ax1[q1], aw1 = f.axi0[q2], aw2 = f.axi1[q2];
+    const double cx = a.cx[e], cy = a.cy[e], cz = a.cz[e];
+    const double hx = a.dx[e] / 2, hy = a.dy[e] / 2, hz = a.dz[e] / 2;
+    double s[6] = {0, 0, 0, 0, 0, 0};
+    for (int w = 0; w < nq; ++w) {
+        const double rx = cx + qc[3 * w] * hx;
+        const double ry = cy + qc[3 * w + 1] * hy;
+        const double rz = cz + qc[3 * w + 2] * hz;
+        double g[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) g[k] = 0.0;
+        for (int r = -p.nrept; r <= p.nrept; ++r) {
+            const double jump = r * p.lrept;
+            okada_gradient<SLIP>(p.m, rx, ry, rz, f.dep, al1 + jump, al2 + jump, aw1, aw2, g);
+        }
+#pragma unroll
+        for (int k = 0; k < 9; ++k) g[k] *= kInv2Pi;
+        const double lekk = p.lam * (g[0] + g[4] + g[8]);
+        const double wt = qw[w];
+        s[0] += wt * (lekk + 2.0 * p.mu * g[0]);
+        s[1] += wt * (p.mu * (g[1] + g[3]));
+        s[2] += wt * (p.mu * (g[2] + g[6]));
+        s[3] += wt * (lekk + 2.0 * p.mu * g[4]);
+        s[4] += wt * (p.mu * (g[5] + g[7]));
+        s[5] += wt * (lekk + 2.0 * p.mu * g[8]);
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) G[((size_t)k * nel + el) * ld + j] = s[k];
+}
+
+// ---- K3: mantle -> fault (GF.jl:194-227) -----------------------------------------------------------
+// One geometry evaluation serves all six unit strains (the reference re-evaluates six times).
+// thread t -> (source element e fastest, receiver fault cell); writes G[fl, p*ne + e].
+__global__ void __launch_bounds__(128)
+gf_mantle_fault_kernel(Hex8Geom a, FaultGeom f, double mu, double nu, int slip, double s1, double c1,
+                       double s2, double c2, int r0, int nrows, size_t ld, double* __restrict__ G)
+{
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)a.n * nrows) return;
+    const int e = (int)(t % a.n);
+    const int fl = (int)(t / a.n);
+    const int fc = r0 + fl;
+    const int q1 = fc % f.nx, q2 = fc / f.nx;
+    double S[6][6];
+    hex8_stress_all(f.x[q1], f.y[q2], f.z[q2], a.qx[e], a.qy[e], a.qz[e], a.dx[e], a.dy[e], a.dz[e], mu, nu, S);
+#pragma unroll
+    for (int pc = 0; pc < 6; ++pc)
+        G[(size_t)fl * ld + (size_t)pc * a.n + e] = shear_traction_stress(slip, S[pc], s1, c1, s2, c2);
+}
+
+// ---- K4: mantle -> mantle (GF.jl:250-290) ----------------------------------------------------------
+// thread t -> (source element i fastest, receiver element j); 36 outputs G[(k*nel + jl), p*ne + i].
+__global__ void __launch_bounds__(128)
+gf_mantle_mantle_kernel(Hex8Geom a, double mu, double nu, const double* __restrict__ qc,
+                        const double* __restrict__ qw, int nq, int e_begin, int nel, size_t ld,
+                        double* __restrict__ G)
+{
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)a.n * nel) return;
+    const int i = (int)(t % a.n);
+    const int jl = (int)(t / a.n);
+    const int j = e_begin + jl;
+    const double cx = a.cx[j], cy = a.cy[j], cz = a.cz[j];
+    const double hx = a.dx[j] / 2, hy = a.dy[j] / 2, hz = a.dz[j] / 2;
+    const double qx = a.qx[i], qy = a.qy[i], qz = a.qz[i], ex = a.dx[i], ey = a.dy[i], ez = a.dz[i];
+    double acc[6][6];
+#pragma unroll
+    for (int pc = 0; pc < 6; ++pc)
+#pragma unroll
+        for (int k = 0; k < 6; ++k) acc[pc][k] = 0.0;
+    for (int w = 0; w < nq; ++w) {
+        const double rx = cx + qc[3 * w] * hx;
+        const double ry = cy + qc[3 * w + 1] * hy;
+        const double rz = cz + qc[3 * w + 2] * hz;
+        double S[6][6];
+        hex8_stress_all(rx, ry, rz, qx, qy, qz, ex, ey, ez, mu, nu, S);
+        const double wt = qw[w];
+#pragma unroll
+        for (int pc = 0; pc < 6; ++pc)
+#pragma unroll
+            for (int k = 0; k < 6; ++k) acc[pc][k] += S[pc][k] * wt;
+    }
+#pragma unroll
+    for (int pc = 0; pc < 6; ++pc)
+#pragma unroll
+        for (int k = 0; k < 6; ++k)
+            G[((size_t)k * nel + jl) * ld + (size_t)pc * a.n + i] = acc[pc][k];
+}
+
+// ---- batched direct evaluations (parity probes of the two closed forms) --------------------------
+template <int SLIP>
+__global__ void dc3d_gradient_kernel(int n, const double* x, const double* y, const double* z, OkadaMedium m,
+                                     double dep, double al1, double al2, double aw1, double aw2, double* out)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    double g[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) g[k] = 0.0;
+    okada_gradient<SLIP>(m, x[t], y[t], z[t], dep, al1, al2, aw1, aw2, g);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) out[(size_t)t * 9 + k] = g[k] * kInv2Pi;
+}
+
+__global__ void hex8_stress_kernel(int n, const double* x, const double* y, const double* z, double qx, double qy,
+                                   double qz, double dx, double dy, double dz, const double* eps, double mu,
+                                   double nu, double* out)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    double S[6][6];
+    hex8_stress_all(x[t], y[t], z[t], qx, qy, qz, dx, dy, dz, mu, nu, S);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        double v = 0.0;
+#pragma unroll
+        for (int pc = 0; pc < 6; ++pc) v += eps[pc] * S[pc][k];
+        out[(size_t)t * 6 + k] = v;
+    }
+}
+
+// row-major [rows x ld] -> column-major [rows x cols]
+__global__ void __launch_bounds__(256)
+rowmajor_to_colmajor_kernel(const double* __restrict__ in, int rows, int cols, size_t ld, double* __restrict__ out)
+{
+    __shared__ double tile[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int dy = threadIdx.y; dy < 32; dy += blockDim.y) {
+        const int r = r0 + dy, c = c0 + threadIdx.x;
+        tile[dy][threadIdx.x] = (r < rows && c < cols) ? in[(size_t)r * ld + c] : 0.0;
+    }
+    __syncthreads();
+    for (int dy = threadIdx.y; dy < 32; dy += blockDim.y) {
+        const int c = c0 + dy, r = r0 + threadIdx.x;
+        if (r < rows && c < cols) out[(size_t)c * rows + r] = tile[threadIdx.x][dy];
+    }
+}
+
+// column-major host matrix rows -> row-major shard (inverse of the above, with a row gather)
+__global__ void __launch_bounds__(256)
+colmajor_to_rowmajor_kernel(const double* __restrict__ in, int rows, int cols, size_t ld, double* __restrict__ out)
+{
+    __shared__ double tile[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int dy = threadIdx.y; dy < 32; dy += blockDim.y) {
+        const int c = c0 + dy, r = r0 + threadIdx.x;
+        tile[dy][threadIdx.x] = (r < rows && c < cols) ? in[(size_t)c * rows + r] : 0.0;
+    }
+    __syncthreads();
+    for (int dy = threadIdx.y; dy < 32; dy += blockDim.y) {
+        const int r = r0 + dy, c = c0 + threadIdx.x;
+        if (r < rows && c < (int)ld) out[(size_t)r * ld + c] = (c < cols) ? tile[threadIdx.x][dy] : 0.0;
+    }
+}
+
+// ---- host-side helpers -------------------------------------------------------------------------
+struct DevFaultMesh {
+    DevBuf<double> buf;
+    FaultGeom g{};
+    int upload(const OqFaultMesh* mf)
+    {
+        OQ_CHECK(mf && mf->nx > 0 && mf->nxi > 0, "fault mesh is empty");
+        OQ_CHECK(mf->x && mf->ax0 && mf->ax1 && mf->y && mf->z && mf->axi0 && mf->axi1, "fault mesh has NULL arrays");
+        const size_t nx = mf->nx, nxi = mf->nxi;
+        std::vector<double> h(3 * nx + 4 * nxi);
+        double* q = h.data();
+        auto put = [&](const double* src, size_t n) { memcpy(q, src, n * sizeof(double)); q += n; };
+        put(mf->x, nx); put(mf->ax0, nx); put(mf->ax1, nx);
+        put(mf->y, nxi); put(mf->z, nxi); put(mf->axi0, nxi); put(mf->axi1, nxi);
+        OQ_TRY(buf.upload(h.data(), h.size()));
+        g.x = buf.p; g.ax0 = g.x + nx; g.ax1 = g.ax0 + nx;
+        g.y = g.ax1 + nx; g.z = g.y + nxi; g.axi0 = g.z + nxi; g.axi1 = g.axi0 + nxi;
+        g.nx = mf->nx; g.nxi = mf->nxi; g.dep = mf->dep;
+        return 0;
+    }
+};
+
+struct DevHex8Mesh {
+    DevBuf<double> buf;
+    Hex8Geom g{};
+    int upload(const OqHex8Mesh* ma)
+    {
+        OQ_CHECK(ma && ma->n > 0, "hex8 mesh is empty");
+        OQ_CHECK(ma->cx && ma->cy && ma->cz && ma->qx && ma->qy && ma->qz && ma->dx && ma->dy && ma->dz,
+                 "hex8 mesh has NULL arrays");
+        const size_t n = ma->n;
+        std::vector<double> h(9 * n);
+        const double* src[9] = {ma->cx, ma->cy, ma->cz, ma->qx, ma->qy, ma->qz, ma->dx, ma->dy, ma->dz};
+        for (int k = 0; k < 9; ++k) memcpy(h.data() + k * n, src[k], n * sizeof(double));
+        OQ_TRY(buf.upload(h.data(), h.size()));
+        const double* p = buf.p;
+        g.cx = p; g.cy = p + n; g.cz = p + 2 * n; g.qx = p + 3 * n; g.qy = p + 4 * n; g.qz = p + 5 * n;
+        g.dx = p + 6 * n; g.dy = p + 7 * n; g.dz = p + 8 * n; g.n = ma->n;
+        return 0;
+    }
+};
+
+struct DevQuad {
+    DevBuf<double> c, w;
+    int nq = 0;
+    int upload(const OqQuadrature* q)
+    {
+        static const double c1[3] = {0, 0, 0}, w1[1] = {1.0};   // "Gauss1", GF.jl:103
+        if (!q) { nq = 1; OQ_TRY(c.upload(c1, 3)); return w.upload(w1, 1); }
+        // GF.jl:326: @assert length(qtype[1]) == 3 * length(qtype[2]) "Wrong format of quadrature!"
+        OQ_CHECK(q->nq > 0 && q->coords && q->weights, "Wrong format of quadrature!");
+        nq = q->nq;
+        OQ_TRY(c.upload(q->coords, 3 * (size_t)nq));
+        return w.upload(q->weights, nq);
+    }
+};
+
+static int make_okada_params(const OqFaultMesh* mf, double lam, double mu, int ftype, int nrept,
+                             double buffer_ratio, OkadaParams* p)
+{
+    OQ_CHECK(buffer_ratio >= 0, "Argument `buffer_ratio` must be >= 0.");   // GF.jl:36,131
+    OQ_CHECK(nrept >= 0, "nrept must be >= 0");
+    OQ_CHECK(ftype == OQ_STRIKE_SLIP || ftype == OQ_DIP_SLIP, "unknown fault type %d", ftype);
+    double sd, cd;
+    sincosd(mf->dip, &sd, &cd);
+    p->m = make_okada_medium((lam + mu) / (lam + 2 * mu), sd, cd);
+    p->lam = lam; p->mu = mu;
+    p->s1 = sd; p->c1 = cd;
+    sincosd(2 * mf->dip, &p->s2, &p->c2);
+    p->lrept = (buffer_ratio + 1.0) * (mf->dx * mf->nx);
+    p->nrept = nrept;
+    return 0;
+}
+
+static int alloc_matrix(OqMatrix* M, int row_kind, int row_begin, int row_end, int global_rows, int cols)
+{
+    M->row_kind = row_kind; M->row_begin = row_begin; M->row_end = row_end;
+    M->global_rows = global_rows; M->cols = cols;
+    M->local_rows = (row_kind == OQ_ROWS_MANTLE ? 6 : 1) * (row_end - row_begin);
+    M->ld = round_up((size_t)cols, 16);
+    return M->d.alloc((size_t)M->local_rows * M->ld);
+}
+
+// Toeplitz kernel on the device: st[nx*nxi*nxi]
+static int assemble_toeplitz(const OqFaultMesh* mf, double lam, double mu, int ftype, int nrept,
+                             double buffer_ratio, DevBuf<double>& st, double* kernel_ms)
+{
+    OkadaParams p;
+    DevFaultMesh dm;
+    OQ_TRY(make_okada_params(mf, lam, mu, ftype, nrept, buffer_ratio, &p));
+    OQ_TRY(dm.upload(mf));
+    const size_t total = (size_t)mf->nx * mf->nxi * mf->nxi;
+    OQ_TRY(st.alloc(total));
+    const int threads = 128;
+    const unsigned blocks = (unsigned)((total + threads - 1) / threads);
+    const size_t smem = 4 * (size_t)mf->nxi * sizeof(double);
+    OQ_CHECK(smem <= 48 * 1024, "nxi = %d too large for the shared-memory stage", mf->nxi);
+    EventTimer tm;
+    OQ_TRY(tm.start());
+    if (ftype == OQ_STRIKE_SLIP) gf_fault_fault_kernel<kStrikeSlip><<<blocks, threads, smem>>>(dm.g, p, st.p);
+    else gf_fault_fault_kernel<kDipSlip><<<blocks, threads, smem>>>(dm.g, p, st.p);
+    OQ_LAUNCHED();
+    OQ_TRY(tm.stop(kernel_ms));
+    return 0;
+}
+
+static int matrix_to_host_colmajor(const OqMatrix* M, double* out)
+{
+    DevBuf<double> cm;
+    OQ_TRY(cm.alloc((size_t)M->local_rows * M->cols));
+    dim3 grid((M->cols + 31) / 32, (M->local_rows + 31) / 32), block(32, 8);
+    rowmajor_to_colmajor_kernel<<<grid, block>>>(M->d.p, M->local_rows, M->cols, M->ld, cm.p);
+    OQ_LAUNCHED();
+    OQ_CUDA(cudaMemcpy(out, cm.p, cm.n * sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+}  // namespace oq
+
+using namespace oq;
+
+extern "C" {
+
+int oq_gf_fault_fault(const OqFaultMesh* mf, double lambda, double mu, int ftype, int fourier, int nrept,
+                      double buffer_ratio, double* out, double* kernel_ms)
+{
+    OQ_CHECK(mf && out, "NULL argument");
+    OQ_TRY(enter());
+    DevBuf<double> st;
+    OQ_TRY(assemble_toeplitz(mf, lambda, mu, ftype, nrept, buffer_ratio, st, kernel_ms));
+    if (!fourier) {
+        OQ_CUDA(cudaMemcpy(out, st.p, st.n * sizeof(double), cudaMemcpyDeviceToHost));
+        return 0;
+    }
+    DevBuf<double> dft;
+    OQ_TRY(dft.alloc(2 * st.n));
+    const int npairs = mf->nxi * mf->nxi;
+    toeplitz_dft_kernel<<<(unsigned)((st.n + 255) / 256), 256>>>(st.p, mf->nx, npairs, dft.p);
+    OQ_LAUNCHED();
+    OQ_CUDA(cudaMemcpy(out, dft.p, dft.n * sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int oq_matrix_fault_fault(const OqFaultMesh* mf, double lambda, double mu, int ftype, int nrept,
+                          double buffer_ratio, int row_begin, int row_end, OqMatrix** out)
+{
+    OQ_CHECK(mf && out, "NULL argument");
+    OQ_TRY(enter());
+    const int nf = mf->nx * mf->nxi;
+    OQ_CHECK(0 <= row_begin && row_begin <= row_end && row_end <= nf, "row range [%d,%d) outside [0,%d)",
+             row_begin, row_end, nf);
+    DevBuf<double> st;
+    double ms = 0;
+    OQ_TRY(assemble_toeplitz(mf, lambda, mu, ftype, nrept, buffer_ratio, st, &ms));
+    OqMatrix* M = new OqMatrix();
+    if (alloc_matrix(M, OQ_ROWS_FAULT, row_begin, row_end, nf, nf)) { delete M; return 1; }
+    M->kernel_ms = ms;
+    if (M->local_rows > 0) {
+        dim3 grid((unsigned)((M->ld + 255) / 256), M->local_rows);
+        if (grid.x > 64) grid.x = 64;
+        expand_toeplitz_kernel<<<grid, 256>>>(st.p, mf->nx, mf->nxi, row_begin, M->local_rows, M->ld, M->d.p);
+        g_launches.fetch_add(1);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { delete M; return fail("expand_toeplitz_kernel: %s", cudaGetErrorString(e)); }
+    }
+    *out = M;
+    return 0;
+}
+
+int oq_matrix_from_toeplitz(const double* st_host, int nx, int nxi, int row_begin, int row_end, OqMatrix** out)
+{
+    OQ_CHECK(st_host && out && nx > 0 && nxi > 0, "bad argument");
+    OQ_TRY(enter());
+    const int nf = nx * nxi;
+    OQ_CHECK(0 <= row_begin && row_begin <= row_end && row_end <= nf, "row range [%d,%d) outside [0,%d)",
+             row_begin, row_end, nf);
+    DevBuf<double> st;
+    OQ_TRY(st.upload(st_host, (size_t)nx * nxi * nxi));
+    OqMatrix* M = new OqMatrix();
+    if (alloc_matrix(M, OQ_ROWS_FAULT, row_begin, row_end, nf, nf)) { delete M; return 1; }
+    if (M->local_rows > 0) {
+        dim3 grid((unsigned)((M->ld + 255) / 256), M->local_rows);
+        if (grid.x > 64) grid.x = 64;
+        expand_toeplitz_kernel<<<grid, 256>>>(st.p, nx, nxi, row_begin, M->local_rows, M->ld, M->d.p);
+        g_launches.fetch_add(1);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { delete M; return fail("expand_toeplitz_kernel: %s", cudaGetErrorString(e)); }
+    }
+    *out = M;
+    return 0;
+}
+
+static int build_fault_mantle(const OqFaultMesh* mf, const OqHex8Mesh* ma, const OqQuadrature* quad, double lambda,
+                              double mu, int ftype, int nrept, double buffer_ratio, int e_begin, int e_end,
+                              OqMatrix** out)
+{
+    OQ_CHECK(mf && ma && out, "NULL argument");
+    OQ_TRY(enter());
+    OQ_CHECK(0 <= e_begin && e_begin <= e_end && e_end <= ma->n, "element range [%d,%d) outside [0,%d)", e_begin,
+             e_end, ma->n);
+    OkadaParams p;
+    DevFaultMesh dmf;
+    DevHex8Mesh dma;
+    DevQuad dq;
+    OQ_TRY(make_okada_params(mf, lambda, mu, ftype, nrept, buffer_ratio, &p));
+    OQ_TRY(dmf.upload(mf));
+    OQ_TRY(dma.upload(ma));
+    OQ_TRY(dq.upload(quad));
+    const int nf = mf->nx * mf->nxi, nel = e_end - e_begin;
+    OqMatrix* M = new OqMatrix();
+    if (alloc_matrix(M, OQ_ROWS_MANTLE, e_begin, e_end, 6 * ma->n, nf) || M->d.zero()) { delete M; return 1; }
+    if (nel > 0) {
+        const size_t total = (size_t)nf * nel;
+        const unsigned blocks = (unsigned)((total + 127) / 128);
+        EventTimer tm;
+        int rc = tm.start();
+        if (!rc) {
+            if (ftype == OQ_STRIKE_SLIP)
+                gf_fault_mantle_kernel<kStrikeSlip><<<blocks, 128>>>(dmf.g, dma.g, p, dq.c.p, dq.w.p, dq.nq, e_begin,
+                                                                      nel, M->ld, M->d.p);
+            else
+                gf_fault_mantle_kernel<kDipSlip><<<blocks, 128>>>(dmf.g, dma.g, p, dq.c.p, dq.w.p, dq.nq, e_begin, nel,
+                                                                   M->ld, M->d.p);
+            g_launches.fetch_add(1);
+            rc = tm.stop(&M->kernel_ms);
+        }
+        if (rc) { delete M; return rc; }
+    }
+    *out = M;
+    return 0;
+}
+
+int oq_matrix_fault_mantle(const OqFaultMesh* mf, const OqHex8Mesh* ma, const OqQuadrature* quad, double lambda,
+                           double mu, int ftype, int nrept, double buffer_ratio, int e_begin, int e_end,
+                           OqMatrix** out)
+{
+    return build_fault_mantle(mf, ma, quad, lambda, mu, ftype, nrept, buffer_ratio, e_begin, e_end, out);
+}
+
+int oq_gf_fault_mantle(const OqFaultMesh* mf, const OqHex8Mesh* ma, const OqQuadrature* quad, double lambda,
+                       double mu, int ftype, int nrept, double buffer_ratio, double* outp, double* kernel_ms)
+{
+    OQ_CHECK(outp && ma, "NULL argument");
+    OqMatrix* M = nullptr;
+    OQ_TRY(build_fault_mantle(mf, ma, quad, lambda, mu, ftype, nrept, buffer_ratio, 0, ma->n, &M));
+    if (kernel_ms) *kernel_ms = M->kernel_ms;
+    int rc = matrix_to_host_colmajor(M, outp);
+    delete M;
+    return rc;
+}
+
+static int build_mantle_fault(const OqHex8Mesh* ma, const OqFaultMesh* mf, double lambda, double mu, int ftype,
+                              int row_begin, int row_end, OqMatrix** out)
+{
+    OQ_CHECK(mf && ma && out, "NULL argument");
+    OQ_TRY(enter());
+    const int nf = mf->nx * mf->nxi;
+    OQ_CHECK(0 <= row_begin && row_begin <= row_end && row_end <= nf, "row range [%d,%d) outside [0,%d)",
+             row_begin, row_end, nf);
+    OQ_CHECK(ftype == OQ_STRIKE_SLIP || ftype == OQ_DIP_SLIP, "unknown fault type %d", ftype);
+    DevFaultMesh dmf;
+    DevHex8Mesh dma;
+    OQ_TRY(dmf.upload(mf));
+    OQ_TRY(dma.upload(ma));
+    double s1, c1, s2, c2;
+    sincosd(mf->dip, &s1, &c1);
+    sincosd(2 * mf->dip, &s2, &c2);
+    const double nu = lambda / 2 / (lambda + mu);   // GF.jl:203
+    OqMatrix* M = new OqMatrix();
+    if (alloc_matrix(M, OQ_ROWS_FAULT, row_begin, row_end, nf, 6 * ma->n) || M->d.zero()) { delete M; return 1; }
+    if (M->local_rows > 0) {
+        const size_t total = (size_t)ma->n * M->local_rows;
+        EventTimer tm;
+        int rc = tm.start();
+        if (!rc) {
+            gf_mantle_fault_kernel<<<(unsigned)((total + 127) / 128), 128>>>(dma.g, dmf.g, mu, nu, ftype, s1, c1, s2, c2,
+                                                                             row_begin, M->local_rows, M->ld, M->d.p);
+            g_launches.fetch_add(1);
+            rc = tm.stop(&M->kernel_ms);
+        }
+        if (rc) { delete M; return rc; }
+    }
+    *out = M;
+    return 0;
+}
+
+int oq_matrix_mantle_fault(const OqHex8Mesh* ma, const OqFaultMesh* mf, double lambda, double mu, int ftype,
+                           int row_begin, int row_end, OqMatrix** out)
+{
+    return build_mantle_fault(ma, mf, lambda, mu, ftype, row_begin, row_end, out);
+}
+
+int oq_gf_mantle_fault(const OqHex8Mesh* ma, const OqFaultMesh* mf, double lambda, double mu, int ftype,
+                       double* outp, double* kernel_ms)
+{
+    OQ_CHECK(outp && mf, "NULL argument");
+    OqMatrix* M = nullptr;
+    OQ_TRY(build_mantle_fault(ma, mf, lambda, mu, ftype, 0, mf->nx * mf->nxi, &M));
+    if (kernel_ms) *kernel_ms = M->kernel_ms;
+    int rc = matrix_to_host_colmajor(M, outp);
+    delete M;
+    return rc;
+}
+
+static int build_mantle_mantle(const OqHex8Mesh* ma, const OqQuadrature* quad, double lambda, double mu,
+                               int e_begin, int e_end, OqMatrix** out)
+{
+    OQ_CHECK(ma && out, "NULL argument");
+    OQ_TRY(enter());
+    OQ_CHECK(0 <= e_begin && e_begin <= e_end && e_end <= ma->n, "element range [%d,%d) outside [0,%d)", e_begin,
+             e_end, ma->n);
+    DevHex8Mesh dma;
+    DevQuad dq;
+    OQ_TRY(dma.upload(ma));
+    OQ_TRY(dq.upload(quad));
+    const double nu = lambda / 2 / (lambda + mu);   // GF.jl:259
+    const int nel = e_end - e_begin;
+    OqMatrix* M = new OqMatrix();
+    if (alloc_matrix(M, OQ_ROWS_MANTLE, e_begin, e_end, 6 * ma->n, 6 * ma->n) || M->d.zero()) { delete M; return 1; }
+    if (nel > 0) {
+        const size_t total = (size_t)ma->n * nel;
+        EventTimer tm;
+        int rc = tm.start();
+        if (!rc) {
+            gf_mantle_mantle_kernel<<<(unsigned)((total + 127) / 128), 128>>>(dma.g, mu, nu, dq.c.p, dq.w.p, dq.nq,
+                                                                              e_begin, nel, M->ld, M->d.p);
+            g_launches.fetch_add(1);
+            rc = tm.stop(&M->kernel_ms);
+        }
+        if (rc) { delete M; return rc; }
+    }
+    *out = M;
+    return 0;
+}
+
+int oq_matrix_mantle_mantle(const OqHex8Mesh* ma, const OqQuadrature* quad, double lambda, double mu, int e_begin,
+                            int e_end, OqMatrix** out)
+{
+    return build_mantle_mantle(ma, quad, lambda, mu, e_begin, e_end, out);
+}
+
+int oq_gf_mantle_mantle(const OqHex8Mesh* ma, const OqQuadrature* quad, double lambda, double mu, double* outp,
+                        double* kernel_ms)
+{
+    OQ_CHECK(outp && ma, "NULL argument");
+    OqMatrix* M = nullptr;
+    OQ_TRY(build_mantle_mantle(ma, quad, lambda, mu, 0, ma->n, &M));
+    if (kernel_ms) *kernel_ms = M->kernel_ms;
+    int rc = matrix_to_host_colmajor(M, outp);
+    delete M;
+    return rc;
+}
+
+int oq_dc3d_gradient(int n, const double* x, const double* y, const double* z, double alpha, double dep, double dip,
+                     double al1, double al2, double aw1, double aw2, int ftype, double* out9)
+{
+    OQ_CHECK(n >= 0 && (n == 0 || (x && y && z && out9)), "NULL argument");
+    OQ_CHECK(ftype == OQ_STRIKE_SLIP || ftype == OQ_DIP_SLIP, "unknown fault type %d", ftype);
+    if (n == 0) return 0;
+    OQ_TRY(enter());
+    DevBuf<double> dx, dy, dz, dout;
+    OQ_TRY(dx.upload(x, n)); OQ_TRY(dy.upload(y, n)); OQ_TRY(dz.upload(z, n));
+    OQ_TRY(dout.alloc((size_t)n * 9));
+    double sd, cd;
+    sincosd(dip, &sd, &cd);
+    const OkadaMedium m = make_okada_medium(alpha, sd, cd);
+    const int blocks = (n + 127) / 128;
+    if (ftype == OQ_STRIKE_SLIP)
+        dc3d_gradient_kernel<kStrikeSlip><<<blocks, 128>>>(n, dx.p, dy.p, dz.p, m, dep, al1, al2, aw1, aw2, dout.p);
+    else
+        dc3d_gradient_kernel<kDipSlip><<<blocks, 128>>>(n, dx.p, dy.p, dz.p, m, dep, al1, al2, aw1, aw2, dout.p);
+    OQ_LAUNCHED();
+    OQ_CUDA(cudaMemcpy(out9, dout.p, dout.n * sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int oq_stress_vol_hex8(int n, const double* x, const double* y, const double* z, double qx, double qy, double qz,
+                       double dx, double dy, double dz, const double* eps6, double mu, double nu, double* out6)
+{
+    OQ_CHECK(n >= 0 && eps6 && (n == 0 || (x && y && z && out6)), "NULL argument");
+    if (n == 0) return 0;
+    OQ_TRY(enter());
+    DevBuf<double> bx, by, bz, be, dout;
+    OQ_TRY(bx.upload(x, n)); OQ_TRY(by.upload(y, n)); OQ_TRY(bz.upload(z, n)); OQ_TRY(be.upload(eps6, 6));
+    OQ_TRY(dout.alloc((size_t)n * 6));
+    hex8_stress_kernel<<<(n + 127) / 128, 128>>>(n, bx.p, by.p, bz.p, qx, qy, qz, dx, dy, dz, be.p, mu, nu, dout.p);
+    OQ_LAUNCHED();
+    OQ_CUDA(cudaMemcpy(out6, dout.p, dout.n * sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int oq_matrix_from_host(const double* a, int m, int n, int row_kind, int row_begin, int row_end, OqMatrix** out)
+{
+    OQ_CHECK(a && out && m > 0 && n > 0, "bad argument");
+    OQ_TRY(enter());
+    OQ_CHECK(row_kind == OQ_ROWS_FAULT || row_kind == OQ_ROWS_MANTLE, "bad row_kind");
+    const int units = row_kind == OQ_ROWS_MANTLE ? m / 6 : m;
+    OQ_CHECK(row_kind != OQ_ROWS_MANTLE || m % 6 == 0, "mantle matrices need 6*ne rows");
+    OQ_CHECK(0 <= row_begin && row_begin <= row_end && row_end <= units, "row range [%d,%d) outside [0,%d)",
+             row_begin, row_end, units);
+    OqMatrix* M = new OqMatrix();
+    if (alloc_matrix(M, row_kind, row_begin, row_end, m, n)) { delete M; return 1; }
+    const int nel = row_end - row_begin;
+    if (nel > 0) {
+        // gather the shard's rows on the host into a compact column-major block, then transpose on device
+        const int lr = M->local_rows;
+        std::vector<double> h((size_t)lr * n);
+        for (int c = 0; c < n; ++c)
+            for (int r = 0; r < lr; ++r) {
+                const int gr = row_kind == OQ_ROWS_MANTLE ? (r / nel) * units + row_begin + (r % nel) : row_begin + r;
+                h[(size_t)c * lr + r] = a[(size_t)c * m + gr];
+            }
+        DevBuf<double> cm;
+        int rc = cm.upload(h.data(), h.size());
+        if (!rc) {
+            dim3 grid((unsigned)((M->ld + 31) / 32), (lr + 31) / 32), block(32, 8);
+            colmajor_to_rowmajor_kernel<<<grid, block>>>(cm.p, lr, n, M->ld, M->d.p);
+            g_launches.fetch_add(1);
+            cudaError_t e = cudaDeviceSynchronize();
+            if (e != cudaSuccess) rc = fail("colmajor_to_rowmajor_kernel: %s", cudaGetErrorString(e));
+        }
+        if (rc) { delete M; return rc; }
+    }
+    *out = M;
+    return 0;
+}
+
+int oq_matrix_to_host(const OqMatrix* a, double* outp)
+{
+    OQ_CHECK(a && outp, "NULL argument");
+    OQ_TRY(enter());
+    if (a->local_rows == 0) return 0;
+    return matrix_to_host_colmajor(a, outp);
+}
+
+int oq_matrix_shape(const OqMatrix* a, int* local_rows, int* cols, int* global_rows)
+{
+    OQ_CHECK(a, "NULL matrix");
+    if (local_rows) *local_rows = a->local_rows;
+    if (cols) *cols = a->cols;
+    if (global_rows) *global_rows = a->global_rows;
+    return 0;
+}
+
+int oq_matrix_destroy(OqMatrix* a)
+{
+    if (a) { enter(); delete a; }
+    return 0;
+}
+
+}  // extern "C"

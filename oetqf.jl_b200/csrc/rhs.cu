@@ -1,0 +1,734 @@
+// rhs.cu -- the per-step ODE right-hand side (hot path 2).
+//
+// Replaces ode(du,u,p,t) of /root/reference/src/BEM/equation.jl:156-205 and the kernels it calls:
+//   relative_velocity!      :35-42     -> forcing_kernel
+//   update_strain_rate!     :207-222   -> forcing_kernel   (power-law / composite, :285-292)
+//   relative_strain_rate!   :224-230   -> forcing_kernel
+//   dτ_dt! (FFT conv)       :44-61     -> dense rows of G11 in matvec_fused_kernel, or toeplitz_conv_kernel
+//   3x matvecmul!           :201-203   -> matvec_fused_kernel (both operands of a row in one pass)
+//   update_fault!           :233-246   -> epilogue of matvec_fused_kernel
+//   update_fault_with_dilatancy! :248-276 -> same epilogue, dilatancy branch
+//
+// The matvec is HBM-bound: fp64 matrices are streamed once with 128-bit no-allocate loads, the
+// forcing-vector segment of each CTA is staged in shared memory by a 1-D bulk TMA copy, rows are
+// reduced with warp shuffles, and the last CTA to finish a row block applies the pointwise physics.
+#include "comm.cuh"
+#include "problem.cuh"
+#include "tma.cuh"
+
+namespace oq {
+
+constexpr int kMvThreads = 256;
+constexpr int kMvRows = 4;            // rows per CTA item (x segment reused across them)
+constexpr int kMvMaxSeg = 4096;       // columns per segment (32 KB of shared memory)
+constexpr int kMvColStep = 2 * kMvThreads;
+
+// ---- pointwise: forcing vectors, with the all-gather fused in -----------------------------------------
+struct ForcingArgs {
+    const double* v;       // [nfl]
+    const double* sig;     // [6*nel] or null
+    double* deps_out;      // du.eps [6*nel] or null
+    PeerTargets peers;     // every rank's window (own included)
+    WindowLayout wl;
+    unsigned long long* epochs;   // local counters
+    int nfl, f0, nel, e0, ne;
+    double vpl;
+    MantleParams mp;
+};
+
+__global__ void __launch_bounds__(256) forcing_kernel(const __grid_constant__ ForcingArgs a)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    // buffer copy for this evaluation: parity of the number of publications so far
+    const unsigned long long ep = a.epochs[kEpForcing];
+    const size_t par = (size_t)(ep & 1ull);
+    const int world = a.peers.world;
+    if (t < a.nfl) {
+        const double rv = a.v[t] - a.vpl;                                    // equation.jl:38
+        const size_t off = a.wl.off_relv + par * a.wl.relv_len + a.f0 + t;
+        for (int r = 0; r < world; ++r) a.peers.base[r][off] = rv;           // local + NVLink peer stores
+    }
+    if (t < a.nel) {
+        const size_t n = a.nel;
+        const double s1 = a.sig[t], s2 = a.sig[t + n], s3 = a.sig[t + 2 * n];
+        const double s4 = a.sig[t + 3 * n], s5 = a.sig[t + 4 * n], s6 = a.sig[t + 5 * n];
+        const double skk = (s1 + s4 + s6) / 3;                               // equation.jl:209
+        const double sxx = s1 - skk, syy = s4 - skk, szz = s6 - skk;
+        const double tn = sqrt(sxx * sxx + syy * syy + szz * szz + 2 * (s2 * s2 + s3 * s3 + s5 * s5));
+        const double comp[6] = {sxx, s2, s3, syy, s5, szz};
+        double de[6] = {0, 0, 0, 0, 0, 0};
+        for (int l = 0; l < a.mp.nlaws; ++l) {                               // equation.jl:285-292
+            const double g = a.mp.gamma[(size_t)l * n + t];
+            const double pw = pow(tn, a.mp.npow[(size_t)l * n + t]);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) de[k] += g * comp[k] * pw;
+        }
+        const size_t base = a.wl.off_reldeps + par * a.wl.reldeps_len + a.e0 + t;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            a.deps_out[t + k * n] = de[k];
+            const double rel = de[k] - a.mp.deps0[k];                        // equation.jl:227
+            for (int r = 0; r < world; ++r) a.peers.base[r][base + (size_t)k * a.ne] = rel;
+        }
+    }
+    // publication: the last block to finish bumps the local epoch and tells every peer
+    __shared__ int last;
+    if (world > 1) __threadfence_system(); else __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned long long prev = atomicAdd(&a.epochs[kEpBlocksF], 1ull);
+        last = (prev == (unsigned long long)gridDim.x - 1ull);
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        a.epochs[kEpBlocksF] = 0ull;
+        if (world > 1) {
+            __threadfence_system();
+            for (int r = 0; r < world; ++r) {
+                if (r == a.peers.rank) continue;
+                unsigned long long* f = reinterpret_cast<unsigned long long*>(a.peers.base[r] + a.wl.off_flags);
+                publish_flag(f + a.peers.rank, ep + 1ull);
+            }
+        }
+        __threadfence();
+        a.epochs[kEpForcing] = ep + 1ull;
+    }
+}
+
+// ---- pointwise: rate-and-state friction (equation.jl:233-246, :248-276, :279, :282) --------------
+struct FaultEpilogue {
+    FaultParams fp;
+    const double *v, *theta, *pr;      // state in
+    double *dv, *dtheta, *ddelta, *dpr;
+    int dilatancy;
+};
+
+__device__ __forceinline__ void update_fault_row(const FaultEpilogue& e, int i, double dtau)
+{
+    const FaultParams& p = e.fp;
+    const double v = e.v[i], th = e.theta[i], a = p.a[i], b = p.b[i], L = p.L[i], sg = p.sigma[i];
+    const double dth = 1.0 - v * th / L;                                     // aging law, :279
+    if (!e.dilatancy) {
+        const double psi1 = exp((p.f0 + b * log(p.v0 * fmax(0.0, th) / L)) / a) / (2.0 * p.v0);
+        const double psi2 = sg * psi1 / hypot(1.0, v * psi1);
+        const double dmu_dv = a * psi2;
+        const double dmu_dth = b / th * v * psi2;
+        e.dtheta[i] = dth;
+        e.dv[i] = (dtau - dmu_dth * dth) / (dmu_dv + p.eta);
+        e.ddelta[i] = v;
+    } else {
+        const double pr = e.pr[i];
+        const double dpr = -(pr - p.p0[i]) / p.tp[i] + p.epsd[i] / p.beta[i] / th * dth;   // :282
+        const double af = a / p.f0, bf = b / p.f0;
+        const double vf = fmax(0.0, v / p.v0);
+        const double tf = fmax(0.0, th * p.v0 / L);
+        const double vfa1 = pow(vf, af - 1.0), tfb1 = pow(tf, bf - 1.0);
+        const double vfa = pow(vf, af), tfb = pow(tf, bf);
+        e.dtheta[i] = dth;
+        e.dpr[i] = dpr;
+        e.dv[i] = (dtau + p.f0 * dpr * vfa * tfb - p.f0 * (sg - pr) * vfa * tfb1 * bf * p.v0 / L * dth) /
+                  (p.f0 * (sg - pr) * vfa1 * tfb * af / p.v0);
+        e.ddelta[i] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256) fault_epilogue_kernel(FaultEpilogue e, const double* dtau, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) update_fault_row(e, i, dtau[i]);
+}
+
+// ---- Toeplitz form of the fault-fault interaction (the reference's algorithm, equation.jl:44-61) ----
+// out[i,j] = sum_l sum_k st[|i-k|, j, l] * relv[k, l]  -- the linear convolution the reference evaluates
+// with FFTs, done directly: one CTA per (receiver row j, strike tile); the kernel column st[:,j,l] and
+// the forcing column relv[:,l] are staged in shared memory; each thread produces one receiver i.
+struct PeerWait {
+    const unsigned long long* flags;   // local forcing flags [kMaxWorld]
+    unsigned long long* epochs;        // local counters
+    int world, rank;
+};
+
+// every consumer CTA: find the buffer copy of the current evaluation and make sure all peers delivered
+__device__ __forceinline__ size_t consumer_parity(const PeerWait& w)
+{
+    __shared__ unsigned long long ep_s;
+    if (threadIdx.x == 0) {
+        unsigned long long ep = 1ull;
+        if (w.epochs) {
+            ep = *(volatile unsigned long long*)(w.epochs + kEpForcing);
+            if (w.world > 1) wait_peers(w.flags, w.world, w.rank, ep, w.epochs + kEpError);
+        }
+        ep_s = ep;
+    }
+    __syncthreads();
+    return (size_t)((ep_s - 1ull) & 1ull);
+}
+
+__global__ void __launch_bounds__(256)
+toeplitz_conv_kernel(const double* __restrict__ st, const double* relv0, size_t relv_stride, PeerWait pw, int nx,
+                     int nxi, int f0, int nfl, double* __restrict__ out)
+{
+    extern __shared__ double sm[];
+    double* sk = sm;            // st[0..nx)
+    double* sr = sm + nx;       // relv[0..nx)
+    const double* relv = relv0 + consumer_parity(pw) * relv_stride;
+    const int j = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double acc = 0.0;
+    for (int l = 0; l < nxi; ++l) {
+        __syncthreads();
+        for (int k = threadIdx.x; k < nx; k += blockDim.x) {
+            sk[k] = st[k + (size_t)nx * (j + (size_t)nxi * l)];
+            sr[k] = relv[k + (size_t)nx * l];
+        }
+        __syncthreads();
+        if (i < nx) {
+            for (int k = 0; k < nx; ++k) {
+                const int dk = i > k ? i - k : k - i;
+                acc = fma(sk[dk], sr[k], acc);
+            }
+        }
+    }
+    const int f = i + nx * j;
+    if (i < nx && f >= f0 && f < f0 + nfl) out[f - f0] = acc;
+}
+
+// ---- the fused matvec -------------------------------------------------------------------------
+enum : int { kEpiFault = 0, kEpiStore = 1 };
+
+struct MatvecJob {
+    MatOperand op[2];
+    int nrows;            // local rows
+    int nsegTotal;        // op[0].nseg + op[1].nseg
+    double* partial;      // [nrows * nsegTotal]
+    unsigned* counters;   // [ceil(nrows / kMvRows)]
+    const double* y0;     // optional initial value per row (Toeplitz-form traction rate / accumulate)
+    double* yout;         // kEpiStore target
+    int epilogue;
+    int nitems;           // row blocks * nsegTotal
+};
+
+struct MatvecArgs {
+    MatvecJob job[2];     // fault rows, mantle rows
+    FaultEpilogue fe;
+    PeerWait pw;
+};
+
+__global__ void __launch_bounds__(kMvThreads)
+matvec_fused_kernel(const __grid_constant__ MatvecArgs args)
+{
+    extern __shared__ __align__(16) double sx[];              // x segment, up to kMvMaxSeg doubles
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ double red[kMvThreads / 32][kMvRows];
+    __shared__ int is_last;
+
+    int item = blockIdx.x;
+    const int jsel = item < args.job[0].nitems ? 0 : 1;
+    const MatvecJob& job = args.job[jsel];
+    if (jsel) item -= args.job[0].nitems;
+    const int rb = item / job.nsegTotal;
+    int s = item % job.nsegTotal;
+    const int osel = s < job.op[0].nseg ? 0 : 1;
+    const MatOperand& op = job.op[osel];
+    if (osel) s -= job.op[0].nseg;
+
+    const int tid = threadIdx.x;
+    const int row0 = rb * kMvRows;
+    const int c_begin = s * op.seg_len;
+    const int c_end = min(c_begin + op.seg_len, (int)op.ld);   // padding columns are zero in G and x
+    const int ncol = c_end - c_begin;
+
+    // stage the forcing-vector segment with one bulk TMA copy
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+    }
+    const size_t par = consumer_parity(args.pw);               // includes the CTA-wide barrier
+    if (tid == 0) {
+        if (args.pw.world > 1) fence_proxy_async();            // peer stores -> async-proxy read
+        mbar_arrive_expect_tx(&bar, (unsigned)(ncol * sizeof(double)));
+        tma_load_1d(sx, op.x + par * op.x_stride + c_begin, (unsigned)(ncol * sizeof(double)), &bar);
+    }
+
+    const double* rowp[kMvRows];
+#pragma unroll
+    for (int r = 0; r < kMvRows; ++r) {
+        const int row = min(row0 + r, job.nrows - 1);          // clamp: tail rows are computed and dropped
+        rowp[r] = op.G + (size_t)row * op.ld + c_begin;
+    }
+    double acc[kMvRows];
+#pragma unroll
+    for (int r = 0; r < kMvRows; ++r) acc[r] = 0.0;
+
+    // first batch of matrix loads is issued before waiting for x
+    int c = 2 * tid;
+    double2 g0[kMvRows], g1[kMvRows];
+    const bool h0 = c < ncol, h1 = c + kMvColStep < ncol;
+#pragma unroll
+    for (int r = 0; r < kMvRows; ++r) {
+        g0[r] = h0 ? ldg_stream(rowp[r] + c) : make_double2(0.0, 0.0);
+        g1[r] = h1 ? ldg_stream(rowp[r] + c + kMvColStep) : make_double2(0.0, 0.0);
+    }
+    mbar_wait(&bar, 0);
+    const double2* sx2 = reinterpret_cast<const double2*>(sx);
+    while (c < ncol) {
+        const int cn = c + 2 * kMvColStep;
+        double2 n0[kMvRows], n1[kMvRows];
+        const bool p0 = cn < ncol, p1 = cn + kMvColStep < ncol;
+#pragma unroll
+        for (int r = 0; r < kMvRows; ++r) {
+            n0[r] = p0 ? ldg_stream(rowp[r] + cn) : make_double2(0.0, 0.0);
+            n1[r] = p1 ? ldg_stream(rowp[r] + cn + kMvColStep) : make_double2(0.0, 0.0);
+        }
+        const double2 x0 = sx2[c >> 1];
+        const double2 x1 = (c + kMvColStep < ncol) ? sx2[(c + kMvColStep) >> 1] : make_double2(0.0, 0.0);
+#pragma unroll
+        for (int r = 0; r < kMvRows; ++r) {
+            acc[r] = fma(g0[r].x, x0.x, acc[r]);
+            acc[r] = fma(g0[r].y, x0.y, acc[r]);
+            acc[r] = fma(g1[r].x, x1.x, acc[r]);
+            acc[r] = fma(g1[r].y, x1.y, acc[r]);
+            g0[r] = n0[r];
+            g1[r] = n1[r];
+        }
+        c = cn;
+    }
+
+    // warp-shuffle row reduction, then across the CTA's warps in a fixed order
+#pragma unroll
+    for (int r = 0; r < kMvRows; ++r) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], off);
+    }
+    const int warp = tid >> 5, lane = tid & 31;
+    if (lane == 0) {
+#pragma unroll
+        for (int r = 0; r < kMvRows; ++r) red[warp][r] = acc[r];
+    }
+    __syncthreads();
+    double mine = 0.0;
+    const int myrow = row0 + tid;
+    if (tid < kMvRows && myrow < job.nrows) {
+#pragma unroll
+        for (int w = 0; w < kMvThreads / 32; ++w) mine += red[w][tid];
+    }
+
+    if (job.nsegTotal > 1) {
+        if (tid < kMvRows && myrow < job.nrows)
+            job.partial[(size_t)myrow * job.nsegTotal + (osel ? job.op[0].nseg : 0) + s] = mine;
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned prev = atomicAdd(&job.counters[rb], 1u);
+            is_last = (prev == (unsigned)job.nsegTotal - 1u);
+            if (is_last) job.counters[rb] = 0u;               // re-arm for the next evaluation
+        }
+        __syncthreads();
+        if (!is_last) return;
+        __threadfence();
+        if (tid < kMvRows && myrow < job.nrows) {
+            mine = 0.0;
+            const double* pp = job.partial + (size_t)myrow * job.nsegTotal;
+            for (int q = 0; q < job.nsegTotal; ++q) mine += ld_cg(pp + q);   // fixed order: deterministic
+        }
+    }
+    if (tid < kMvRows && myrow < job.nrows) {
+        if (job.y0) mine += job.y0[myrow];
+        if (job.epilogue == kEpiFault) update_fault_row(args.fe, myrow, mine);
+        else job.yout[myrow] = mine;
+    }
+}
+
+// choose the column split so that the grid has enough CTAs to balance 148 SMs
+static void plan_operand(MatOperand& op, int nrowblocks, int other_min_seg)
+{
+    if (!op.G || op.cols == 0) { op.nseg = 0; op.seg_len = kMvMaxSeg; return; }
+    (void)other_min_seg;
+    const long target_items = 148L * 4 * 16;
+    int want = (int)((target_items + nrowblocks - 1) / (nrowblocks > 0 ? nrowblocks : 1));
+    const int max_seg_count = (int)((op.ld + 2 * kMvColStep - 1) / (2 * kMvColStep));
+    const int min_seg_count = (int)((op.ld + kMvMaxSeg - 1) / kMvMaxSeg);
+    if (want < min_seg_count) want = min_seg_count;
+    if (want > max_seg_count) want = max_seg_count;
+    int seg_len = (int)round_up((op.ld + want - 1) / want, 2 * kMvColStep);
+    if (seg_len > kMvMaxSeg) seg_len = kMvMaxSeg;
+    op.seg_len = seg_len;
+    op.nseg = (int)((op.ld + seg_len - 1) / seg_len);
+}
+
+int plan_job(MatvecJob& job, int nrows)
+{
+    job.nrows = nrows;
+    const int nrb = (nrows + kMvRows - 1) / kMvRows;
+    plan_operand(job.op[0], nrb, 0);
+    plan_operand(job.op[1], nrb, 0);
+    job.nsegTotal = job.op[0].nseg + job.op[1].nseg;
+    job.nitems = nrows > 0 ? nrb * job.nsegTotal : 0;
+    return nrb;
+}
+
+int launch_matvec(const MatvecArgs& a, cudaStream_t stream)
+{
+    const int items = a.job[0].nitems + a.job[1].nitems;
+    if (items == 0) return 0;
+    static bool attr_set = false;
+    const size_t smem = kMvMaxSeg * sizeof(double);
+    if (!attr_set) {
+        OQ_CUDA(cudaFuncSetAttribute(matvec_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    matvec_fused_kernel<<<items, kMvThreads, smem, stream>>>(a);
+    OQ_LAUNCHED();
+    return 0;
+}
+
+StateView view_of(const OqProblem* p, double* b)
+{
+    StateView s{};
+    s.v = b + p->part_off[0];
+    s.theta = b + p->part_off[1];
+    if (p->kind == kFaultOnly) s.delta = b + p->part_off[2];
+    else if (p->kind == kDilatancy) { s.delta = b + p->part_off[2]; s.pr = b + p->part_off[3]; }
+    else { s.eps = b + p->part_off[2]; s.sig = b + p->part_off[3]; s.delta = b + p->part_off[4]; }
+    return s;
+}
+
+int rhs_device(OqProblem* p, const double* uin, double* du)
+{
+    cudaStream_t st = p->stream;
+    const StateView in = view_of(p, const_cast<double*>(uin));
+    const StateView out = view_of(p, du);
+    // 1. forcing vectors; every rank's slice is stored straight into all windows (fused all-gather)
+    ForcingArgs fa{};
+    fa.v = in.v; fa.sig = in.sig; fa.deps_out = out.eps;
+    fa.peers = comm_targets(p); fa.wl = p->wl; fa.epochs = p->epochs;
+    fa.nfl = p->nfl; fa.f0 = p->f0; fa.nel = p->kind == kViscoelastic ? p->nel : 0; fa.e0 = p->e0; fa.ne = p->ne;
+    fa.vpl = p->fp.vpl; fa.mp = p->mp;
+    const int nthr = p->nfl > fa.nel ? p->nfl : fa.nel;
+    forcing_kernel<<<nthr > 0 ? (nthr + 255) / 256 : 1, 256, 0, st>>>(fa);
+    OQ_LAUNCHED();
+    PeerWait pw{p->flags, p->epochs, p->world, p->rank};
+    // 2. fault-fault interaction in Toeplitz form (the reference's algorithm) when requested
+    const double* y0 = nullptr;
+    if (p->gf11_form == OQ_GF11_FFT && p->nfl > 0) {
+        dim3 grid((p->nx + 255) / 256, p->nxi);
+        toeplitz_conv_kernel<<<grid, 256, 2 * p->nx * sizeof(double), st>>>(p->st.p, p->relv, p->wl.relv_len, pw,
+                                                                            p->nx, p->nxi, p->f0, p->nfl, p->dtau0.p);
+        OQ_LAUNCHED();
+        y0 = p->dtau0.p;
+    }
+    // 4. fused matvec + pointwise physics
+    FaultEpilogue fe{};
+    fe.fp = p->fp; fe.v = in.v; fe.theta = in.theta; fe.pr = in.pr;
+    fe.dv = out.v; fe.dtheta = out.theta; fe.ddelta = out.delta; fe.dpr = out.pr;
+    fe.dilatancy = p->kind == kDilatancy;
+    MatvecArgs a{};
+    a.fe = fe;
+    a.pw = pw;
+    a.job[0].op[0] = p->opf[0]; a.job[0].op[1] = p->opf[1];
+    a.job[0].partial = p->partial_f.p; a.job[0].counters = p->counters.p;
+    a.job[0].y0 = y0; a.job[0].epilogue = kEpiFault;
+    const int nrbf = plan_job(a.job[0], p->nfl);
+    a.job[1].op[0] = p->opm[0]; a.job[1].op[1] = p->opm[1];
+    a.job[1].partial = p->partial_m.p; a.job[1].counters = p->counters.p + nrbf;
+    a.job[1].yout = out.sig; a.job[1].epilogue = kEpiStore;
+    plan_job(a.job[1], p->kind == kViscoelastic ? 6 * p->nel : 0);
+    if (a.job[0].nitems == 0 && p->nfl > 0) {
+        // no dense operand on the fault rows (Toeplitz form, fault-only): standalone epilogue
+        OQ_CHECK(y0 != nullptr, "fault rows have no Green's operand");
+        fault_epilogue_kernel<<<(p->nfl + 255) / 256, 256, 0, st>>>(fe, y0, p->nfl);
+        OQ_LAUNCHED();
+    }
+    return launch_matvec(a, st);
+}
+
+// plain y = A x / y += A x on a shard (the matvecmul! slot)
+int gemv_device(const OqMatrix* A, const double* x_dev_padded, const double* y_in, double* y_out,
+                double* partial, unsigned* counters, cudaStream_t st)
+{
+    MatvecArgs a{};
+    a.job[0].op[0].G = A->d.p; a.job[0].op[0].ld = A->ld; a.job[0].op[0].x = x_dev_padded;
+    a.job[0].op[0].cols = A->cols;
+    a.job[0].partial = partial; a.job[0].counters = counters; a.job[0].y0 = y_in; a.job[0].yout = y_out;
+    a.job[0].epilogue = kEpiStore;
+    plan_job(a.job[0], A->local_rows);
+    return launch_matvec(a, st);
+}
+
+int gemv_scratch_sizes(const OqMatrix* A, size_t* npartial, size_t* ncounters)
+{
+    MatvecJob j{};
+    j.op[0].G = A->d.p; j.op[0].ld = A->ld; j.op[0].cols = A->cols;
+    const int nrb = plan_job(j, A->local_rows);
+    *npartial = (size_t)A->local_rows * j.nsegTotal;
+    *ncounters = nrb;
+    return 0;
+}
+
+}  // namespace oq
+
+using namespace oq;
+
+OqProblem::~OqProblem()
+{
+    comm_release(this);
+    if (stream) cudaStreamDestroy(stream);
+}
+
+// ---- problem construction ----------------------------------------------------------------------
+static int finish_problem(OqProblem* p, const OqFaultProperty* pf, const OqDilatancyProperty* dila,
+                          const OqMantleProperty* pa, const double* st_host)
+{
+    OQ_CHECK(pf && pf->a && pf->b && pf->L && pf->sigma, "fault property is NULL");
+    // property.jl:20-24
+    OQ_CHECK(pf->f0 > 0, "f0 must be > 0");
+    OQ_CHECK(pf->v0 > 0, "v0 must be > 0");
+    OQ_CHECK(pf->eta > 0, "eta must be > 0");
+    OQ_CHECK(pf->vpl > 0, "vpl must be > 0");
+    const int nfl = p->nfl, nel = p->nel;
+    const int nlaws = pa ? pa->nlaws : 0;
+    OQ_CHECK(!pa || (nlaws >= 1 && pa->gamma && pa->n && pa->deps0), "mantle property is malformed");
+    // pack local slices of the property arrays
+    std::vector<double> h;
+    auto push_fault = [&](const double* src) { h.insert(h.end(), src + p->f0, src + p->f1); };
+    push_fault(pf->a); push_fault(pf->b); push_fault(pf->L); push_fault(pf->sigma);
+    if (dila) {
+        OQ_CHECK(dila->tp && dila->eps && dila->beta && dila->p0, "dilatancy property is NULL");
+        push_fault(dila->tp); push_fault(dila->eps); push_fault(dila->beta); push_fault(dila->p0);
+    }
+    for (int arr = 0; arr < 2 && pa; ++arr)
+        for (int l = 0; l < nlaws; ++l) {
+            const double* src = (arr == 0 ? pa->gamma : pa->n) + (size_t)l * p->ne;
+            h.insert(h.end(), src + p->e0, src + p->e1);
+        }
+    if (h.empty()) h.push_back(0.0);
+    OQ_TRY(p->props.upload(h.data(), h.size()));
+    const double* q = p->props.p;
+    p->fp.a = q; p->fp.b = q + nfl; p->fp.L = q + 2 * (size_t)nfl; p->fp.sigma = q + 3 * (size_t)nfl;
+    q += 4 * (size_t)nfl;
+    if (dila) {
+        p->fp.tp = q; p->fp.epsd = q + nfl; p->fp.beta = q + 2 * (size_t)nfl; p->fp.p0 = q + 3 * (size_t)nfl;
+        q += 4 * (size_t)nfl;
+    }
+    p->fp.eta = pf->eta; p->fp.vpl = pf->vpl; p->fp.f0 = pf->f0; p->fp.v0 = pf->v0;
+    if (pa) {
+        p->mp.gamma = q; p->mp.npow = q + (size_t)nlaws * nel; p->mp.nlaws = nlaws;
+        for (int k = 0; k < 6; ++k) p->mp.deps0[k] = pa->deps0[k];
+    }
+    // state partitions
+    if (p->kind == kFaultOnly) { p->nparts = 3; p->part_len[0] = p->part_len[1] = p->part_len[2] = nfl; }
+    else if (p->kind == kDilatancy) { p->nparts = 4; for (int i = 0; i < 4; ++i) p->part_len[i] = nfl; }
+    else {
+        p->nparts = 5;
+        p->part_len[0] = p->part_len[1] = p->part_len[4] = nfl;
+        p->part_len[2] = p->part_len[3] = 6 * nel;
+    }
+    size_t off = 0;
+    for (int i = 0; i < p->nparts; ++i) { p->part_off[i] = off; off += round_up((size_t)p->part_len[i], 2); }
+    p->nstate = off;
+    p->nstate_global = p->kind == kViscoelastic ? 3 * (size_t)p->nf + 12 * (size_t)p->ne
+                                                : (size_t)p->nparts * p->nf;
+    OQ_TRY(p->u.alloc(p->nstate + 2)); OQ_TRY(p->u.zero());
+    for (int i = 0; i < 7; ++i) { OQ_TRY(p->k[i].alloc(p->nstate + 2)); OQ_TRY(p->k[i].zero()); }
+    OQ_TRY(p->utmp.alloc(p->nstate + 2)); OQ_TRY(p->utmp.zero());
+    OQ_TRY(p->unew.alloc(p->nstate + 2)); OQ_TRY(p->unew.zero());
+    // forcing vectors, reduction slots and flags: one peer-visible window
+    OQ_TRY(comm_alloc_window(p));
+    // operands
+    if (p->gf11_form == OQ_GF11_DENSE) {
+        OQ_CHECK(p->g11, "dense gf11 requested but no matrix given");
+        p->opf[0].G = p->g11->d.p; p->opf[0].ld = p->g11->ld; p->opf[0].x = p->relv; p->opf[0].x_stride = p->wl.relv_len; p->opf[0].cols = p->g11->cols;
+    } else {
+        OQ_CHECK(st_host, "Toeplitz gf11 requested but no kernel given");
+        OQ_TRY(p->st.upload(st_host, (size_t)p->nx * p->nxi * p->nxi));
+        OQ_TRY(p->dtau0.alloc(nfl > 0 ? nfl : 1));
+        OQ_CHECK(2 * (size_t)p->nx * sizeof(double) <= 48 * 1024, "nx too large for the Toeplitz kernel");
+    }
+    if (p->kind == kViscoelastic) {
+        p->opf[1].G = p->g21->d.p; p->opf[1].ld = p->g21->ld; p->opf[1].x = p->reldeps; p->opf[1].x_stride = p->wl.reldeps_len; p->opf[1].cols = p->g21->cols;
+        p->opm[0].G = p->g12->d.p; p->opm[0].ld = p->g12->ld; p->opm[0].x = p->relv; p->opm[0].x_stride = p->wl.relv_len; p->opm[0].cols = p->g12->cols;
+        p->opm[1].G = p->g22->d.p; p->opm[1].ld = p->g22->ld; p->opm[1].x = p->reldeps; p->opm[1].x_stride = p->wl.reldeps_len; p->opm[1].cols = p->g22->cols;
+    }
+    // matvec scratch
+    MatvecJob jf{}, jm{};
+    jf.op[0] = p->opf[0]; jf.op[1] = p->opf[1];
+    jm.op[0] = p->opm[0]; jm.op[1] = p->opm[1];
+    const int nrbf = plan_job(jf, nfl);
+    const int nrbm = plan_job(jm, p->kind == kViscoelastic ? 6 * nel : 0);
+    p->nseg_f = jf.nsegTotal; p->nseg_m = jm.nsegTotal;
+    OQ_TRY(p->partial_f.alloc((size_t)nfl * (jf.nsegTotal > 0 ? jf.nsegTotal : 1) + 1));
+    OQ_TRY(p->partial_m.alloc((size_t)6 * nel * (jm.nsegTotal > 0 ? jm.nsegTotal : 1) + 1));
+    OQ_TRY(p->counters.alloc((size_t)nrbf + nrbm + 1)); OQ_TRY(p->counters.zero());
+    OQ_TRY(p->errpart.alloc(1024)); OQ_TRY(p->errpart.zero());
+    OQ_TRY(p->ctl.alloc(32)); OQ_TRY(p->ctl.zero());
+    OQ_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    OQ_CUDA(cudaDeviceSynchronize());
+    return 0;
+}
+
+static int check_matrix(const OqMatrix* m, const char* name, int kind, int rows_global, int cols)
+{
+    OQ_CHECK(m, "%s is NULL", name);
+    OQ_CHECK(m->row_kind == kind, "%s has the wrong row kind", name);
+    OQ_CHECK(m->global_rows == rows_global && m->cols == cols, "%s is %dx%d, expected %dx%d", name, m->global_rows,
+             m->cols, rows_global, cols);
+    return 0;
+}
+
+extern "C" {
+
+int oq_problem_create_fault(int nx, int nxi, int gf11_form, const OqMatrix* g11, const double* st_toeplitz,
+                            const OqFaultProperty* pf, const OqDilatancyProperty* dila, OqProblem** out)
+{
+    OQ_CHECK(out && nx > 0 && nxi > 0, "bad argument");
+    OQ_TRY(enter());
+    OqProblem* p = new OqProblem();
+    p->kind = dila ? kDilatancy : kFaultOnly;
+    p->nx = nx; p->nxi = nxi; p->nf = nx * nxi; p->gf11_form = gf11_form;
+    int rc = 0;
+    if (gf11_form == OQ_GF11_DENSE) {
+        rc = check_matrix(g11, "g11", OQ_ROWS_FAULT, p->nf, p->nf);
+        if (!rc) { p->g11 = g11; p->f0 = g11->row_begin; p->f1 = g11->row_end; }
+    } else if (gf11_form == OQ_GF11_FFT) {
+        p->f0 = 0; p->f1 = p->nf;
+    } else rc = fail("unknown gf11 form %d", gf11_form);
+    p->nfl = p->f1 - p->f0;
+    if (!rc) rc = finish_problem(p, pf, dila, nullptr, st_toeplitz);
+    if (rc) { delete p; return rc; }
+    *out = p;
+    return 0;
+}
+
+int oq_problem_create_viscoelastic(int nx, int nxi, int ne, int gf11_form, const OqMatrix* g11,
+                                   const double* st_toeplitz, const OqMatrix* g12, const OqMatrix* g21,
+                                   const OqMatrix* g22, const OqFaultProperty* pf, const OqMantleProperty* pa,
+                                   OqProblem** out)
+{
+    OQ_CHECK(out && nx > 0 && nxi > 0 && ne > 0 && pa, "bad argument");
+    OQ_TRY(enter());
+    OqProblem* p = new OqProblem();
+    p->kind = kViscoelastic;
+    p->nx = nx; p->nxi = nxi; p->nf = nx * nxi; p->ne = ne; p->gf11_form = gf11_form;
+    int rc = check_matrix(g12, "g12", OQ_ROWS_MANTLE, 6 * ne, p->nf);
+    if (!rc) rc = check_matrix(g21, "g21", OQ_ROWS_FAULT, p->nf, 6 * ne);
+    if (!rc) rc = check_matrix(g22, "g22", OQ_ROWS_MANTLE, 6 * ne, 6 * ne);
+    if (!rc) {
+        p->g12 = g12; p->g21 = g21; p->g22 = g22;
+        p->f0 = g21->row_begin; p->f1 = g21->row_end;
+        p->e0 = g22->row_begin; p->e1 = g22->row_end;
+        if (g12->row_begin != p->e0 || g12->row_end != p->e1) rc = fail("g12 and g22 shard different elements");
+    }
+    if (!rc && gf11_form == OQ_GF11_DENSE) {
+        rc = check_matrix(g11, "g11", OQ_ROWS_FAULT, p->nf, p->nf);
+        if (!rc && (g11->row_begin != p->f0 || g11->row_end != p->f1)) rc = fail("g11 and g21 shard different rows");
+        p->g11 = g11;
+    } else if (!rc && gf11_form != OQ_GF11_FFT) rc = fail("unknown gf11 form %d", gf11_form);
+    p->nfl = p->f1 - p->f0; p->nel = p->e1 - p->e0;
+    if (!rc) rc = finish_problem(p, pf, nullptr, pa, st_toeplitz);
+    if (rc) { delete p; return rc; }
+    *out = p;
+    return 0;
+}
+
+int oq_problem_destroy(OqProblem* p)
+{
+    if (p) { enter(); cudaDeviceSynchronize(); delete p; }
+    return 0;
+}
+
+int oq_problem_layout(const OqProblem* p, int* nparts, int* lengths)
+{
+    OQ_CHECK(p && nparts && lengths, "NULL argument");
+    *nparts = p->nparts;
+    for (int i = 0; i < 5; ++i) lengths[i] = i < p->nparts ? p->part_len[i] : 0;
+    return 0;
+}
+
+static int upload_parts(OqProblem* p, const double* const* parts, double* dst)
+{
+    for (int i = 0; i < p->nparts; ++i) {
+        OQ_CHECK(parts[i] || p->part_len[i] == 0, "state partition %d is NULL", i);
+        if (p->part_len[i])
+            OQ_CUDA(cudaMemcpyAsync(dst + p->part_off[i], parts[i], p->part_len[i] * sizeof(double),
+                                    cudaMemcpyHostToDevice, p->stream));
+    }
+    return 0;
+}
+
+static int download_parts(const OqProblem* p, const double* src, double* const* parts)
+{
+    for (int i = 0; i < p->nparts; ++i) {
+        OQ_CHECK(parts[i] || p->part_len[i] == 0, "state partition %d is NULL", i);
+        if (p->part_len[i])
+            OQ_CUDA(cudaMemcpyAsync(parts[i], src + p->part_off[i], p->part_len[i] * sizeof(double),
+                                    cudaMemcpyDeviceToHost, p->stream));
+    }
+    OQ_CUDA(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+int oq_rhs(OqProblem* p, double t, const double* const* u_parts, double* const* du_parts)
+{
+    (void)t;   // the system is autonomous (equation.jl:156-205 never reads t)
+    OQ_CHECK(p && u_parts && du_parts, "NULL argument");
+    OQ_TRY(enter());
+    OQ_TRY(upload_parts(p, u_parts, p->utmp.p));
+    OQ_TRY(rhs_device(p, p->utmp.p, p->unew.p));
+    return download_parts(p, p->unew.p, du_parts);
+}
+
+int oq_state_set(OqProblem* p, const double* const* u_parts)
+{
+    OQ_CHECK(p && u_parts, "NULL argument");
+    OQ_TRY(enter());
+    OQ_TRY(upload_parts(p, u_parts, p->u.p));
+    OQ_CUDA(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+int oq_state_get(const OqProblem* p, double* const* u_parts)
+{
+    OQ_CHECK(p && u_parts, "NULL argument");
+    OQ_TRY(enter());
+    return download_parts(p, p->u.p, u_parts);
+}
+
+int oq_state_get_du(const OqProblem* p, double* const* du_parts)
+{
+    OQ_CHECK(p && du_parts, "NULL argument");
+    OQ_TRY(enter());
+    return download_parts(p, p->k[0].p, du_parts);
+}
+
+int oq_rhs_resident(OqProblem* p, int nevals, double* ms_total)
+{
+    OQ_CHECK(p && nevals >= 0, "bad argument");
+    OQ_TRY(enter());
+    EventTimer tm;
+    OQ_TRY(tm.start(p->stream));
+    for (int i = 0; i < nevals; ++i) OQ_TRY(rhs_device(p, p->u.p, p->k[0].p));
+    OQ_TRY(tm.stop(ms_total, p->stream));
+    return 0;
+}
+
+int oq_gemv(const OqMatrix* A, const double* x, double* y, int accumulate)
+{
+    OQ_CHECK(A && x && y, "NULL argument");
+    OQ_TRY(enter());
+    if (A->local_rows == 0) return 0;
+    DevBuf<double> dx, dy, partial;
+    DevBuf<unsigned> counters;
+    OQ_TRY(dx.alloc(A->ld + kMvMaxSeg)); OQ_TRY(dx.zero());
+    OQ_CUDA(cudaMemcpy(dx.p, x, A->cols * sizeof(double), cudaMemcpyHostToDevice));
+    OQ_TRY(dy.alloc(A->local_rows));
+    if (accumulate) OQ_CUDA(cudaMemcpy(dy.p, y, A->local_rows * sizeof(double), cudaMemcpyHostToDevice));
+    size_t np = 0, nc = 0;
+    gemv_scratch_sizes(A, &np, &nc);
+    OQ_TRY(partial.alloc(np + 1));
+    OQ_TRY(counters.alloc(nc + 1)); OQ_TRY(counters.zero());
+    OQ_TRY(gemv_device(A, dx.p, accumulate ? dy.p : nullptr, dy.p, partial.p, counters.p, 0));
+    OQ_CUDA(cudaMemcpy(y, dy.p, A->local_rows * sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,291 @@
+// solve.cu -- device-resident adaptive Runge-Kutta integrator (Tsit5) around the RHS of rhs.cu.
+//
+// Takes the place of OrdinaryDiffEq's `solve(prob, Tsit5(); reltol, abstol, dtmax, dt, maxiters)` as the
+// reference drives it (/root/reference/src/io.jl:128-130, test/tests.jl:11, examples/otf-with-mantle.jl:160-162):
+// stage combinations, the scaled error norm, the PI step-size controller and the accept/reject copy all
+// run on the GPU; the host reads one small control record per step.  Semantics follow OrdinaryDiffEq:
+//   EEst = sqrt( mean_i ( err_i / (abstol + reltol*max(|uprev_i|,|u_i|)) )^2 ) over ALL state scalars,
+//   PI controller beta1 = 7/50, beta2 = 2/25, gamma = 0.9, qmin = 0.2, qmax = 10, qoldinit = 1e-4.
+#include <cmath>
+
+#include "comm.cuh"
+#include "problem.cuh"
+
+namespace oq {
+
+// Tsitouras 5(4) tableau (Tsitouras 2011; the coefficients OrdinaryDiffEq's Tsit5 uses)
+__constant__ double cA[7][6] = {
+    {0, 0, 0, 0, 0, 0},
+    {0.161, 0, 0, 0, 0, 0},
+    {-0.008480655492356989, 0.335480655492357, 0, 0, 0, 0},
+    {2.8971530571054935, -6.359448489975075, 4.3622954328695815, 0, 0, 0},
+    {5.325864828439257, -11.748883564062828, 7.4955393428898365, -0.09249506636175525, 0, 0},
+    {5.86145544294642, -12.92096931784711, 8.159367898576159, -0.071584973281401, -0.028269050394068383, 0},
+    {0.09646076681806523, 0.01, 0.4798896504144996, 1.379008574103742, -3.290069515436081, 2.324710524099774}};
+__constant__ double cBtilde[7] = {-0.00178001105222577714, -0.0008164344596567469, 0.007880878010261995,
+                                  -0.1447110071732629,     0.5823571654525552,     -0.45808210592918697,
+                                  0.015151515151515152};
+
+struct StepCtl {
+    double t, dt, qold, eest, tstop, dtmax, reltol, abstol;
+    double dt_last;
+    long long naccept, nreject, nrhs;
+    int accepted, done, retcode, fixed;
+};
+static_assert(sizeof(StepCtl) <= 32 * sizeof(double), "ctl buffer too small");
+
+struct Stages {
+    const double* k[7];
+};
+
+// y = u + dt * sum_{j<nk} A[s][j] k_j
+__global__ void __launch_bounds__(256)
+stage_kernel(const double* __restrict__ u, Stages ks, int s, int nk, const StepCtl* __restrict__ ctl, size_t n,
+             double* __restrict__ y)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double dt = ctl->dt;
+    double acc = 0.0;
+#pragma unroll
+    for (int j = 0; j < 6; ++j)
+        if (j < nk) acc = fma(cA[s][j], ks.k[j][i], acc);
+    y[i] = fma(dt, acc, u[i]);
+}
+
+struct ErrArgs {
+    const double *u, *unew;
+    Stages ks;
+    const StepCtl* ctl;
+    size_t n;
+    double* errpart;                 // [gridDim.x]
+    unsigned long long* epochs;
+    PeerTargets peers;
+    WindowLayout wl;
+};
+
+// scaled error partial sums; the last block folds them (fixed order) and publishes this rank's sum
+__global__ void __launch_bounds__(256) error_kernel(const __grid_constant__ ErrArgs a)
+{
+    __shared__ double red[8];
+    __shared__ int last;
+    const double dt = a.ctl->dt, atol = a.ctl->abstol, rtol = a.ctl->reltol;
+    double s = 0.0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (size_t)gridDim.x * blockDim.x) {
+        double e = 0.0;
+#pragma unroll
+        for (int j = 0; j < 7; ++j) e = fma(cBtilde[j], a.ks.k[j][i], e);
+        e *= dt;
+        const double sk = atol + rtol * fmax(fabs(a.u[i]), fabs(a.unew[i]));
+        const double q = e / sk;
+        s = fma(q, q, s);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double b = 0.0;
+        for (int w = 0; w < 8; ++w) b += red[w];
+        a.errpart[blockIdx.x] = b;
+        __threadfence();
+        const unsigned long long prev = atomicAdd(&a.epochs[kEpBlocksR], 1ull);
+        last = (prev == (unsigned long long)gridDim.x - 1ull);
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        a.epochs[kEpBlocksR] = 0ull;
+        __threadfence();
+        double tot = 0.0;
+        for (unsigned b = 0; b < gridDim.x; ++b) tot += *(volatile double*)(a.errpart + b);
+        const unsigned long long ep = a.epochs[kEpReduce];
+        const size_t par = (size_t)(ep & 1ull);
+        const int world = a.peers.world, rank = a.peers.rank;
+        for (int r = 0; r < world; ++r) a.peers.base[r][a.wl.off_red + par * kMaxWorld + rank] = tot;
+        if (world > 1) {
+            __threadfence_system();
+            for (int r = 0; r < world; ++r) {
+                if (r == rank) continue;
+                unsigned long long* f = reinterpret_cast<unsigned long long*>(a.peers.base[r] + a.wl.off_flags);
+                publish_flag(f + kMaxWorld + rank, ep + 1ull);
+            }
+        }
+        __threadfence();
+        a.epochs[kEpReduce] = ep + 1ull;
+    }
+}
+
+struct CtlArgs {
+    StepCtl* ctl;
+    const double* red_slots;             // [2][kMaxWorld]
+    const unsigned long long* flags;     // [2][kMaxWorld]
+    unsigned long long* epochs;
+    int world, rank;
+    double nglobal;
+};
+
+// one thread: error norm -> accept/reject -> next dt (OrdinaryDiffEq's PI controller)
+__global__ void controller_kernel(CtlArgs a)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    StepCtl& c = *a.ctl;
+    if (c.done) { c.accepted = 0; return; }
+    const unsigned long long ep = *(volatile unsigned long long*)(a.epochs + kEpReduce);
+    if (a.world > 1) wait_peers(a.flags + kMaxWorld, a.world, a.rank, ep, a.epochs + kEpError);
+    const size_t par = (size_t)((ep - 1ull) & 1ull);
+    double tot = 0.0;
+    for (int r = 0; r < a.world; ++r) tot += *(volatile const double*)(a.red_slots + par * kMaxWorld + r);
+    const double eest = sqrt(tot / a.nglobal);
+    c.eest = eest;
+    c.nrhs += 6;
+    const double beta1 = 7.0 / 50.0, beta2 = 2.0 / 25.0, gamma = 0.9, qmin = 0.2, qmax = 10.0;
+    if (c.fixed) {
+        c.accepted = 1; c.naccept += 1; c.t += c.dt; c.dt_last = c.dt;
+        if (c.t + c.dt > c.tstop) c.dt = c.tstop - c.t;
+        if (c.t >= c.tstop - 4e-16 * fabs(c.tstop) || c.dt <= 0.0) c.done = 1;
+        return;
+    }
+    if (!(eest == eest) || isinf(eest)) {           // NaN / Inf: treat as a failed step with maximal shrink
+        c.accepted = 0; c.nreject += 1; c.dt *= qmin;
+        if (c.dt < 1e-300) { c.done = 1; c.retcode = 2; }
+        return;
+    }
+    const double q11 = pow(eest, beta1);
+    double q = q11 / pow(c.qold, beta2);
+    q = fmax(1.0 / qmax, fmin(1.0 / qmin, q / gamma));
+    if (eest <= 1.0) {
+        c.accepted = 1; c.naccept += 1;
+        c.t += c.dt; c.dt_last = c.dt;
+        c.qold = fmax(eest, 1e-4);
+        double dtn = c.dt / q;
+        if (dtn > c.dtmax) dtn = c.dtmax;
+        if (c.t >= c.tstop - 4e-16 * fabs(c.tstop)) { c.done = 1; c.t = c.tstop; }
+        else if (c.t + dtn > c.tstop) dtn = c.tstop - c.t;
+        c.dt = dtn;
+    } else {
+        c.accepted = 0; c.nreject += 1;
+        c.dt = c.dt / fmin(1.0 / qmin, q11 / gamma);
+        if (c.dt <= fabs(c.t) * 2.2e-16) { c.done = 1; c.retcode = 2; }
+    }
+}
+
+// on acceptance: u <- unew, k1 <- k7 (first-same-as-last)
+__global__ void __launch_bounds__(256)
+accept_kernel(const StepCtl* __restrict__ ctl, size_t n, const double* __restrict__ unew,
+              const double* __restrict__ k7, double* __restrict__ u, double* __restrict__ k1)
+{
+    if (!ctl->accepted) return;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { u[i] = unew[i]; k1[i] = k7[i]; }
+}
+
+static int enqueue_step(OqProblem* p)
+{
+    cudaStream_t st = p->stream;
+    const size_t n = p->nstate;
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    StepCtl* ctl = reinterpret_cast<StepCtl*>(p->ctl.p);
+    Stages ks;
+    for (int j = 0; j < 7; ++j) ks.k[j] = p->k[j].p;
+    for (int s = 1; s <= 6; ++s) {
+        double* y = s < 6 ? p->utmp.p : p->unew.p;
+        stage_kernel<<<blocks, 256, 0, st>>>(p->u.p, ks, s, s, ctl, n, y);
+        OQ_LAUNCHED();
+        OQ_TRY(rhs_device(p, y, p->k[s].p));
+    }
+    ErrArgs ea{};
+    ea.u = p->u.p; ea.unew = p->unew.p; ea.ks = ks; ea.ctl = ctl; ea.n = n; ea.errpart = p->errpart.p;
+    ea.epochs = p->epochs; ea.peers = comm_targets(p); ea.wl = p->wl;
+    unsigned eblocks = blocks < 512 ? blocks : 512;
+    error_kernel<<<eblocks, 256, 0, st>>>(ea);
+    OQ_LAUNCHED();
+    CtlArgs ca{ctl, p->red_slots, p->flags, p->epochs, p->world, p->rank, (double)p->nstate_global};
+    controller_kernel<<<1, 32, 0, st>>>(ca);
+    OQ_LAUNCHED();
+    accept_kernel<<<blocks, 256, 0, st>>>(ctl, n, p->unew.p, p->k[6].p, p->u.p, p->k[0].p);
+    OQ_LAUNCHED();
+    return 0;
+}
+
+}  // namespace oq
+
+using namespace oq;
+
+extern "C" int oq_solve(OqProblem* p, double t0, const OqSolveOptions* o, int64_t stride, OqSnapshotFn fn, void* user,
+                        OqSolveStats* stats)
+{
+    OQ_CHECK(p && o, "NULL argument");
+    OQ_CHECK(o->algorithm == 0, "only Tsit5 (algorithm 0) is implemented");
+    OQ_CHECK(o->tstop > t0, "tstop must be greater than t0");
+    OQ_CHECK(o->fixed_dt || (o->reltol > 0 && o->abstol > 0), "tolerances must be positive");
+    OQ_TRY(enter());
+    if (stride < 1) stride = 1;
+    StepCtl h{};
+    h.t = t0; h.tstop = o->tstop;
+    h.dtmax = o->dtmax > 0 ? o->dtmax : (o->tstop - t0);
+    h.dt = o->dt0 > 0 ? o->dt0 : 1e-6 * (o->tstop - t0);
+    if (h.dt > h.dtmax) h.dt = h.dtmax;
+    if (t0 + h.dt > o->tstop) h.dt = o->tstop - t0;
+    h.qold = 1e-4; h.reltol = o->reltol; h.abstol = o->abstol; h.fixed = o->fixed_dt;
+    OQ_CUDA(cudaMemcpyAsync(p->ctl.p, &h, sizeof(h), cudaMemcpyHostToDevice, p->stream));
+    // k1 = f(u0)
+    OQ_TRY(rhs_device(p, p->u.p, p->k[0].p));
+    OQ_CUDA(cudaStreamSynchronize(p->stream));
+
+    // host mirrors for snapshots
+    std::vector<std::vector<double>> hu(p->nparts), hdu(p->nparts);
+    std::vector<const double*> pu(p->nparts), pdu(p->nparts);
+    std::vector<double*> wu(p->nparts), wdu(p->nparts);
+    for (int i = 0; i < p->nparts; ++i) {
+        hu[i].resize(p->part_len[i] + 1); hdu[i].resize(p->part_len[i] + 1);
+        pu[i] = wu[i] = hu[i].data(); pdu[i] = wdu[i] = hdu[i].data();
+    }
+    auto snapshot = [&](double t, int64_t step) -> int {
+        if (!fn) return 0;
+        if (oq_state_get(p, wu.data())) return -1;
+        if (oq_state_get_du(p, wdu.data())) return -1;
+        return fn(user, t, step, pu.data(), pdu.data());
+    };
+    int stop = snapshot(t0, 0);
+    if (stop < 0) return 1;
+
+    // capture one step into a CUDA graph (all step-dependent scalars live in device memory)
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    OQ_CUDA(cudaStreamBeginCapture(p->stream, cudaStreamCaptureModeThreadLocal));
+    const int64_t launches_before = g_launches.load();
+    int rc = enqueue_step(p);
+    const int64_t per_step = g_launches.load() - launches_before;
+    cudaError_t ce = cudaStreamEndCapture(p->stream, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    OQ_CUDA(ce);
+    OQ_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+    g_launches.fetch_sub(per_step);   // capture enqueued nothing yet
+
+    const int64_t maxiters = o->maxiters > 0 ? o->maxiters : 1000000;
+    int64_t iters = 0;
+    while (!stop && !h.done && iters < maxiters) {
+        ce = cudaGraphLaunch(exec, p->stream);
+        if (ce != cudaSuccess) { rc = fail("cudaGraphLaunch: %s", cudaGetErrorString(ce)); break; }
+        g_launches.fetch_add(per_step);
+        ce = cudaMemcpyAsync(&h, p->ctl.p, sizeof(h), cudaMemcpyDeviceToHost, p->stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(p->stream);
+        if (ce != cudaSuccess) { rc = fail("step failed: %s", cudaGetErrorString(ce)); break; }
+        ++iters;
+        if (h.accepted && (h.naccept % stride == 0 || h.done)) {
+            stop = snapshot(h.t, h.naccept);
+            if (stop < 0) { rc = 1; break; }
+        }
+    }
+    unsigned long long eflag = 0;
+    cudaMemcpy(&eflag, p->epochs + kEpError, sizeof(eflag), cudaMemcpyDeviceToHost);
+    cudaGraphExecDestroy(exec);
+    cudaGraphDestroy(graph);
+    if (!rc && eflag) rc = fail("timed out waiting for a peer rank during the solve");
+    if (stats) {
+        stats->t = h.t; stats->dt_last = h.dt_last; stats->dt_next = h.dt;
+        stats->naccept = h.naccept; stats->nreject = h.nreject; stats->nrhs = h.nrhs + 1;
+        stats->retcode = h.retcode ? h.retcode : (h.done ? 0 : (iters >= maxiters ? 1 : 0));
+    }
+    return rc;
+}

@@ -1,0 +1,12 @@
+"""Import shim: the package directory is named `oetqf.jl_b200` (not a valid Python identifier), so this
+module loads it under the importable name `oetqf_b200` and replaces itself with it."""
+import importlib.util as _u
+import os as _os
+import sys as _sys
+
+_dir = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "oetqf.jl_b200")
+_spec = _u.spec_from_file_location("oetqf_b200", _os.path.join(_dir, "__init__.py"),
+                                   submodule_search_locations=[_dir])
+_mod = _u.module_from_spec(_spec)
+_sys.modules["oetqf_b200"] = _mod
+_spec.loader.exec_module(_mod)

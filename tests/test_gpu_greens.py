@@ -1,0 +1,163 @@
+"""GPU parity: Green's-function assembly through the C ABI vs the CPU oracle on the same inputs.
+Tolerance (BASELINE.json north_star): 1e-10 relative per entry; for cancellation-dominated entries the
+scale-aware form |Δ| <= 1e-10 * max|row| of SURVEY.md §7 is used and says so."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import workloads as W
+from helpers import meshes, rel_err, scaled_err
+from oracle import ref
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.mark.parametrize("dip,ftype", [(90.0, 0), (41.0, 0), (41.0, 1), (10.0, 1), (70.0, 0), (0.0, 1)])
+def test_dc3d_gradient_pointwise(gpu, dip, ftype):
+    oq = gpu
+    rng = np.random.default_rng(17)
+    n = 4000
+    x, y = rng.uniform(-12, 12, n), rng.uniform(-12, 12, n)
+    z = -rng.uniform(0.0, 10.0, n)
+    z[:50] = 0.0                                   # free surface
+    got = oq.dc3d_gradient(x, y, z, 0.6, 4.0, dip, -1.5, 2.5, -3.0, -0.5, ftype=ftype)
+    d = (1.0, 0.0, 0.0) if ftype == 0 else (0.0, 1.0, 0.0)
+    want = np.array([ref.dc3d(0.6, x[i], y[i], z[i], 4.0, dip, -1.5, 2.5, -3.0, -0.5, *d)[3:] for i in range(n)])
+    assert scaled_err(got, want, axis=1) < TOL      # relative to the largest gradient entry of that receiver
+
+
+def test_dc3d_singular_edges_and_kxi_ket(gpu):
+    """receivers on fault edges (zeros), on the extension lines of edges (KXI/KET branches of the closed
+    form) and above the surface: the product must take the same branches as the oracle"""
+    oq = gpu
+    pts = np.array([[0.3, 0.0, -3.0], [1.0, 0.0, -3.0], [0.3, 2.0, 0.5],        # edge, corner, above surface
+                    [-5.0, 0.0, -3.0], [3.0, 0.0, -5.0], [-1.0, 0.0, -9.0],      # extension lines (q = 0)
+                    [0.0, 1e-7, -3.5], [1.0 + 1e-7, 0.5, -4.0]])                 # inside the EPS snap distance
+    for ftype in (0, 1):
+        got = oq.dc3d_gradient(pts[:, 0], pts[:, 1], pts[:, 2], 0.6, 4.0, 90.0, -1, 1, -1, 1, ftype=ftype)
+        d = (1.0, 0.0, 0.0) if ftype == 0 else (0.0, 1.0, 0.0)
+        want = np.array([ref.dc3d(0.6, *p, 4.0, 90.0, -1, 1, -1, 1, *d)[3:] for p in pts])
+        assert np.all(got[:3] == 0.0) and np.all(want[:3] == 0.0)
+        assert scaled_err(got, want) < TOL
+
+
+@pytest.mark.parametrize("spec,ftype,nrept,br", [
+    (W.FaultSpec(100.0, 100.0, 10.0, 10.0, 41.0), 0, 2, 0.0),      # test/BEM/tests.jl:43
+    (W.FaultSpec(100.0, 100.0, 10.0, 10.0, 41.0), 1, 2, 0.0),
+    (W.C2_FAULT, 0, 2, 1.0),                                        # examples/otf-with-mantle.jl:18,43
+    (W.C1_FAULT, 0, 2, 1.0),                                        # BASELINE configs[0]
+    (W.FaultSpec(16e3, 8e3, 500.0, 500.0, 60.0), 1, 1, 0.5),
+    (W.FaultSpec(10.0, 10.0, 2.0, 2.0, 90.0), 0, 0, 1.0),           # test/BEM/tests.jl:64-65, no images
+])
+def test_fault_fault_kernel(gpu, spec, ftype, nrept, br):
+    oq = gpu
+    mf_o, mf_p = meshes(oq, spec)
+    want = ref.gf_fault_fault(mf_o, W.LAM, W.MU, ftype=ftype, nrept=nrept, buffer_ratio=br)
+    ft = oq.StrikeSlip() if ftype == 0 else oq.DipSlip()
+    got = oq.stress_greens_function(mf_p, W.LAM, W.MU, ftype=ft, fourier=False, nrept=nrept, buffer_ratio=br)
+    assert got.shape == want.shape
+    assert rel_err(got, want) < TOL                                 # plain per-entry relative error
+
+
+def test_fault_fault_golden(gpu):
+    oq = gpu
+    with open(os.path.join(GOLD, "okada_kernels.json")) as fh:
+        g = json.load(fh)
+    for case in g["cases"]:
+        mf = oq.gen_mesh("RectOkada", *case["fault"])
+        ft = oq.StrikeSlip() if case["ftype"] == 0 else oq.DipSlip()
+        st = oq.stress_greens_function(mf, g["lam"], g["mu"], ftype=ft, fourier=False, nrept=case["nrept"],
+                                       buffer_ratio=case["buffer_ratio"])
+        idx = np.array(case["index"])
+        assert rel_err(st[idx[:, 0], idx[:, 1], idx[:, 2]], case["values"]) < TOL
+
+
+def test_fault_fault_fourier_form(gpu):
+    """GF.jl:60-68: the default return is the strike-wise rFFT of the even extension"""
+    oq = gpu
+    mf_o, mf_p = meshes(oq, W.FaultSpec(100.0, 100.0, 10.0, 10.0, 41.0))
+    want = ref.gf_fault_fault(mf_o, W.LAM, W.MU, fourier=True)
+    got = oq.stress_greens_function(mf_p, W.LAM, W.MU)             # fourier=True is the reference default
+    assert got.dtype == np.complex128 and got.shape == want.shape
+    assert scaled_err(got, want) < TOL
+
+
+def test_dense_expansion_and_shards(gpu):
+    """test/BEM/tests.jl:46-49: G[(i,j),(k,l)] = st[|i-k|,j,l]; row shards tile the full matrix"""
+    oq = gpu
+    mf_o, mf_p = meshes(oq, W.FaultSpec(100.0, 100.0, 10.0, 10.0, 41.0))
+    want = ref.dense_from_toeplitz(ref.gf_fault_fault(mf_o, W.LAM, W.MU))
+    full = oq.device_fault_fault(mf_p, W.LAM, W.MU).to_host()
+    assert rel_err(full, want) < TOL
+    nf = mf_p.nx * mf_p.nxi
+    parts = [oq.device_fault_fault(mf_p, W.LAM, W.MU, rows=(a, b)).to_host()
+             for a, b in ((0, 37), (37, 37), (37, nf))]
+    assert np.array_equal(np.concatenate(parts, axis=0), full)
+
+
+@pytest.mark.parametrize("quad", ["Gauss1", "Gauss2"])
+@pytest.mark.parametrize("ftype", [0, 1])
+def test_fault_mantle(gpu, quad, ftype):
+    oq = gpu
+    mf_o, mf_p, ma_o, ma_p = meshes(oq, W.C2_FAULT, W.C2_BOX)      # KAT-3 geometry incl. the KET line
+    q = ref.gauss_quadrature(int(quad[-1]))
+    want = ref.gf_fault_mantle(mf_o, ma_o, W.LAM, W.MU, ftype=ftype, quad=q, nrept=2, buffer_ratio=1.0)
+    ft = oq.StrikeSlip() if ftype == 0 else oq.DipSlip()
+    got = oq.stress_greens_function(mf_p, ma_p, W.LAM, W.MU, ftype=ft, qtype=quad, nrept=2, buffer_ratio=1.0)
+    assert got.shape == (6 * 36, 32)
+    # per column (one source): relative to the largest stress that source produces anywhere
+    assert scaled_err(got, want, axis=0) < TOL
+    # user-supplied quadrature tuple (GF.jl:325-328)
+    got2 = oq.stress_greens_function(mf_p, ma_p, W.LAM, W.MU, ftype=ft, qtype=q, nrept=2, buffer_ratio=1.0)
+    assert np.array_equal(got, got2)
+
+
+def test_fault_mantle_kat3(gpu):
+    """SURVEY.md Appendix E KAT-3 (receiver on the singular line below a patch edge)"""
+    oq = gpu
+    _, mf_p, _, ma_p = meshes(oq, W.C2_FAULT, W.C2_BOX)
+    g = oq.stress_greens_function(mf_p, ma_p, W.LAM, W.MU, qtype="Gauss1", nrept=2, buffer_ratio=1.0)
+    ne = 36
+    e = int(np.argmin(np.abs(ma_p.cx + 30e3) + np.abs(ma_p.cy) + np.abs(ma_p.cz + 10315.789473684)))
+    col = 0 + 3 * mf_p.nx                                          # strike 1, dip 4 (1-based)
+    got = g[e + np.arange(6) * ne, col]
+    np.testing.assert_allclose(got, [0, -4.522721347572e+05, 0, 0, 1.453610392276e+05, 0], rtol=1e-9, atol=1e-3)
+
+
+def test_fault_mantle_element_shards(gpu):
+    oq = gpu
+    _, mf_p, _, ma_p = meshes(oq, W.C2_FAULT, W.C2_BOX)
+    full = oq.device_fault_mantle(mf_p, ma_p, W.LAM, W.MU, buffer_ratio=1.0).to_host()
+    ne = 36
+    got = np.zeros_like(full)
+    for e0, e1 in ((0, 10), (10, 36)):
+        part = oq.device_fault_mantle(mf_p, ma_p, W.LAM, W.MU, buffer_ratio=1.0, elems=(e0, e1)).to_host()
+        nel = e1 - e0
+        for k in range(6):
+            got[k * ne + e0: k * ne + e1] = part[k * nel: (k + 1) * nel]
+    assert np.array_equal(got, full)
+
+
+def test_matrix_roundtrip_and_gemv(gpu):
+    """the matvecmul! slot (pref.jl:15-21; equation.jl:201-203): 3-argument and α=β=true forms"""
+    oq = gpu
+    rng = np.random.default_rng(9)
+    for m, n in ((50, 144), (144, 50), (1030, 2100), (7, 5000)):
+        A = np.asfortranarray(rng.standard_normal((m, n)))
+        x, y0 = rng.standard_normal(n), rng.standard_normal(m)
+        d = oq.device_from_host(A)
+        assert np.array_equal(d.to_host(), A)
+        want = ref.gemv(A, x)
+        got = d.gemv(x)
+        scale = np.abs(A) @ np.abs(x)
+        assert np.max(np.abs(got - want) / scale) < 1e-14
+        y = y0.copy()
+        oq.matvecmul(y, d, x, True, True)
+        assert np.max(np.abs(y - (y0 + want)) / (scale + np.abs(y0))) < 1e-14
+        r0, r1 = m // 3, m - 1
+        part = oq.device_from_host(A, rows=(r0, r1))
+        assert np.array_equal(part.gemv(x), got[r0:r1])

@@ -1,0 +1,178 @@
+"""GPU parity: the ODE right-hand side through the C ABI vs the CPU oracle (1e-10 relative per component,
+BASELINE.json north_star) and the reference's own FFT == dense test (test/BEM/tests.jl:39-61)."""
+import numpy as np
+import pytest
+
+import workloads as W
+from helpers import meshes, scaled_err
+from oracle import ref
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def _fault_setup(oq, spec, seed=42):
+    mf_o, mf_p = meshes(oq, spec)
+    a, b, L, sig = W.fault_properties(mf_o.x, mf_o.z, mf_o.nx, mf_o.nxi)
+    rng = np.random.default_rng(seed)
+    v, th, dl = W.initial_state(mf_o.nx, mf_o.nxi, L, rng=rng)
+    v = v * (1 + 0.3 * rng.uniform(-1, 1, v.shape))
+    pf_o = ref.FaultProp(a, b, L, sig, W.ETA, W.VPL, W.F0, W.V0)
+    pf_p = oq.RateStateQuasiDynamicProperty(a, b, L, sig, W.ETA, W.VPL, W.F0, W.V0)
+    return mf_o, mf_p, pf_o, pf_p, v, th, dl
+
+
+def _close(got, want, tol=TOL):
+    """per-component relative error, with the field's max as the floor for components crossing zero"""
+    got, want = np.asarray(got), np.asarray(want)
+    den = np.maximum(np.abs(want), 1e-6 * np.max(np.abs(want)))
+    return float(np.max(np.abs(got - want) / den)) < tol
+
+
+@pytest.mark.parametrize("form", ["dense", "fft"])
+@pytest.mark.parametrize("spec", [W.C1_FAULT, W.FaultSpec(100.0, 100.0, 10.0, 10.0, 41.0)])
+def test_rhs_fault_only(gpu, spec, form):
+    oq = gpu
+    mf_o, mf_p, pf_o, pf_p, v, th, dl = _fault_setup(oq, spec)
+    st = ref.gf_fault_fault(mf_o, W.LAM, W.MU, buffer_ratio=1.0)
+    want = ref.rhs_fault(pf_o, st, v, th, form="toeplitz")
+    want_fft = ref.rhs_fault(pf_o, ref.gf_fourier(st), v, th, form="fft")    # the reference's own algorithm
+    gf = oq.stress_greens_function(mf_p, W.LAM, W.MU, buffer_ratio=1.0)     # Fourier form, as the reference passes it
+    u0 = oq.ArrayPartition(v, th, dl)
+    prob = oq.assemble(gf, pf_p, u0, (0.0, 1.0), gf11_form=form)
+    du = u0.similar()
+    prob.f(du, u0, prob.p, 1.0)
+    for g, w, wf in zip(du.x, want, want_fft):
+        assert _close(g, w)
+        assert _close(g, wf, 1e-8)          # FFT round-off of the CPU path itself (rtol sqrt(eps) in the reference test)
+
+
+def test_fft_conv_equals_dense_reference_test(gpu):
+    """test/BEM/tests.jl:39-61 on the device: Toeplitz-form dτ/dt == dense contraction, both slip types"""
+    oq = gpu
+    spec = W.FaultSpec(100.0, 100.0, 10.0, 10.0, 41.0)
+    mf_o, mf_p, pf_o, pf_p, v, th, dl = _fault_setup(oq, spec, seed=1)
+    for ft in (oq.StrikeSlip(), oq.DipSlip()):
+        gf = oq.stress_greens_function(mf_p, W.LAM, W.MU, ftype=ft)
+        u0 = oq.ArrayPartition(v, th, dl)
+        outs = []
+        for form in ("dense", "fft"):
+            prob = oq.assemble(gf, pf_p, u0, (0.0, 1.0), gf11_form=form)
+            du = u0.similar()
+            prob.f(du, u0, prob.p, 0.0)
+            outs.append(du.x[0].copy())
+        assert _close(outs[0], outs[1], 1e-12)
+
+
+def test_rhs_dilatancy(gpu):
+    """equation.jl:168-183, 248-276 with positive random properties (test/BEM/tests.jl:73-82 shapes)"""
+    oq = gpu
+    spec = W.FaultSpec(10.0, 10.0, 2.0, 2.0, 90.0)
+    mf_o, mf_p = meshes(oq, spec)
+    rng = np.random.default_rng(4)
+    shp = (mf_o.nx, mf_o.nxi)
+    a, b, L, sig = (rng.uniform(0.5, 1.5, shp) for _ in range(4))
+    tp, ed, be, p0 = (rng.uniform(0.5, 1.5, shp) for _ in range(4))
+    v, th, dl, pr = (rng.uniform(0.5, 1.5, shp) for _ in range(4))
+    pr *= 0.1
+    st = ref.gf_fault_fault(mf_o, 1.0, 1.0, buffer_ratio=1.0)
+    pf_o = ref.FaultProp(a, b, L, sig, 0.7, 0.3, 0.6, 0.9)
+    want = ref.rhs_fault_dilatancy(pf_o, ref.DilatancyProp(tp, ed, be, p0), st, v, th, pr, form="toeplitz")
+    pf_p = oq.RateStateQuasiDynamicProperty(a, b, L, sig, 0.7, 0.3, 0.6, 0.9)
+    dila = oq.DilatancyProperty(tp, ed, be, p0)
+    gf = oq.stress_greens_function(mf_p, 1.0, 1.0, buffer_ratio=1.0)
+    u0 = oq.ArrayPartition(v, th, dl, pr)
+    for form in ("dense", "fft"):
+        prob = oq.assemble(gf, pf_p, dila, u0, (0.0, 1.0), gf11_form=form)
+        du = u0.similar()
+        prob.f(du, u0, prob.p, 1.0)
+        dv, dth, ddl, dpr = want
+        for g, w in zip(du.x, (dv, dth, ddl, dpr)):
+            assert _close(g, w)
+
+
+@pytest.mark.parametrize("nlaws", [1, 2])
+def test_rhs_viscoelastic_machinery(gpu, nlaws):
+    """equation.jl:185-205 with the Okada-built gf11/gf12 and random gf21/gf22 (isolates the RHS machinery
+    from the hex8 closed form); power-law and composite viscosity"""
+    oq = gpu
+    mf_o, mf_p, ma_o, ma_p = meshes(oq, W.C2_FAULT, W.C2_BOX)
+    a, b, L, sig = W.fault_properties(mf_o.x, mf_o.z, mf_o.nx, mf_o.nxi)
+    g, n, d0 = W.mantle_properties(ma_o.cz)
+    rng = np.random.default_rng(8)
+    v, th, eps, sg, dl = W.initial_state(mf_o.nx, mf_o.nxi, L, ma_o.cz, g, n, rng=rng)
+    sg = sg * (1 + 0.2 * rng.uniform(-1, 1, sg.shape))
+    nf, ne = 32, 36
+    st = ref.gf_fault_fault(mf_o, W.LAM, W.MU, buffer_ratio=1.0)
+    gf12 = ref.gf_fault_mantle(mf_o, ma_o, W.LAM, W.MU, buffer_ratio=1.0)
+    gf21 = np.asfortranarray(rng.standard_normal((nf, 6 * ne)) * 1e9)
+    gf22 = np.asfortranarray(rng.standard_normal((6 * ne, 6 * ne)) * 1e9)
+    gam = np.stack([g * (1 + 0.1 * l) for l in range(nlaws)])
+    npw = np.stack([n - 0.5 * l for l in range(nlaws)])
+    pa_o = ref.MantleProp(gam, npw, d0)
+    pf_o = ref.FaultProp(a, b, L, sig, W.ETA, W.VPL, W.F0, W.V0)
+    want = ref.rhs_viscoelastic(pf_o, pa_o, st, gf12, gf21, gf22, v, th, sg, form="toeplitz")
+    pf_p = oq.RateStateQuasiDynamicProperty(a, b, L, sig, W.ETA, W.VPL, W.F0, W.V0)
+    laws = [oq.PowerLawViscosityProperty(gam[l], npw[l], d0) for l in range(nlaws)]
+    pa_p = laws[0] if nlaws == 1 else oq.CompositePowerLawViscosityProperty(laws, d0)
+    u0 = oq.ArrayPartition(v, th, eps, sg, dl)
+    gf11 = oq.stress_greens_function(mf_p, W.LAM, W.MU, buffer_ratio=1.0)
+    gf12p = oq.stress_greens_function(mf_p, ma_p, W.LAM, W.MU, buffer_ratio=1.0)
+    for form in ("dense", "fft"):
+        prob = oq.assemble(gf11, gf12p, gf21, gf22, pf_p, pa_p, u0, (0.0, 1.0), gf11_form=form)
+        du = u0.similar()
+        prob.f(du, u0, prob.p, 0.0)
+        for gt, w in zip(du.x, want):
+            assert gt.shape == w.shape
+            assert _close(gt, w), form
+    # resident mode gives the same derivative
+    prob.p.set_state(u0.x)
+    prob.p.rhs_resident(1)
+    du2 = u0.similar()
+    prob.p.get_du(du2.x)
+    for a_, b_ in zip(du.x, du2.x):
+        assert np.array_equal(a_, b_)
+
+
+def test_rhs_is_deterministic_and_rearms(gpu):
+    """the split-row partial sums are combined in a fixed order: bitwise repeatable across evaluations"""
+    oq = gpu
+    mf_o, mf_p, pf_o, pf_p, v, th, dl = _fault_setup(oq, W.C1_FAULT)
+    gf = oq.stress_greens_function(mf_p, W.LAM, W.MU, buffer_ratio=1.0)
+    u0 = oq.ArrayPartition(v, th, dl)
+    prob = oq.assemble(gf, pf_p, u0, (0.0, 1.0))
+    outs = []
+    for _ in range(3):
+        du = u0.similar()
+        prob.f(du, u0, prob.p, 0.0)
+        outs.append(du.x[0].copy())
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[1], outs[2])
+
+
+def test_rhs_large_linearity(gpu):
+    """BASELINE configs[2] size (256x64, 2.1 GB dense matrix): size-independent properties instead of the
+    oracle -- dense form == Toeplitz form, and linearity of dτ/dt in (v - vpl)."""
+    oq = gpu
+    mf_o, mf_p, pf_o, pf_p, v, th, dl = _fault_setup(oq, W.C3_FAULT)
+    gf = oq.stress_greens_function(mf_p, W.LAM, W.MU, buffer_ratio=1.0, fourier=False)
+    u0 = oq.ArrayPartition(v, th, dl)
+    res = {}
+    for form in ("dense", "fft"):
+        prob = oq.assemble(gf, pf_p, u0, (0.0, 1.0), gf11_form=form)
+        du = u0.similar()
+        prob.f(du, u0, prob.p, 0.0)
+        res[form] = [x.copy() for x in du.x]
+        prob.p.free()
+    for a_, b_ in zip(res["dense"], res["fft"]):
+        assert _close(a_, b_, 1e-11)
+    # spot-check 64 rows against the oracle's Toeplitz contraction
+    st_o = np.asfortranarray(gf)
+    relv = v - W.VPL
+    rows = np.random.default_rng(0).integers(0, v.size, 64)
+    dtau = np.array([sum(st_o[np.abs(i - np.arange(mf_o.nx)), j, l] @ relv[:, l] for l in range(mf_o.nxi))
+                     for i, j in zip(rows % mf_o.nx, rows // mf_o.nx)])
+    # (the pointwise law is covered at small sizes; here the matvec itself is checked)
+    prob = oq.assemble(gf, pf_p, u0, (0.0, 1.0), gf11_form="dense")
+    G = prob.p._keep[0]
+    y = G.gemv(relv.reshape(-1, order="F"))
+    assert _close(y[rows], dtau, 1e-11)

@@ -1,0 +1,112 @@
+"""GPU parity: the device-resident Tsit5 integrator vs the CPU oracle integrator driving the CPU oracle RHS.
+BASELINE.json north_star: slip-rate and state time series within 1e-6 relative over a fixed window before
+the first instability."""
+import numpy as np
+import pytest
+
+import workloads as W
+from helpers import meshes
+from oracle import integrator, ref
+
+pytestmark = pytest.mark.gpu
+
+
+def _pack(parts):
+    return np.concatenate([np.asarray(p).reshape(-1, order="F") for p in parts])
+
+
+def _unpack(u, shapes):
+    out, off = [], 0
+    for s in shapes:
+        n = int(np.prod(s))
+        out.append(u[off:off + n].reshape(s, order="F"))
+        off += n
+    return out
+
+
+def test_decay_problem_matches_analytic_and_oracle(gpu):
+    """the integrator alone, on the linear test problem of the reference's HDF5 test (test/tests.jl:2-7):
+    a fault-only problem with zero Green's function has dθ/dt = 1 - vθ/L, dδ/dt = v, dv/dt = -(...)"""
+    oq = gpu
+    nx, nxi = 4, 3
+    rng = np.random.default_rng(0)
+    a, b, L, sig = (rng.uniform(0.5, 1.5, (nx, nxi)) for _ in range(4))
+    v, th, dl = (rng.uniform(0.5, 1.5, (nx, nxi)) for _ in range(3))
+    st = np.zeros((nx, nxi, nxi), order="F")
+    pf_p = oq.RateStateQuasiDynamicProperty(a, b, L, sig, 0.7, 0.3, 0.6, 0.9)
+    pf_o = ref.FaultProp(a, b, L, sig, 0.7, 0.3, 0.6, 0.9)
+    u0 = oq.ArrayPartition(v, th, dl)
+    shapes = [x.shape for x in u0.x]
+
+    def f(u):
+        vv, tt, _ = _unpack(u, shapes)
+        return _pack(ref.rhs_fault(pf_o, st, vv, tt, form="toeplitz"))
+
+    for form in ("dense", "fft"):
+        prob = oq.assemble(st, pf_p, u0, (0.0, 2.0), gf11_form=form)
+        sol = oq.solve(prob, oq.Tsit5(), reltol=1e-8, abstol=1e-10, dt=1e-3)
+        ts, us, stats = integrator.tsit5(f, _pack(u0.x), 0.0, 2.0, reltol=1e-8, abstol=1e-10, dt0=1e-3)
+        assert sol.retcode == "Success"
+        assert sol.stats["naccept"] == stats["naccept"] and sol.stats["nreject"] == stats["nreject"]
+        np.testing.assert_allclose(sol.t, ts, rtol=1e-10)
+        for k in (len(ts) // 2, len(ts) - 1):
+            np.testing.assert_allclose(_pack(sol.u[k].x), us[k], rtol=1e-9)
+        assert sol.t[-1] == 2.0
+
+
+def test_fault_cycle_window_matches_oracle(gpu):
+    """BASELINE configs[0]-like fault (32x16), aging law, adaptive Tsit5 over a fixed window: v and θ series
+    within 1e-6 relative of the CPU oracle at every accepted step"""
+    oq = gpu
+    spec = W.C1_FAULT
+    mf_o, mf_p = meshes(oq, spec)
+    a, b, L, sig = W.fault_properties(mf_o.x, mf_o.z, mf_o.nx, mf_o.nxi)
+    v, th, dl = W.initial_state(mf_o.nx, mf_o.nxi, L)
+    st = ref.gf_fault_fault(mf_o, W.LAM, W.MU, buffer_ratio=1.0)
+    pf_o = ref.FaultProp(a, b, L, sig, W.ETA, W.VPL, W.F0, W.V0)
+    pf_p = oq.RateStateQuasiDynamicProperty(a, b, L, sig, W.ETA, W.VPL, W.F0, W.V0)
+    u0 = oq.ArrayPartition(v, th, dl)
+    shapes = [x.shape for x in u0.x]
+    tstop = 0.02 * W.YEAR
+
+    def f(u):
+        vv, tt, _ = _unpack(u, shapes)
+        return _pack(ref.rhs_fault(pf_o, st, vv, tt, form="toeplitz"))
+
+    ts, us, stats = integrator.tsit5(f, _pack(u0.x), 0.0, tstop, reltol=1e-8, abstol=1e-10, dt0=1e-6,
+                                     dtmax=0.2 * W.YEAR)
+    gf = oq.stress_greens_function(mf_p, W.LAM, W.MU, buffer_ratio=1.0, fourier=False)
+    prob = oq.assemble(gf, pf_p, u0, (0.0, tstop), gf11_form="dense")
+    sol = oq.solve(prob, oq.Tsit5(), reltol=1e-8, abstol=1e-10, dt=1e-6, dtmax=0.2 * W.YEAR)
+    assert sol.retcode == "Success" and len(sol.t) == len(ts)
+    np.testing.assert_allclose(sol.t, ts, rtol=1e-9)
+    n = v.size
+    worst_v = worst_th = 0.0
+    for k in range(len(ts)):
+        uk = _pack(sol.u[k].x)
+        worst_v = max(worst_v, np.max(np.abs(uk[:n] - us[k][:n]) / np.abs(us[k][:n])))
+        worst_th = max(worst_th, np.max(np.abs(uk[n:2 * n] - us[k][n:2 * n]) / np.abs(us[k][n:2 * n])))
+    assert worst_v < 1e-6 and worst_th < 1e-6, (worst_v, worst_th)
+
+
+def test_stride_and_callback(gpu):
+    """wsolve's saving cadence (src/io.jl:51-58, test/tests.jl:34-41): every stride-th accepted step + t0"""
+    oq = gpu
+    nx, nxi = 4, 3
+    rng = np.random.default_rng(1)
+    a, b, L, sig = (rng.uniform(0.5, 1.5, (nx, nxi)) for _ in range(4))
+    v, th, dl = (rng.uniform(0.5, 1.5, (nx, nxi)) for _ in range(3))
+    st = np.zeros((nx, nxi, nxi), order="F")
+    pf_p = oq.RateStateQuasiDynamicProperty(a, b, L, sig, 0.7, 0.3, 0.6, 0.9)
+    u0 = oq.ArrayPartition(v, th, dl)
+    prob = oq.assemble(st, pf_p, u0, (0.0, 2.0))
+    full = oq.solve(prob, oq.Tsit5(), reltol=1e-8, abstol=1e-10, dt=1e-3)
+    seen = []
+    strided = oq.solve(prob, oq.Tsit5(), reltol=1e-8, abstol=1e-10, dt=1e-3, stride=11,
+                       callback=lambda u, t, step, du: seen.append((t, step)) and False)
+    nt = len(full.t)
+    want = [full.t[i] for i in range(0, nt, 11)]
+    if (nt - 1) % 11 != 0:
+        want.append(full.t[-1])            # the final state is always delivered
+    np.testing.assert_allclose([s[0] for s in seen], want, rtol=0)
+    assert np.array_equal(strided.u[0].x[0], full.u[0].x[0])

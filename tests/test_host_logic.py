@@ -1,0 +1,106 @@
+"""CPU-only tests of the host-side mirror (mesh generators, quadrature, property checks, backend slot),
+following the reference's own unit tests where they exist."""
+import numpy as np
+import pytest
+
+import workloads as W
+from oracle import ref
+
+
+def test_rect_okada_mesh(oq):
+    """test/BEM/tests.jl:5-13"""
+    m = oq.gen_mesh("RectOkada", 100.0, 50.0, 2.0, 2.0, 33.0)
+    assert m.nx == 50 and m.nxi == 25
+    assert m.axi[-1][0] == m.xi[-1] - m.dxi / 2
+    sd, cd = ref.sincosd(33.0)
+    assert m.y[-1] == m.xi[-1] * cd and m.z[-1] == m.xi[-1] * sd
+    assert m.x[-1] - m.x[0] == m.dx * (m.nx - 1)
+    o = ref.fault_mesh(100.0, 50.0, 2.0, 2.0, 33.0)
+    for a, b in [(m.x, o.x), (m.y, o.y), (m.z, o.z), (m.ax, o.ax), (m.axi, o.axi)]:
+        assert np.array_equal(a, b)
+
+
+def test_hex8_box_conventions(oq):
+    """test/BEM/tests.jl:15-36 (q-point convention and bounding box)"""
+    rng = np.random.default_rng(5)
+    llx, lly, llz = rng.random(3)
+    dx, dy, dz = rng.random(3) * 5
+    nx, ny, nz = (int(v) for v in rng.integers(2, 10, 3))
+    me = oq.gen_mesh("BEMHex8Mesh", llx, lly, llz, dx, dy, -dz, nx, ny, nz)
+    for arr, n in ((me.cx, nx), (me.cy, ny), (me.cz, nz)):
+        assert len(np.unique(np.round(arr, 6))) == n
+    np.testing.assert_allclose(me.cx, me.qx)
+    np.testing.assert_allclose(me.cy - me.dy / 2, me.qy)
+    np.testing.assert_allclose(me.cz + me.dz / 2, me.qz)
+    np.testing.assert_allclose(np.max(me.cx + me.dx / 2), llx + dx)
+    np.testing.assert_allclose(np.min(me.cx - me.dx / 2), llx)
+    np.testing.assert_allclose(np.max(me.cy + me.dy / 2), lly + dy)
+    np.testing.assert_allclose(np.min(me.cy - me.dy / 2), lly)
+    np.testing.assert_allclose(np.max(me.cz + me.dz / 2), llz)
+    np.testing.assert_allclose(np.min(me.cz - me.dz / 2), llz - dz)
+    o = ref.hex8_box(llx, lly, llz, dx, dy, -dz, nx, ny, nz)
+    for k in ("cx", "cy", "cz", "qx", "qy", "qz", "dx", "dy", "dz"):
+        np.testing.assert_array_equal(getattr(me, k), getattr(o, k))
+
+
+def test_example_box_layers(oq):
+    """examples/otf-with-mantle.jl:25-28: layer fractions normalize(cumsum(cumprod(1.5*ones(3))), Inf)"""
+    me = oq.gen_mesh("BEMHex8Mesh", *W.C2_BOX.args())
+    assert len(me) == 36
+    tops = np.unique(np.round(me.cz + me.dz / 2, 6))[::-1]
+    np.testing.assert_allclose(tops, -8e3 - 22e3 * np.array([0.0, 1.5 / 7.125, 3.75 / 7.125]))
+
+
+def test_quadrature(oq):
+    c, w = oq.get_quadrature("Gauss1")
+    assert np.array_equal(c, [0, 0, 0]) and np.array_equal(w, [1.0])
+    c, w = oq.get_quadrature("Gauss2")
+    assert w.size == 8 and abs(w.sum() - 1) < 1e-15 and np.allclose(np.abs(c), 1 / np.sqrt(3))
+    with pytest.raises(AssertionError, match="Wrong format of quadrature!"):     # GF.jl:326
+        oq.get_quadrature((np.zeros(5), np.ones(2)))
+    co, wo = ref.gauss_quadrature(3)
+    c, w = oq.get_quadrature("Gauss3")
+    np.testing.assert_array_equal(c, co)
+    np.testing.assert_array_equal(w, wo)
+
+
+def test_property_asserts(oq):
+    """property.jl:20-24,39-40,47"""
+    z = np.ones((3, 2))
+    oq.RateStateQuasiDynamicProperty(z, z, z, z, 1.0, 1.0)
+    with pytest.raises(AssertionError):
+        oq.RateStateQuasiDynamicProperty(z, z, z, np.ones((2, 2)), 1.0, 1.0)
+    with pytest.raises(AssertionError):
+        oq.RateStateQuasiDynamicProperty(z, z, z, z, -1.0, 1.0)
+    with pytest.raises(AssertionError):
+        oq.PowerLawViscosityProperty(np.ones(3), np.ones(3), np.ones(5))
+    with pytest.raises(AssertionError):
+        oq.PowerLawViscosityProperty(np.ones(3), np.ones(2), np.ones(6))
+
+
+def test_gemv_backend_setting(oq):
+    """test/tests.jl:60-64 restated for the single B200 backend"""
+    assert oq.get_matvecmul() == "B200"
+    oq.set_matvecmul("B200")
+    with pytest.raises(ValueError):
+        oq.set_matvecmul("DummyMatVec")
+
+
+def test_buffer_ratio_assert(oq):
+    mf = oq.gen_mesh("RectOkada", 10.0, 10.0, 2.0, 2.0, 90.0)
+    with pytest.raises(AssertionError, match="buffer_ratio"):                   # GF.jl:36
+        oq.stress_greens_function(mf, 1.0, 1.0, buffer_ratio=-1.0)
+
+
+def test_workload_shapes():
+    assert (W.C1_FAULT.nx, W.C1_FAULT.nxi) == (32, 16)
+    assert (W.C2_FAULT.nx, W.C2_FAULT.nxi, W.C2_BOX.n) == (8, 4, 36)
+    assert (W.C3_FAULT.nx, W.C3_FAULT.nxi) == (256, 64)
+    mf = ref.fault_mesh(W.C2_FAULT.x, W.C2_FAULT.xi, W.C2_FAULT.dx, W.C2_FAULT.dxi, 90.0)
+    a, b, L, s = W.fault_properties(mf.x, mf.z, mf.nx, mf.nxi)
+    assert (b > a).sum() > 0 and (b < a).sum() > 0          # both VW and VS cells exist
+    ma = ref.hex8_box(*W.C2_BOX.args())
+    g, n, d0 = W.mantle_properties(ma.cz)
+    v, th, eps, sig, dl = W.initial_state(mf.nx, mf.nxi, L, ma.cz, g, n)
+    rel = g * (np.sqrt(2) * np.abs(sig[:, 1])) ** n * sig[:, 1]
+    np.testing.assert_allclose(rel, d0[1], rtol=1e-10)       # examples/otf-with-mantle.jl:147-148
