@@ -32,6 +32,37 @@ def okada():
         json.dump(dict(lam=3e10, mu=3e10, cases=cases), fh, indent=1)
 
 
+def hex8():
+    """Values from the QUADRATURE oracle (oracle/hex8_numeric.py, 64-point Gauss-Legendre per face axis):
+    independent of the closed form they pin."""
+    from oracle import hex8_numeric as hn
+    rng = np.random.default_rng(77)
+    cases = []
+    # App. B geometry of SURVEY.md plus random cuboids; receivers at centroid-like distances
+    geoms = [(0.0, 0.0, -1.0, 2.0, 2.0, 2.0)] + [
+        (rng.uniform(-2, 2), rng.uniform(-2, 2), -rng.uniform(0.2, 3), *rng.uniform(0.5, 3, 3)) for _ in range(5)]
+    for g in geoms:
+        qx, qy, qz, dx, dy, dz = g
+        c = np.array([qx, qy + dy / 2, qz - dz / 2])
+        pts = [c,                                         # self (inside)
+               c + np.array([dx, 0, 0]), c + np.array([0, -dy, 0]), c + np.array([0, 0, -dz]),   # neighbours
+               c + np.array([3 * dx, -2 * dy, 0.0]),
+               np.array([c[0] + 2.5 * dx, c[1] + 1.5 * dy, 0.0]),                           # on the free surface
+               np.array([c[0] - 4.0, c[1] + 5.0, max(c[2], -0.1 - dz) * 0.3])]
+        lam, mu = rng.uniform(0.5, 2), rng.uniform(0.5, 2)
+        nu = lam / 2 / (lam + mu)
+        eps = rng.uniform(-1, 1, 6)
+        for p in pts:
+            if p[2] > 0:
+                continue
+            s = hn.stress_vol_hex8(*p, qx, qy, qz, dx, dy, dz, eps, mu, nu, nquad=64)
+            cases.append(dict(point=[float(v) for v in p], geom=[float(v) for v in g], mu=mu, nu=nu,
+                              eps=[float(v) for v in eps], sigma=[float(v) for v in s]))
+    with open(os.path.join(HERE, "hex8_quadrature.json"), "w") as fh:
+        json.dump(dict(cases=cases), fh, indent=1)
+
+
 if __name__ == "__main__":
     okada()
+    hex8()
     print("wrote", os.listdir(HERE))
