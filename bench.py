@@ -1,0 +1,406 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 hot path (contract: see the task statement / DESIGN.md §6).
+
+Workload (config.workload): BASELINE.json configs[2], "fault-only synthetic 256x64 mesh (16k elements), dense
+Green's matvec RHS" -- the configuration the metric's 1/2/4/8-GPU scaling is quoted on and the largest RHS
+config that fits one GPU.  A step = ONE evaluation of the ODE right-hand side (equation.jl:156-166) on the
+resident state: forcing kernel + fused dense matvec with the rate-and-state epilogue.  The fp64 Green's matrix
+(2.15 GB) is far larger than the 126 MB L2, so every step streams it from HBM (no L2 flush needed).
+
+  value        RHS evaluations / s, state and matrix resident in HBM (device-timed, max over ranks)
+  e2e          the same through the reference-facing call prob.f(du, u, p, t) with HOST buffers (pinned):
+               H2D of u and D2H of du inside the timed region
+  roofline     the fused matvec kernel: algorithmic bytes / its CUDA-event time vs the measured HBM copy peak
+  cpu_baseline the oracle port of the reference's own CPU algorithm (FFT form of equation.jl:44-61, OpenMP +
+               pocketfft) on this box's host cores, bounded sample
+  extra        Green's assembly throughput (entries/s, fp64 pipe fraction) and the example config
+
+N > 1 (torchrun): the matrix is row-sharded (strong scaling); every RHS all-gathers v - vpl through peer stores
+over NVLink (comm.cu).  `--impl reference` times the CPU port alone (rank 0 only).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import workloads as W  # noqa: E402
+
+METRIC = "rhs_evals_per_s"
+UNIT = "evals/s"
+WORKLOAD = "BASELINE configs[2]: fault-only 256x64 (16384 cells), dense fp64 Green's matvec RHS, aging law"
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            d = json.load(fh)
+        return float(d["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    return 6650.0, "B200_PROFILING.md fallback (of fallback)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                 parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_fault_problem(oq, fs, rows, rng_seed=42):
+    mf = oq.gen_mesh("RectOkada", fs.x, fs.xi, fs.dx, fs.dxi, fs.dip)
+    a, b, L, sig = W.fault_properties(mf.x, mf.z, mf.nx, mf.nxi)
+    v, th, dl = W.initial_state(mf.nx, mf.nxi, L, rng=np.random.default_rng(rng_seed))
+    pf = oq.RateStateQuasiDynamicProperty(a, b, L, sig, W.ETA, W.VPL, W.F0, W.V0)
+    g11 = oq.device_fault_fault(mf, W.LAM, W.MU, buffer_ratio=1.0, rows=rows)
+    u0 = oq.ArrayPartition(v, th, dl)
+    prob = oq.assemble(g11, pf, u0, (0.0, 1.0))
+    return mf, prob, u0
+
+
+def local_slices(u0, r0, r1):
+    return [np.ascontiguousarray(a.reshape(-1, order="F")[r0:r1]) for a in u0.x]
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def cpu_reference(fs, budget_s=12.0, steps=None, warmup=1):
+    """The reference's own CPU algorithm for this path, restated (oracle port): FFT form of the fault-fault
+    interaction (equation.jl:44-61) + update_fault! (equation.jl:233-246), all host threads."""
+    from oracle import ref
+    mf = ref.fault_mesh(fs.x, fs.xi, fs.dx, fs.dxi, fs.dip)
+    a, b, L, sig = W.fault_properties(mf.x, mf.z, mf.nx, mf.nxi)
+    v, th, _ = W.initial_state(mf.nx, mf.nxi, L, rng=np.random.default_rng(42))
+    pf = ref.FaultProp(a, b, L, sig, W.ETA, W.VPL, W.F0, W.V0)
+    t0 = time.perf_counter()
+    # Green's kernel: a bounded sample of source rows (the full 256x64 kernel is 5.2 M dc3d calls)
+    nsrc = min(mf.nxi, 8)
+    sub = ref.FaultMesh(mf.x, mf.dx, mf.nx, mf.ax, mf.xi[:nsrc], mf.dxi, nsrc, mf.axi[:nsrc], mf.y[:nsrc],
+                        mf.z[:nsrc], mf.dep, mf.dip)
+    ta = time.perf_counter()
+    st_sub = ref.gf_fault_fault(sub, W.LAM, W.MU, buffer_ratio=1.0)
+    asm_s = time.perf_counter() - ta
+    asm_entries_per_s = st_sub.size / asm_s
+    # RHS timing needs a kernel of the full shape; its values do not affect the time
+    rng = np.random.default_rng(0)
+    st = np.asfortranarray(rng.standard_normal((mf.nx, mf.nxi, mf.nxi)) * 1e6)
+    gf = ref.gf_fourier(st)
+    for _ in range(max(1, warmup)):
+        ref.rhs_fault(pf, gf, v, th, form="fft")
+    n, t1 = 0, time.perf_counter()
+    while True:
+        ref.rhs_fault(pf, gf, v, th, form="fft")
+        n += 1
+        el = time.perf_counter() - t1
+        if (steps is not None and n >= steps) or (steps is None and el > budget_s):
+            break
+    fft_evals = n / el
+    # dense form of the same RHS on a bounded row sample (the full dense matrix is 2.1 GB)
+    nf = mf.nx * mf.nxi
+    rows = min(nf, 2048)
+    A = np.asfortranarray(rng.standard_normal((rows, nf)))
+    x = rng.standard_normal(nf)
+    ref.gemv(A, x)
+    m, t2 = 0, time.perf_counter()
+    while time.perf_counter() - t2 < 2.0:
+        ref.gemv(A, x)
+        m += 1
+    dense_s_per_eval = (time.perf_counter() - t2) / m * (nf / rows)
+    return dict(value=fft_evals, unit=UNIT, cores=ref.num_threads(), kind="port",
+                sample=f"{n} FFT-form RHS evaluations of the full 256x64 problem in {el:.1f} s "
+                       f"(reference algorithm, equation.jl:44-61); dense form extrapolated from a {rows}-row gemv",
+                dense_form_evals_per_s=1.0 / dense_s_per_eval,
+                okada_assembly_entries_per_s=asm_entries_per_s, wall_s=time.perf_counter() - t0), el / n
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    fs = W.C3_FAULT
+    base, s_per = cpu_reference(fs, steps=max(1, args.steps), warmup=max(1, args.warmup))
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * s_per, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "reference_algorithm": "FFT/Toeplitz form (equation.jl:44-61), CPU port"},
+            "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------ extras
+def assembly_extras(oq, fp64_peak):
+    """Green's assembly throughput: entries/s and executed-fp64 fraction (flop counts from profiles/, ncu)."""
+    from oetqf_b200 import gf as gfmod
+    out = {}
+    fs = W.C3_FAULT
+    mf = oq.gen_mesh("RectOkada", fs.x, fs.xi, fs.dx, fs.dxi, fs.dip)
+    best = None
+    for _ in range(4):
+        st = oq.stress_greens_function(mf, W.LAM, W.MU, buffer_ratio=1.0, fourier=False)
+        ms = gfmod.last_kernel_ms["value"]
+        best = ms if best is None else min(best, ms)
+    out["okada_fault_fault_256x64"] = {"unique_entries": int(st.size), "kernel_ms": best,
+                                       "entries_per_s": st.size / (best * 1e-3),
+                                       "dense_equivalent_entries_per_s": (mf.nx * mf.nxi) ** 2 / (best * 1e-3)}
+    fsm = W.FaultSpec(64e3, 16e3, 1000.0, 1000.0)
+    mfm = oq.gen_mesh("RectOkada", fsm.x, fsm.xi, fsm.dx, fsm.dxi, fsm.dip)
+    ma = oq.gen_mesh("BEMHex8Mesh", *W.box_for(32, 8, 8, fsm).args())
+    for name, builder in (("okada_fault_mantle", lambda: oq.device_fault_mantle(mfm, ma, W.LAM, W.MU, buffer_ratio=1.0)),
+                          ("hex8_mantle_fault", lambda: oq.device_mantle_fault(ma, mfm, W.LAM, W.MU)),
+                          ("hex8_mantle_mantle", lambda: oq.device_mantle_mantle(ma, W.LAM, W.MU))):
+        best, shape = None, None
+        for _ in range(3):
+            t0 = oq.kernel_launch_count()
+            m = builder()
+            shape = (m.local_rows, m.cols)
+            ms = _matrix_kernel_ms(m)
+            best = ms if best is None else min(best, ms)
+            m.free()
+            del t0
+        out[name] = {"shape": list(shape), "kernel_ms": best, "entries_per_s": shape[0] * shape[1] / (best * 1e-3)}
+    out["fp64_peak_tflops_measured"] = fp64_peak / 1e12
+    return out
+
+
+def _matrix_kernel_ms(m):
+    # device time of the assembly kernel recorded by the library (CUDA events around the launch)
+    import ctypes as C
+    from oetqf_b200 import _lib
+    ms = C.c_double()
+    _lib.check(_lib.load().oq_matrix_kernel_ms(m.handle, C.byref(ms)))
+    return ms.value
+
+
+def example_extra(oq):
+    """BASELINE configs[1]: the example problem (N_f = 32, N_e = 36; 0.5 MB of matrices: launch-latency bound)."""
+    fs, bs = W.C2_FAULT, W.C2_BOX
+    mf = oq.gen_mesh("RectOkada", fs.x, fs.xi, fs.dx, fs.dxi, fs.dip)
+    ma = oq.gen_mesh("BEMHex8Mesh", *bs.args())
+    a, b, L, sig = W.fault_properties(mf.x, mf.z, mf.nx, mf.nxi)
+    g, n, d0 = W.mantle_properties(ma.cz)
+    v, th, eps, sg, dl = W.initial_state(mf.nx, mf.nxi, L, ma.cz, g, n)
+    pf = oq.RateStateQuasiDynamicProperty(a, b, L, sig, W.ETA, W.VPL, W.F0, W.V0)
+    pa = oq.PowerLawViscosityProperty(g, n, d0)
+    d11 = oq.device_fault_fault(mf, W.LAM, W.MU, buffer_ratio=1.0)
+    d12 = oq.device_fault_mantle(mf, ma, W.LAM, W.MU, buffer_ratio=1.0)
+    d21 = oq.device_mantle_fault(ma, mf, W.LAM, W.MU)
+    d22 = oq.device_mantle_mantle(ma, W.LAM, W.MU)
+    u0 = oq.ArrayPartition(v, th, eps, sg, dl)
+    prob = oq.assemble(d11, d12, d21, d22, pf, pa, u0, (0.0, 0.1 * W.YEAR))
+    prob.p.set_state(u0.x)
+    prob.p.rhs_resident(20)
+    ms = prob.p.rhs_resident(500) / 500
+    t0 = time.perf_counter()
+    sol = oq.solve(prob, oq.Tsit5(), reltol=1e-6, abstol=1e-8, dt=1e-8, dtmax=0.2 * W.YEAR, maxiters=300,
+                   save_everystep=False)
+    wall = time.perf_counter() - t0
+    steps = sol.stats["naccept"] + sol.stats["nreject"]
+    return {"workload": "BASELINE configs[1]: examples/otf-with-mantle.jl (8x4 fault, 4x3x3 hex8 mantle), coupled RHS",
+            "rhs_evals_per_s": 1e3 / ms, "rhs_us": 1e3 * ms, "tsit5_steps_per_s": steps / wall,
+            "tsit5_rhs_per_s": 6 * steps / wall}
+
+
+# ------------------------------------------------------------------------------------------ main arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import oetqf_b200 as oq
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch N>1 with torchrun (one rank per GPU)")
+    torch.cuda.set_device(local)
+    oq.init(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    fs = W.C3_FAULT
+    nf = fs.nx * fs.nxi
+    # contiguous row shards in rank order, multiples of 4 rows (the matvec's row-block size)
+    per = -(-nf // world)
+    per = -(-per // 4) * 4
+    r0, r1 = min(nf, rank * per), min(nf, (rank + 1) * per)
+    mf, prob, u0 = build_fault_problem(oq, fs, (r0, r1))
+    p = prob.p
+    if world > 1:
+        mine = p.comm_export(rank, world)
+        handles = [None] * world
+        dist.all_gather_object(handles, mine)
+        p.comm_connect(handles)
+        dist.barrier()
+    loc = local_slices(u0, r0, r1)
+    p.set_state(loc)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident value ------------------------------------------------------------------
+    p.rhs_resident(max(3, args.warmup))
+    torch.cuda.synchronize()
+    p.profile_enable(True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    launches0 = oq.kernel_launch_count()
+    barrier()
+    ms = p.rhs_resident(args.steps)
+    barrier()
+    launches = oq.kernel_launch_count() - launches0
+    mv_ms, mv_n = p.profile_read()
+    p.profile_enable(False)
+    if rank == 0:
+        time.sleep(0.15)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = args.steps / (ms_max * 1e-3)
+
+    # ---- end to end through prob.f(du, u, p, t) with pinned host buffers ---------------------------
+    hu = [torch.empty(a.size, dtype=torch.float64).pin_memory() for a in loc]
+    hdu = [torch.empty(a.size, dtype=torch.float64).pin_memory() for a in loc]
+    for h, a in zip(hu, loc):
+        h.numpy()[:] = a
+    u_np = [h.numpy() for h in hu]
+    du_np = [h.numpy() for h in hdu]
+    for _ in range(max(3, args.warmup)):
+        p.rhs(du_np, u_np, 0.0)
+    ksteps = args.steps
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    ev0.record()
+    for _ in range(ksteps):
+        p.rhs(du_np, u_np, 0.0)          # H2D(u) -> kernels -> D2H(du), synchronous at return
+    ev1.record()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0     # host clock: the call is synchronous and includes both copies
+    barrier()
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = ksteps / float(t.item())
+    bytes_in = sum(a.nbytes for a in u_np)
+    bytes_out = sum(a.nbytes for a in du_np)
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    peak_gbs, peak_src = measured_peaks()
+    rhs_bytes = p.rhs_bytes()
+    mat_bytes = 8.0 * (r1 - r0) * nf
+    mv_avg_ms = mv_ms / max(1, mv_n)
+    achieved = rhs_bytes / (mv_avg_ms * 1e-3) / 1e9
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "r01_matvec_traffic.json")
+    if os.path.exists(prof):
+        with open(prof) as fh:
+            traffic = json.load(fh).get("dram_bytes_per_launch")
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "nx": fs.nx, "nxi": fs.nxi, "rows_per_rank": r1 - r0,
+                   "matrix_bytes_per_rank": mat_bytes, "l2": "inputs larger than L2 (2.15 GB fp64 matrix vs 126 MB)",
+                   "parallelism": f"row-sharded x{world}, peer-store all-gather" if world > 1 else "single GPU"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+                     "frac": achieved / peak_gbs, "traffic": traffic, "kernel": "matvec_fused_kernel",
+                     "kernel_ms": mv_avg_ms, "algorithmic_bytes_per_launch": rhs_bytes, "peak_source": peak_src,
+                     "kernel_share_of_step": mv_ms / ms if ms > 0 else None},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": bytes_out},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+    if world == 1:
+        base, _ = cpu_reference(fs, budget_s=10.0)
+        line["cpu_baseline"] = base
+        if not args.no_extra:
+            try:
+                fp64_peak = oq.measure_fp64_peak()
+                line["extra"] = {"assembly": assembly_extras(oq, fp64_peak), "example": example_extra(oq),
+                                 "hbm_copy_gbs_own_kernel": oq.measure_hbm_copy(1 << 30) / 1e9}
+            except Exception as exc:      # extras must never take the headline line down
+                line["extra"] = {"error": repr(exc)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-extra", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

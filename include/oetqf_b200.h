@@ -131,6 +131,8 @@ int oq_matrix_from_host(const double *a_colmajor, int m, int n, int row_kind, in
  * fault: f - row_begin ; mantle: (e - e_begin) + k*(e_end - e_begin). */
 int oq_matrix_to_host(const OqMatrix *a, double *out_colmajor);
 int oq_matrix_shape(const OqMatrix *a, int *local_rows, int *cols, int *global_rows);
+/* device time (CUDA events) of the assembly kernel that filled this shard, in ms (0 for uploads) */
+int oq_matrix_kernel_ms(const OqMatrix *a, double *ms);
 int oq_matrix_destroy(OqMatrix *a);
 
 /* The `matvecmul!` backend slot, src/pref.jl:15-21 as used at src/BEM/equation.jl:201-203:
@@ -193,6 +195,14 @@ int oq_state_get_du(const OqProblem *p, double *const *du_parts); /* derivative 
 /* nevals back-to-back device RHS evaluations on the resident state (for throughput measurement);
  * ms_total receives the CUDA-event time. */
 int oq_rhs_resident(OqProblem *p, int nevals, double *ms_total);
+
+/* Per-kernel timing of the dominant kernel (the fused matvec) inside the caller's timed region: when enabled,
+ * every RHS evaluation brackets its matvec launch with CUDA events on the problem's stream.
+ * oq_profile_read synchronises, returns the summed matvec time and launch count since the last read. */
+int oq_profile_enable(OqProblem *p, int on);
+int oq_profile_read(OqProblem *p, double *matvec_ms_total, int64_t *launches);
+/* Algorithmic bytes one RHS evaluation streams from HBM on this rank (matrix shards + vectors). */
+int oq_rhs_bytes(const OqProblem *p, double *bytes);
 
 /* Adaptive integrator options (OrdinaryDiffEq semantics: examples/otf-with-mantle.jl:160-162). */
 typedef struct OqSolveOptions {

@@ -748,6 +748,13 @@ int oq_matrix_shape(const OqMatrix* a, int* local_rows, int* cols, int* global_r
     return 0;
 }
 
+int oq_matrix_kernel_ms(const OqMatrix* a, double* ms)
+{
+    OQ_CHECK(a && ms, "NULL argument");
+    *ms = a->kernel_ms;
+    return 0;
+}
+
 int oq_matrix_destroy(OqMatrix* a)
 {
     if (a) { enter(); delete a; }

@@ -3,7 +3,7 @@
 // Replaces `stress_vol_hex8!(out, x,y,z, qx,qy,qz, Δx,Δy,Δz, 0, ε..., μ, ν)` as called at
 // /root/reference/src/BEM/GF.jl:215-221 and :277-283 (GeoGreensFunctions.jl, Barbot et al. 2017; un-vendored).
 // The closed form is this repository's own derivation from the kernel's definition
-// (oracle/derive/hex8_derive.py generates hex8_gen.cuh): the strain is a signed sum over the 8 corners of
+// (derive/hex8_derive.py generates hex8_gen.cuh): the strain is a signed sum over the 8 corners of
 // the cuboid, for the real and the image source, of explicit functions of the corner vector.
 //
 // B200-first restructuring: the field is linear in the eigenstrain, so ONE geometry evaluation (36 strain

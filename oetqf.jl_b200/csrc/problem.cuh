@@ -87,6 +87,11 @@ struct OqProblem {
 
     cudaStream_t stream = nullptr;
 
+    // optional per-launch timing of the matvec (bench.py's roofline line)
+    bool prof_on = false;
+    std::vector<cudaEvent_t> prof_ev;               // pairs (start, stop)
+    size_t prof_used = 0;
+
     // multi-GPU
     int rank = 0, world = 1;
     oq::PeerWindow* peers = nullptr;

@@ -439,7 +439,19 @@ int rhs_device(OqProblem* p, const double* uin, double* du)
         fault_epilogue_kernel<<<(p->nfl + 255) / 256, 256, 0, st>>>(fe, y0, p->nfl);
         OQ_LAUNCHED();
     }
-    return launch_matvec(a, st);
+    const bool capturing = [&] {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(st, &cs);
+        return cs != cudaStreamCaptureStatusNone;
+    }();
+    const bool prof = p->prof_on && !capturing && p->prof_used + 2 <= p->prof_ev.size();
+    if (prof) OQ_CUDA(cudaEventRecord(p->prof_ev[p->prof_used], st));
+    OQ_TRY(launch_matvec(a, st));
+    if (prof) {
+        OQ_CUDA(cudaEventRecord(p->prof_ev[p->prof_used + 1], st));
+        p->prof_used += 2;
+    }
+    return 0;
 }
 
 // plain y = A x / y += A x on a shard (the matvecmul! slot)
@@ -471,6 +483,7 @@ using namespace oq;
 
 OqProblem::~OqProblem()
 {
+    for (cudaEvent_t e : prof_ev) cudaEventDestroy(e);
     comm_release(this);
     if (stream) cudaStreamDestroy(stream);
 }
@@ -708,6 +721,50 @@ int oq_rhs_resident(OqProblem* p, int nevals, double* ms_total)
     OQ_TRY(tm.start(p->stream));
     for (int i = 0; i < nevals; ++i) OQ_TRY(rhs_device(p, p->u.p, p->k[0].p));
     OQ_TRY(tm.stop(ms_total, p->stream));
+    return 0;
+}
+
+int oq_profile_enable(OqProblem* p, int on)
+{
+    OQ_CHECK(p, "NULL problem");
+    OQ_TRY(enter());
+    if (on && p->prof_ev.empty()) {
+        p->prof_ev.resize(2 * 4096);
+        for (auto& e : p->prof_ev) OQ_CUDA(cudaEventCreate(&e));
+    }
+    p->prof_on = on != 0;
+    p->prof_used = 0;
+    return 0;
+}
+
+int oq_profile_read(OqProblem* p, double* matvec_ms_total, int64_t* launches)
+{
+    OQ_CHECK(p && matvec_ms_total && launches, "NULL argument");
+    OQ_TRY(enter());
+    OQ_CUDA(cudaStreamSynchronize(p->stream));
+    double tot = 0.0;
+    for (size_t i = 0; i + 1 < p->prof_used; i += 2) {
+        float ms = 0;
+        OQ_CUDA(cudaEventElapsedTime(&ms, p->prof_ev[i], p->prof_ev[i + 1]));
+        tot += ms;
+    }
+    *matvec_ms_total = tot;
+    *launches = (int64_t)(p->prof_used / 2);
+    p->prof_used = 0;
+    return 0;
+}
+
+int oq_rhs_bytes(const OqProblem* p, double* bytes)
+{
+    OQ_CHECK(p && bytes, "NULL argument");
+    double b = 0.0;
+    const OqMatrix* ms[4] = {p->g11, p->g12, p->g21, p->g22};
+    for (const OqMatrix* m : ms)
+        if (m) b += 8.0 * (double)m->local_rows * (double)m->cols;
+    if (p->gf11_form == OQ_GF11_FFT) b += 8.0 * (double)p->nx * p->nxi * p->nxi;
+    // vectors: state in, derivative out, properties, forcing vectors
+    b += 8.0 * (2.0 * (double)p->nstate + 4.0 * p->nfl + (double)p->nf + 6.0 * p->ne);
+    *bytes = b;
     return 0;
 }
 

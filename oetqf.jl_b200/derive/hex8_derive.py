@@ -2,9 +2,9 @@
 (the quantity `stress_vol_hex8!` of GeoGreensFunctions.jl returns; Barbot et al. 2017), from its definition.
 
 This script is the derivation AND the code generator: it writes
-    oracle/hex8_gen.inc                     (C, included by oracle/hex8.c)
     oetqf.jl_b200/csrc/hex8_gen.cuh         (CUDA device code, included by hex8_dev.cuh)
-Run from the repo root:  python oracle/derive/hex8_derive.py
+    oracle/hex8_gen.inc                     (the same expressions as plain C for the CPU checker)
+Run from the repo root:  python oetqf.jl_b200/derive/hex8_derive.py
 
 Method ("closed-form derivation plan"):
   u_i(x) = sum_k m_jk * surface integral over the two faces normal to k of G_ij(x, xi) (outward sign),
@@ -19,7 +19,7 @@ Method ("closed-form derivation plan"):
   The functions are produced here by symbolic differentiation (all transcendental pieces are symbols with
   hand-coded derivative rules, so expressions stay rational) and common-subexpression elimination.
 Every antiderivative and derivative rule is verified numerically below before code is emitted; the emitted
-code is validated against the quadrature oracle (oracle/hex8_numeric.py) by tests/test_oracle_hex8.py.
+code is validated against an independent quadrature evaluation of the definition by tests/test_oracle_hex8.py.
 """
 import itertools
 import os
@@ -328,7 +328,7 @@ def emit(name, exprs, inputs, real_t="double"):
 def main():
     verify()
     here = os.path.dirname(os.path.abspath(__file__))
-    root = os.path.dirname(os.path.dirname(here))
+    root = os.path.dirname(os.path.dirname(here))   # <repo>/oetqf.jl_b200/derive -> <repo>
     out = {}
     for image in (False, True):
         F = build(image)
@@ -336,7 +336,7 @@ def main():
         body, nops = emit("img" if image else "real", Q, None)
         out[image] = (body, nops)
         print("image" if image else "real", "ops after CSE:", nops, file=sys.stderr)
-    header = ("// GENERATED by oracle/derive/hex8_derive.py -- do not edit.\n"
+    header = ("// GENERATED by oetqf.jl_b200/derive/hex8_derive.py -- do not edit.\n"
               "// q[36] += sgn * Q[(il),(jk)] for one corner; (il),(jk) in the order xx,xy,xz,yy,yz,zz.\n"
               "// Inputs: R1,R2,R3 corner vector, R its norm, w_c = R+R_c, q_c = R^2-R_c^2, iR/iw_c/iq_c their reciprocals, L_c = ln(w_c),\n"
               "// A_c = atan(R_a R_b/(R_c R)), Ba = atan(R1/R2), Bb = atan(R2/R1), x3 receiver depth (<= 0), al = alpha.\n")

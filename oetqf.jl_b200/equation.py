@@ -96,6 +96,20 @@ class DeviceProblem:
         _lib.check(_lib.load().oq_rhs_resident(self.handle, int(nevals), C.byref(ms)))
         return ms.value
 
+    def profile_enable(self, on: bool = True):
+        _lib.check(_lib.load().oq_profile_enable(self.handle, int(on)))
+
+    def profile_read(self):
+        """(summed matvec kernel time in ms, number of launches) since the last read"""
+        ms, n = C.c_double(), C.c_int64()
+        _lib.check(_lib.load().oq_profile_read(self.handle, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def rhs_bytes(self) -> float:
+        b = C.c_double()
+        _lib.check(_lib.load().oq_rhs_bytes(self.handle, C.byref(b)))
+        return b.value
+
     def comm_export(self, rank: int, world: int) -> bytes:
         buf = (C.c_uint8 * _lib.HANDLE_BYTES)()
         _lib.check(_lib.load().oq_comm_export(self.handle, int(rank), int(world), buf))

@@ -5,7 +5,7 @@
  * The routine belongs to the un-vendored GeoGreensFunctions.jl (Barbot et al. 2017, BSSA 107(2)); its
  * source is not available, so this file implements the DEFINITION of the kernel (stress of a uniform
  * eigenstrain in a cuboid of an elastic half-space) through the closed form derived
- * in oracle/derive/hex8_derive.py.  Parity with GeoGreensFunctions.jl is UNPINNED; the closed form is
+ * in oetqf.jl_b200/derive/hex8_derive.py (hex8_gen.inc is its plain-C output).  Parity with GeoGreensFunctions.jl is UNPINNED; the closed form is
  * pinned against an independent quadrature evaluation of the same definition (oracle/hex8_numeric.py,
  * tests/test_oracle_hex8.py) and against physical invariants.
  *

@@ -248,8 +248,10 @@ def dtau_dt_fft(gf_dft, relv):
     nx, nxi, _ = gf_dft.shape
     pad = np.zeros((2 * nx - 1, nxi))
     pad[:nx] = relv
-    rd = np.fft.rfft(pad, axis=0)                                # [nx, nxi(l)]
-    td = np.einsum("ijl,il->ij", gf_dft, rd)
+    rd = np.asfortranarray(np.fft.rfft(pad, axis=0))             # [nx, nxi(l)]
+    td = np.zeros((nx, nxi), dtype=np.complex128, order="F")
+    g = np.asfortranarray(gf_dft, dtype=np.complex128)
+    lib().oq_ref_fft_contract(nx, nxi, g.ctypes.data_as(_dp), rd.ctypes.data_as(_dp), td.ctypes.data_as(_dp))
     return np.fft.irfft(td, n=2 * nx - 1, axis=0)[:nx]
 
 

@@ -130,3 +130,25 @@ void oq_ref_update_fault_dilatancy(int n, const double *a, const double *b, cons
         ddelta[i] = v[i];
     }
 }
+
+/*
+ * equation.jl:46-54: dτ_dft[i,j] = Σ_l gf[i,j,l] * relv_dft[i,l] on interleaved complex arrays,
+ * threads over j as the reference's @batch loop.  gf: [nx,nxi,nxi] complex, rd: [nx,nxi] complex.
+ */
+void oq_ref_fft_contract(int nx, int nxi, const double *gf, const double *rd, double *out)
+{
+#pragma omp parallel for schedule(static)
+    for (int j = 0; j < nxi; ++j) {
+        double *o = out + 2 * (size_t)nx * j;
+        for (int i = 0; i < 2 * nx; ++i) o[i] = 0.0;
+        for (int l = 0; l < nxi; ++l) {
+            const double *g = gf + 2 * (size_t)nx * (j + (size_t)nxi * l);
+            const double *r = rd + 2 * (size_t)nx * l;
+            for (int i = 0; i < nx; ++i) {
+                const double gr = g[2 * i], gi = g[2 * i + 1], rr = r[2 * i], ri = r[2 * i + 1];
+                o[2 * i] += gr * rr - gi * ri;
+                o[2 * i + 1] += gr * ri + gi * rr;
+            }
+        }
+    }
+}

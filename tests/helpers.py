@@ -20,6 +20,9 @@ def scaled_err(got, want, axis=None):
     cancellation-dominated entries (relative to the largest entry of the same row)."""
     got, want = np.asarray(got), np.asarray(want)
     scale = np.max(np.abs(want), axis=axis, keepdims=axis is not None)
+    # rows/columns that vanish by symmetry hold only round-off of O(1) corner terms: floor at 1e-3 of the
+    # largest entry of the whole array
+    scale = np.maximum(scale, 1e-3 * np.max(np.abs(want)))
     scale = np.where(scale == 0, 1.0, scale)
     return float(np.max(np.abs(got - want) / scale))
 
