@@ -1,0 +1,118 @@
+"""Multi-GPU parity check (run under torchrun, one rank per GPU): row-sharded RHS and integrator vs the
+single-GPU result of the same problem.  Exit code 0 = all ranks agree."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import oetqf_b200 as oq  # noqa: E402
+import workloads as W  # noqa: E402
+
+
+def shard(n, world, rank, align=1):
+    per = -(-n // world)
+    per = -(-per // align) * align
+    return min(n, rank * per), min(n, (rank + 1) * per)
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    oq.init(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ok = True
+
+    # ---------------- coupled problem: example geometry refined (fault 16x8, mantle 8x3x4) ----------------
+    fs = W.FaultSpec(80e3, 8e3, 5e3, 1e3)
+    bs = W.BoxSpec(-40e3, -2.5e3, -8e3, 80e3, 5e3, -22e3, 8, 3, 4, tuple(np.cumprod(np.ones(4) * 1.3)))
+    mf = oq.gen_mesh("RectOkada", fs.x, fs.xi, fs.dx, fs.dxi, fs.dip)
+    ma = oq.gen_mesh("BEMHex8Mesh", *bs.args())
+    nf, ne = mf.nx * mf.nxi, len(ma)
+    a, b, L, sig = W.fault_properties(mf.x, mf.z, mf.nx, mf.nxi)
+    g, n, d0 = W.mantle_properties(ma.cz)
+    rng = np.random.default_rng(5)
+    v, th, eps, sg, dl = W.initial_state(mf.nx, mf.nxi, L, ma.cz, g, n, rng=rng)
+    pf = oq.RateStateQuasiDynamicProperty(a, b, L, sig, W.ETA, W.VPL, W.F0, W.V0)
+    pa = oq.PowerLawViscosityProperty(g, n, d0)
+    u0 = oq.ArrayPartition(v, th, eps, sg, dl)
+    tspan = (0.0, 0.05 * W.YEAR)
+
+    def build(rows, elems):
+        d11 = oq.device_fault_fault(mf, W.LAM, W.MU, buffer_ratio=1.0, rows=rows)
+        d12 = oq.device_fault_mantle(mf, ma, W.LAM, W.MU, buffer_ratio=1.0, elems=elems)
+        d21 = oq.device_mantle_fault(ma, mf, W.LAM, W.MU, rows=rows)
+        d22 = oq.device_mantle_mantle(ma, W.LAM, W.MU, elems=elems)
+        return oq.assemble(d11, d12, d21, d22, pf, pa, u0, tspan)
+
+    def slices(rows, elems):
+        f0, f1 = rows
+        e0, e1 = elems
+        fl = lambda x: np.ascontiguousarray(x.reshape(-1, order="F")[f0:f1])          # noqa: E731
+        ml = lambda x: np.ascontiguousarray(x[e0:e1, :].reshape(-1, order="F"))       # noqa: E731
+        return [fl(v), fl(th), ml(eps), ml(sg), fl(dl)]
+
+    rows, elems = shard(nf, world, rank), shard(ne, world, rank)
+    prob = build(rows, elems)
+    handles = [None] * world
+    dist.all_gather_object(handles, prob.p.comm_export(rank, world))
+    prob.p.comm_connect(handles)
+    dist.barrier()
+    loc = slices(rows, elems)
+    du = [np.zeros_like(x) for x in loc]
+    for it in range(3):                       # repeated: exercises the parity double-buffering and epoch flags
+        prob.p.rhs(du, loc, 0.0)
+    # reference: the full problem on this rank's GPU alone
+    full = build((0, nf), (0, ne))
+    duf = u0.similar()
+    full.f(duf, u0, full.p, 0.0)
+    want = slices(rows, elems)
+    wf = [duf.x[0], duf.x[1], duf.x[2], duf.x[3], duf.x[4]]
+    f0, f1 = rows
+    e0, e1 = elems
+    want = [wf[0].reshape(-1, order="F")[f0:f1], wf[1].reshape(-1, order="F")[f0:f1],
+            wf[2][e0:e1, :].reshape(-1, order="F"), wf[3][e0:e1, :].reshape(-1, order="F"),
+            wf[4].reshape(-1, order="F")[f0:f1]]
+    for k, (gt, w) in enumerate(zip(du, want)):
+        den = np.maximum(np.abs(w), 1e-9 * np.max(np.abs(w)) + 1e-300)
+        err = float(np.max(np.abs(gt - w) / den)) if w.size else 0.0
+        if err > 1e-11:
+            ok = False
+            print(f"[rank {rank}] RHS partition {k}: rel err {err:.3e}", flush=True)
+
+    # ---------------- integrator: sharded vs full ----------------
+    sol = oq.solve(prob, oq.Tsit5(), reltol=1e-7, abstol=1e-9, dt=1e-6, dtmax=0.2 * W.YEAR, local_u0=loc,
+                   save_everystep=False, maxiters=4000)
+    solf = oq.solve(full, oq.Tsit5(), reltol=1e-7, abstol=1e-9, dt=1e-6, dtmax=0.2 * W.YEAR,
+                    save_everystep=False, maxiters=4000)
+    if sol.retcode != "Success" or solf.retcode != "Success":
+        ok = False
+        print(f"[rank {rank}] retcodes {sol.retcode} {solf.retcode}", flush=True)
+    if sol.stats["naccept"] != solf.stats["naccept"] or sol.stats["nreject"] != solf.stats["nreject"]:
+        ok = False
+        print(f"[rank {rank}] step counts differ: {sol.stats} vs {solf.stats}", flush=True)
+    uf = solf.u[-1].x
+    wantu = [uf[0].reshape(-1, order="F")[f0:f1], uf[1].reshape(-1, order="F")[f0:f1],
+             uf[2][e0:e1, :].reshape(-1, order="F"), uf[3][e0:e1, :].reshape(-1, order="F"),
+             uf[4].reshape(-1, order="F")[f0:f1]]
+    for k, (gt, w) in enumerate(zip(sol.u[-1].x, wantu)):
+        gt = np.asarray(gt).reshape(-1, order="F")
+        # components that stay ~0 by symmetry (e.g. eps_xz) carry only round-off: floor at 1e-3 of the field
+        den = np.maximum(np.abs(w), 1e-3 * np.max(np.abs(w)) + 1e-300)
+        err = float(np.max(np.abs(gt - w) / den)) if w.size else 0.0
+        if err > 1e-6:
+            ok = False
+            print(f"[rank {rank}] solve partition {k}: rel err {err:.3e}", flush=True)
+    print(f"[rank {rank}] rows={rows} elems={elems} steps={sol.stats['naccept']}+{sol.stats['nreject']} "
+          f"t={sol.stats['t']:.4e} ok={ok}", flush=True)
+    t = torch.tensor([0 if ok else 1], device="cuda")
+    dist.all_reduce(t)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(int(t.item() != 0))
+
+
+if __name__ == "__main__":
+    main()
