@@ -108,10 +108,6 @@ def build_fault_problem(oq, fs, rows, rng_seed=42):
     return mf, prob, u0
 
 
-def local_slices(u0, r0, r1):
-    return [np.ascontiguousarray(a.reshape(-1, order="F")[r0:r1]) for a in u0.x]
-
-
 # ------------------------------------------------------------------------------------------ reference arm
 def cpu_reference(fs, budget_s=12.0, steps=None, warmup=1):
     """The reference's own CPU algorithm for this path, restated (oracle port): FFT form of the fault-fault
@@ -271,18 +267,12 @@ def run_ours(args):
     fs = W.C3_FAULT
     nf = fs.nx * fs.nxi
     # contiguous row shards in rank order, multiples of 4 rows (the matvec's row-block size)
-    per = -(-nf // world)
-    per = -(-per // 4) * 4
-    r0, r1 = min(nf, rank * per), min(nf, (rank + 1) * per)
+    r0, r1 = oq.dist.shard_range(nf, world, rank, align=4)
     mf, prob, u0 = build_fault_problem(oq, fs, (r0, r1))
     p = prob.p
     if world > 1:
-        mine = p.comm_export(rank, world)
-        handles = [None] * world
-        dist.all_gather_object(handles, mine)
-        p.comm_connect(handles)
-        dist.barrier()
-    loc = local_slices(u0, r0, r1)
+        oq.dist.connect(p)
+    loc = oq.dist.local_state(u0.x, (r0, r1))
     p.set_state(loc)
 
     def barrier():

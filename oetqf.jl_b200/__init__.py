@@ -4,7 +4,7 @@ Host-side mirror of the reference's public entry points for those paths (same na
 meaning); every number is produced by the sm_100a kernels in csrc/ through the C ABI declared in
 include/oetqf_b200.h.  There is no CPU fallback.
 """
-from . import _lib
+from . import _lib, dist
 from ._lib import OqError, init, kernel_launch_count, measure_fp64_peak, measure_hbm_copy
 from .equation import ArrayPartition, DeviceProblem, ODEProblem, ODESolution, Tsit5, assemble, ode, solve
 from .gf import (DeviceMatrix, DipSlip, StrikeSlip, dc3d_gradient, device_fault_fault, device_fault_mantle,

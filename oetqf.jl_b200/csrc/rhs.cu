@@ -206,12 +206,19 @@ struct MatvecJob {
     double* yout;         // kEpiStore target
     int epilogue;
     int nitems;           // row blocks * nsegTotal
+    // streaming (TMA) plan, see matvec_stream.cuh
+    int nrb;              // row blocks of kStR rows
+    int nch[2];           // chunks per operand
+    int chunks_per_rb;
+    int slots;            // partial-sum slots per row (max contributing CTAs of a row block)
+    long long chunk_begin;
 };
 
 struct MatvecArgs {
     MatvecJob job[2];     // fault rows, mantle rows
     FaultEpilogue fe;
     PeerWait pw;
+    long long total_chunks;
 };
 
 __global__ void __launch_bounds__(kMvThreads)
@@ -339,6 +346,59 @@ matvec_fused_kernel(const __grid_constant__ MatvecArgs args)
     }
 }
 
+}  // namespace oq
+#include "matvec_stream.cuh"
+namespace oq {
+
+static int sm_count()
+{
+    static int n = 0;
+    if (n == 0) {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, current_device() >= 0 ? current_device() : 0) == cudaSuccess)
+            n = prop.multiProcessorCount;
+        else n = 148;
+    }
+    return n;
+}
+
+// streaming plan over both row sets; returns the grid size
+static int plan_stream(MatvecArgs& a)
+{
+    long long total = 0;
+    for (int jb = 0; jb < 2; ++jb) {
+        MatvecJob& j = a.job[jb];
+        j.nrb = j.nrows > 0 ? (j.nrows + kStR - 1) / kStR : 0;
+        for (int o = 0; o < 2; ++o)
+            j.nch[o] = (j.op[o].G && j.op[o].cols > 0 && j.nrows > 0) ? (int)((j.op[o].ld + kStCH - 1) / kStCH) : 0;
+        j.chunks_per_rb = j.nch[0] + j.nch[1];
+        if (j.chunks_per_rb == 0) j.nrb = 0;
+        j.chunk_begin = total;
+        total += (long long)j.nrb * j.chunks_per_rb;
+    }
+    a.total_chunks = total;
+    if (total == 0) return 0;
+    const int grid = (int)(total < sm_count() ? total : sm_count());
+    const long long min_span = total / grid;
+    for (int jb = 0; jb < 2; ++jb) {
+        MatvecJob& j = a.job[jb];
+        long long s = j.chunks_per_rb > 0 ? (j.chunks_per_rb - 1) / min_span + 2 : 1;
+        if (s > j.chunks_per_rb) s = j.chunks_per_rb > 0 ? j.chunks_per_rb : 1;
+        j.slots = (int)s;
+    }
+    return grid;
+}
+
+static bool use_ldg_matvec()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("OQ_MATVEC");
+        v = (e && strcmp(e, "ldg") == 0) ? 1 : 0;
+    }
+    return v == 1;
+}
+
 // choose the column split so that the grid has enough CTAs to balance 148 SMs
 static void plan_operand(MatOperand& op, int nrowblocks, int other_min_seg)
 {
@@ -367,8 +427,21 @@ int plan_job(MatvecJob& job, int nrows)
     return nrb;
 }
 
-int launch_matvec(const MatvecArgs& a, cudaStream_t stream)
+int launch_matvec(MatvecArgs& a, cudaStream_t stream)
 {
+    if (!use_ldg_matvec()) {
+        const int grid = plan_stream(a);
+        if (grid == 0) return 0;
+        static bool stream_attr_set = false;
+        if (!stream_attr_set) {
+            OQ_CUDA(cudaFuncSetAttribute(matvec_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)kStSmemBytes));
+            stream_attr_set = true;
+        }
+        matvec_stream_kernel<<<grid, kStThreads, kStSmemBytes, stream>>>(a);
+        OQ_LAUNCHED();
+        return 0;
+    }
     const int items = a.job[0].nitems + a.job[1].nitems;
     if (items == 0) return 0;
     static bool attr_set = false;
@@ -469,10 +542,13 @@ int gemv_device(const OqMatrix* A, const double* x_dev_padded, const double* y_i
 
 int gemv_scratch_sizes(const OqMatrix* A, size_t* npartial, size_t* ncounters)
 {
-    MatvecJob j{};
+    MatvecArgs a{};
+    MatvecJob& j = a.job[0];
     j.op[0].G = A->d.p; j.op[0].ld = A->ld; j.op[0].cols = A->cols;
     const int nrb = plan_job(j, A->local_rows);
-    *npartial = (size_t)A->local_rows * j.nsegTotal;
+    plan_stream(a);
+    const int per_row = j.nsegTotal > j.slots ? j.nsegTotal : j.slots;
+    *npartial = (size_t)A->local_rows * (per_row > 0 ? per_row : 1);
     *ncounters = nrb;
     return 0;
 }
@@ -563,14 +639,17 @@ static int finish_problem(OqProblem* p, const OqFaultProperty* pf, const OqDilat
         p->opm[1].G = p->g22->d.p; p->opm[1].ld = p->g22->ld; p->opm[1].x = p->reldeps; p->opm[1].x_stride = p->wl.reldeps_len; p->opm[1].cols = p->g22->cols;
     }
     // matvec scratch
-    MatvecJob jf{}, jm{};
+    MatvecArgs plan{};
+    MatvecJob &jf = plan.job[0], &jm = plan.job[1];
     jf.op[0] = p->opf[0]; jf.op[1] = p->opf[1];
     jm.op[0] = p->opm[0]; jm.op[1] = p->opm[1];
     const int nrbf = plan_job(jf, nfl);
     const int nrbm = plan_job(jm, p->kind == kViscoelastic ? 6 * nel : 0);
-    p->nseg_f = jf.nsegTotal; p->nseg_m = jm.nsegTotal;
-    OQ_TRY(p->partial_f.alloc((size_t)nfl * (jf.nsegTotal > 0 ? jf.nsegTotal : 1) + 1));
-    OQ_TRY(p->partial_m.alloc((size_t)6 * nel * (jm.nsegTotal > 0 ? jm.nsegTotal : 1) + 1));
+    plan_stream(plan);
+    p->nseg_f = jf.nsegTotal > jf.slots ? jf.nsegTotal : jf.slots;
+    p->nseg_m = jm.nsegTotal > jm.slots ? jm.nsegTotal : jm.slots;
+    OQ_TRY(p->partial_f.alloc((size_t)nfl * (p->nseg_f > 0 ? p->nseg_f : 1) + 1));
+    OQ_TRY(p->partial_m.alloc((size_t)6 * nel * (p->nseg_m > 0 ? p->nseg_m : 1) + 1));
     OQ_TRY(p->counters.alloc((size_t)nrbf + nrbm + 1)); OQ_TRY(p->counters.zero());
     OQ_TRY(p->errpart.alloc(1024)); OQ_TRY(p->errpart.zero());
     OQ_TRY(p->ctl.alloc(32)); OQ_TRY(p->ctl.zero());

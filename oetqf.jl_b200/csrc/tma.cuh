@@ -27,6 +27,11 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned by
                  : "memory");
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity)
 {
     asm volatile(
