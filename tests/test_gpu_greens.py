@@ -160,4 +160,5 @@ def test_matrix_roundtrip_and_gemv(gpu):
         assert np.max(np.abs(y - (y0 + want)) / (scale + np.abs(y0))) < 1e-14
         r0, r1 = m // 3, m - 1
         part = oq.device_from_host(A, rows=(r0, r1))
-        assert np.array_equal(part.gemv(x), got[r0:r1])
+        # a shard splits its row blocks across CTAs differently from the full matrix: same sums, other order
+        assert np.max(np.abs(part.gemv(x) - got[r0:r1]) / scale[r0:r1]) < 1e-14
