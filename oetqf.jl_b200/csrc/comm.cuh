@@ -67,9 +67,11 @@ __device__ __forceinline__ void wait_peers(const unsigned long long* flags, int 
     }
 }
 
+// Flag store to a peer.  The caller issues ONE system-scope fence before the loop over peers (a release
+// store per peer would pay the fence once per peer, ~microseconds each over NVLink).
 __device__ __forceinline__ void publish_flag(unsigned long long* remote_flag, unsigned long long epoch)
 {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(remote_flag), "l"(epoch) : "memory");
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(remote_flag), "l"(epoch) : "memory");
 }
 #endif
 

@@ -86,6 +86,31 @@ matvec_stream_kernel(const __grid_constant__ MatvecArgs args)
     if (warp == kStConsumers / 32) {
         // ------------------------------------------------------------------ producer warp
         if (lane == 0) {
+            // The matrix does not depend on this evaluation's forcing vector: the first ring of matrix pieces is
+            // requested BEFORE waiting for the peers' publication, so the flag latency hides behind HBM traffic.
+            int stage = 0;
+            unsigned phase = 0;
+            auto issue = [&](long long g, int stg, bool matrix, bool vector, size_t par) {
+                const ChunkRef c = decode_chunk(args, g);
+                const MatvecJob& j = args.job[c.job];
+                const MatOperand& op = j.op[c.op];
+                const int c0 = c.ch * kStCH;
+                const int ncol = min(kStCH, (int)op.ld - c0);
+                const unsigned bytes = (unsigned)(ncol * sizeof(double));
+                double* dst = smem + (size_t)stg * kStStageDoubles;
+                if (matrix) {
+                    mbar_arrive_expect_tx(&full_bar[stg], bytes * (kStR + 1));
+#pragma unroll
+                    for (int r = 0; r < kStR; ++r) {
+                        const int row = min(c.rb * kStR + r, j.nrows - 1);
+                        tma_load_1d(dst + r * kStCH, op.G + (size_t)row * op.ld + c0, bytes, &full_bar[stg]);
+                    }
+                }
+                if (vector) tma_load_1d(dst + kStR * kStCH, op.x + par * op.x_stride + c0, bytes, &full_bar[stg]);
+            };
+            long long g = g_begin;
+            const long long g_pre = min(g_end, g_begin + kStStages);
+            for (; g < g_pre; ++g) issue(g, (int)(g - g_begin), true, false, 0);
             size_t par = 0;
             if (args.pw.epochs) {
                 const unsigned long long ep = *(volatile unsigned long long*)(args.pw.epochs + kEpForcing);
@@ -95,24 +120,12 @@ matvec_stream_kernel(const __grid_constant__ MatvecArgs args)
                 }
                 par = (size_t)((ep - 1ull) & 1ull);
             }
-            int stage = 0;
-            unsigned phase = 0;
-            for (long long g = g_begin; g < g_end; ++g) {
-                const ChunkRef c = decode_chunk(args, g);
-                const MatvecJob& j = args.job[c.job];
-                const MatOperand& op = j.op[c.op];
-                const int c0 = c.ch * kStCH;
-                const int ncol = min(kStCH, (int)op.ld - c0);
-                const unsigned bytes = (unsigned)(ncol * sizeof(double));
+            for (long long h = g_begin; h < g_pre; ++h) issue(h, (int)(h - g_begin), false, true, par);
+            stage = (int)((g_pre - g_begin) % kStStages);
+            phase = (g_pre - g_begin) >= kStStages ? 1u : 0u;
+            for (; g < g_end; ++g) {
                 mbar_wait(&empty_bar[stage], phase ^ 1u);
-                double* dst = smem + (size_t)stage * kStStageDoubles;
-                mbar_arrive_expect_tx(&full_bar[stage], bytes * (kStR + 1));
-#pragma unroll
-                for (int r = 0; r < kStR; ++r) {
-                    const int row = min(c.rb * kStR + r, j.nrows - 1);
-                    tma_load_1d(dst + r * kStCH, op.G + (size_t)row * op.ld + c0, bytes, &full_bar[stage]);
-                }
-                tma_load_1d(dst + kStR * kStCH, op.x + par * op.x_stride + c0, bytes, &full_bar[stage]);
+                issue(g, stage, true, true, par);
                 if (++stage == kStStages) { stage = 0; phase ^= 1u; }
             }
         }

@@ -77,6 +77,9 @@ struct OqProblem {
     oq::DevBuf<double> partial_f, partial_m;        // [rows * nsegTotal]
     oq::DevBuf<unsigned> counters;                  // [row blocks fault + row blocks mantle]
     oq::DevBuf<double> dtau0;                       // Toeplitz-form traction rate [nfl]
+    // FFT form (toeplitz_fft.cuh): transform length, local receiver-row range, spectrum and work arrays
+    int fftN = 0, fj0 = 0, fnj = 0;
+    oq::DevBuf<double> Ghat, Rhat, That;
     int nseg_f = 0, nseg_m = 0;
     oq::MatOperand opf[2], opm[2];
 

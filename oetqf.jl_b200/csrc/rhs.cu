@@ -36,19 +36,19 @@ struct ForcingArgs {
     MantleParams mp;
 };
 
-__global__ void __launch_bounds__(256) forcing_kernel(const __grid_constant__ ForcingArgs a)
+__global__ void __launch_bounds__(1024) forcing_kernel(const __grid_constant__ ForcingArgs a)
 {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
     // buffer copy for this evaluation: parity of the number of publications so far
     const unsigned long long ep = a.epochs[kEpForcing];
     const size_t par = (size_t)(ep & 1ull);
     const int world = a.peers.world;
-    if (t < a.nfl) {
+    const int stride = gridDim.x * blockDim.x;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < a.nfl; t += stride) {
         const double rv = a.v[t] - a.vpl;                                    // equation.jl:38
         const size_t off = a.wl.off_relv + par * a.wl.relv_len + a.f0 + t;
         for (int r = 0; r < world; ++r) a.peers.base[r][off] = rv;           // local + NVLink peer stores
     }
-    if (t < a.nel) {
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < a.nel; t += stride) {
         const size_t n = a.nel;
         const double s1 = a.sig[t], s2 = a.sig[t + n], s3 = a.sig[t + 2 * n];
         const double s4 = a.sig[t + 3 * n], s5 = a.sig[t + 4 * n], s6 = a.sig[t + 5 * n];
@@ -72,10 +72,12 @@ __global__ void __launch_bounds__(256) forcing_kernel(const __grid_constant__ Fo
         }
     }
     // publication: the last block to finish bumps the local epoch and tells every peer
+    // (one fence per block: the CTA barrier orders every thread's stores before thread 0's fence, which is
+    // cumulative; a system-scope fence costs microseconds over NVLink, so it is not executed per thread)
     __shared__ int last;
-    if (world > 1) __threadfence_system(); else __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
+        if (world > 1) __threadfence_system(); else __threadfence();
         const unsigned long long prev = atomicAdd(&a.epochs[kEpBlocksF], 1ull);
         last = (prev == (unsigned long long)gridDim.x - 1ull);
     }
@@ -83,7 +85,7 @@ __global__ void __launch_bounds__(256) forcing_kernel(const __grid_constant__ Fo
     if (last && threadIdx.x == 0) {
         a.epochs[kEpBlocksF] = 0ull;
         if (world > 1) {
-            __threadfence_system();
+            if (gridDim.x > 1) __threadfence_system();     // acquire the other blocks' publications
             for (int r = 0; r < world; ++r) {
                 if (r == a.peers.rank) continue;
                 unsigned long long* f = reinterpret_cast<unsigned long long*>(a.peers.base[r] + a.wl.off_flags);
@@ -348,7 +350,18 @@ matvec_fused_kernel(const __grid_constant__ MatvecArgs args)
 
 }  // namespace oq
 #include "matvec_stream.cuh"
+#include "toeplitz_fft.cuh"
 namespace oq {
+
+static bool use_direct_toeplitz()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("OQ_TOEPLITZ");
+        v = (e && strcmp(e, "direct") == 0) ? 1 : 0;
+    }
+    return v == 1;
+}
 
 static int sm_count()
 {
@@ -478,23 +491,45 @@ int rhs_device(OqProblem* p, const double* uin, double* du)
     fa.nfl = p->nfl; fa.f0 = p->f0; fa.nel = p->kind == kViscoelastic ? p->nel : 0; fa.e0 = p->e0; fa.ne = p->ne;
     fa.vpl = p->fp.vpl; fa.mp = p->mp;
     const int nthr = p->nfl > fa.nel ? p->nfl : fa.nel;
-    forcing_kernel<<<nthr > 0 ? (nthr + 255) / 256 : 1, 256, 0, st>>>(fa);
+    // small shards: ONE block (no cross-block handshake before the publication); large ones: 256-thread blocks
+    if (nthr <= 4096) forcing_kernel<<<1, 1024, 0, st>>>(fa);
+    else forcing_kernel<<<(nthr + 255) / 256, 256, 0, st>>>(fa);
     OQ_LAUNCHED();
     PeerWait pw{p->flags, p->epochs, p->world, p->rank};
-    // 2. fault-fault interaction in Toeplitz form (the reference's algorithm) when requested
-    const double* y0 = nullptr;
-    if (p->gf11_form == OQ_GF11_FFT && p->nfl > 0) {
-        dim3 grid((p->nx + 255) / 256, p->nxi);
-        toeplitz_conv_kernel<<<grid, 256, 2 * p->nx * sizeof(double), st>>>(p->st.p, p->relv, p->wl.relv_len, pw,
-                                                                            p->nx, p->nxi, p->f0, p->nfl, p->dtau0.p);
-        OQ_LAUNCHED();
-        y0 = p->dtau0.p;
-    }
-    // 4. fused matvec + pointwise physics
+    // 2. fault-fault interaction in its translation-invariant form (the reference's algorithm) when requested
     FaultEpilogue fe{};
     fe.fp = p->fp; fe.v = in.v; fe.theta = in.theta; fe.pr = in.pr;
     fe.dv = out.v; fe.dtheta = out.theta; fe.ddelta = out.delta; fe.dpr = out.pr;
     fe.dilatancy = p->kind == kDilatancy;
+    const double* y0 = nullptr;
+    bool epilogue_done = false;
+    if (p->gf11_form == OQ_GF11_FFT && p->nfl > 0) {
+        if (use_direct_toeplitz()) {
+            dim3 grid((p->nx + 255) / 256, p->nxi);
+            toeplitz_conv_kernel<<<grid, 256, 2 * p->nx * sizeof(double), st>>>(p->st.p, p->relv, p->wl.relv_len, pw,
+                                                                                p->nx, p->nxi, p->f0, p->nfl, p->dtau0.p);
+            OQ_LAUNCHED();
+        } else {
+            const int N = p->fftN, nfreq = N / 2 + 1;
+            const size_t fsmem = 2 * (size_t)N * sizeof(cplx);
+            fft_forward_kernel<<<p->nxi, 256, fsmem, st>>>(p->relv, p->wl.relv_len, pw, p->nx, N,
+                                                         reinterpret_cast<cplx*>(p->Rhat.p));
+            OQ_LAUNCHED();
+            const size_t nt = (size_t)nfreq * p->fnj;
+            spectral_contract_kernel<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(
+                p->Ghat.p, reinterpret_cast<const cplx*>(p->Rhat.p), p->nxi, p->fnj, nfreq,
+                reinterpret_cast<cplx*>(p->That.p));
+            OQ_LAUNCHED();
+            // with no dense operand on the fault rows the pointwise physics is fused into the inverse transform
+            const bool fuse = p->kind != kViscoelastic;
+            fft_inverse_kernel<<<p->fnj, 256, fsmem, st>>>(reinterpret_cast<const cplx*>(p->That.p), p->nx, N, p->fj0,
+                                                         p->f0, p->nfl, p->dtau0.p, fuse ? 1 : 0, fe);
+            OQ_LAUNCHED();
+            epilogue_done = fuse;
+        }
+        y0 = p->dtau0.p;
+    }
+    // 3. fused matvec + pointwise physics
     MatvecArgs a{};
     a.fe = fe;
     a.pw = pw;
@@ -506,7 +541,7 @@ int rhs_device(OqProblem* p, const double* uin, double* du)
     a.job[1].partial = p->partial_m.p; a.job[1].counters = p->counters.p + nrbf;
     a.job[1].yout = out.sig; a.job[1].epilogue = kEpiStore;
     plan_job(a.job[1], p->kind == kViscoelastic ? 6 * p->nel : 0);
-    if (a.job[0].nitems == 0 && p->nfl > 0) {
+    if (a.job[0].nitems == 0 && p->nfl > 0 && !epilogue_done) {
         // no dense operand on the fault rows (Toeplitz form, fault-only): standalone epilogue
         OQ_CHECK(y0 != nullptr, "fault rows have no Green's operand");
         fault_epilogue_kernel<<<(p->nfl + 255) / 256, 256, 0, st>>>(fe, y0, p->nfl);
@@ -632,6 +667,28 @@ static int finish_problem(OqProblem* p, const OqFaultProperty* pf, const OqDilat
         OQ_TRY(p->st.upload(st_host, (size_t)p->nx * p->nxi * p->nxi));
         OQ_TRY(p->dtau0.alloc(nfl > 0 ? nfl : 1));
         OQ_CHECK(2 * (size_t)p->nx * sizeof(double) <= 48 * 1024, "nx too large for the Toeplitz kernel");
+        // FFT form: transform length = power of two >= 2nx-1; receiver rows j that intersect this rank's shard
+        int N = 2;
+        while (N < 2 * p->nx - 1) N <<= 1;
+        OQ_CHECK(2 * (size_t)N * 16 <= 200 * 1024, "nx = %d too large for the shared-memory FFT", p->nx);
+        p->fftN = N;
+        p->fj0 = nfl > 0 ? p->f0 / p->nx : 0;
+        p->fnj = nfl > 0 ? (p->f1 - 1) / p->nx + 1 - p->fj0 : 0;
+        const size_t nfreq = N / 2 + 1;
+        OQ_TRY(p->Rhat.alloc(2 * nfreq * p->nxi + 2));
+        OQ_TRY(p->That.alloc(2 * nfreq * (p->fnj > 0 ? p->fnj : 1) + 2));
+        OQ_TRY(p->Ghat.alloc(nfreq * (p->fnj > 0 ? p->fnj : 1) * p->nxi + 1));
+        if (p->fnj > 0) {
+            const size_t nt = nfreq * p->fnj * p->nxi;
+            toeplitz_spectrum_kernel<<<(unsigned)((nt + 255) / 256), 256>>>(p->st.p, p->nx, p->nxi, N, p->fj0, p->fnj,
+                                                                            p->Ghat.p);
+            OQ_LAUNCHED();
+            const size_t fsmem = 2 * (size_t)N * sizeof(cplx);
+            if (fsmem > 48 * 1024) {
+                OQ_CUDA(cudaFuncSetAttribute(fft_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+                OQ_CUDA(cudaFuncSetAttribute(fft_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+            }
+        }
     }
     if (p->kind == kViscoelastic) {
         p->opf[1].G = p->g21->d.p; p->opf[1].ld = p->g21->ld; p->opf[1].x = p->reldeps; p->opf[1].x_stride = p->wl.reldeps_len; p->opf[1].cols = p->g21->cols;
@@ -840,7 +897,7 @@ int oq_rhs_bytes(const OqProblem* p, double* bytes)
     const OqMatrix* ms[4] = {p->g11, p->g12, p->g21, p->g22};
     for (const OqMatrix* m : ms)
         if (m) b += 8.0 * (double)m->local_rows * (double)m->cols;
-    if (p->gf11_form == OQ_GF11_FFT) b += 8.0 * (double)p->nx * p->nxi * p->nxi;
+    if (p->gf11_form == OQ_GF11_FFT) b += 8.0 * (double)p->Ghat.n + 16.0 * ((double)p->Rhat.n + (double)p->That.n) / 2;
     // vectors: state in, derivative out, properties, forcing vectors
     b += 8.0 * (2.0 * (double)p->nstate + 4.0 * p->nfl + (double)p->nf + 6.0 * p->ne);
     *bytes = b;

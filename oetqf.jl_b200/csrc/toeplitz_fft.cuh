@@ -1,0 +1,123 @@
+// toeplitz_fft.cuh -- the reference's own algorithm for the fault-fault interaction, on the device.
+//
+// /root/reference/src/BEM/equation.jl:44-61 evaluates dτ/dt[i,j] = Σ_l Σ_k st[|i-k|,j,l] (v-vpl)[k,l] as a linear
+// convolution along strike through FFTs: rfft of the zero-padded forcing, a per-frequency nξ x nξ contraction
+// with the transformed kernel (GF.jl:60-68), inverse rfft, first nx rows.  The same three steps here:
+//   fft_forward_kernel      one CTA per source row l: shared-memory Stockham FFT of length N
+//   spectral_contract_kernel  T[f,j] = Σ_l Ĝ[f,j,l] R[f,l]   (Ĝ is REAL: the kernel's extension is even)
+//   fft_inverse_kernel      one CTA per receiver row j: inverse FFT, first nx samples (+ optional fused
+//                           rate-and-state epilogue when no dense operand follows)
+// N is the power of two >= 2nx-1 (the reference uses exactly 2nx-1; any N >= 2nx-1 yields the same linear
+// convolution).  The spectrum Ĝ[l][j][f] (f fastest, (N/2+1) doubles) is built once per problem.
+#pragma once
+
+namespace oq {
+
+struct cplx { double re, im; };
+
+// in-place-by-ping-pong Stockham radix-2 FFT of length N (power of two) in shared memory; returns the buffer
+// holding the result.  All threads of the CTA participate.
+__device__ __forceinline__ cplx* stockham_fft(cplx* a, cplx* b, int N)
+{
+    const int half = N >> 1;
+    for (int Ns = 1; Ns < N; Ns <<= 1) {
+        for (int j = threadIdx.x; j < half; j += blockDim.x) {
+            const int k = j & (Ns - 1);
+            double s, c;
+            sincospi(-(double)k / (double)Ns, &s, &c);
+            const cplx u0 = a[j], v = a[j + half];
+            const cplx u1 = {v.re * c - v.im * s, v.re * s + v.im * c};
+            const int j0 = ((j - k) << 1) + k;
+            b[j0] = {u0.re + u1.re, u0.im + u1.im};
+            b[j0 + Ns] = {u0.re - u1.re, u0.im - u1.im};
+        }
+        __syncthreads();
+        cplx* t = a; a = b; b = t;
+    }
+    return a;
+}
+
+// Ĝ[l][j][f] = st[0,j,l] + 2 Σ_{m=1}^{nx-1} st[m,j,l] cos(2π f m / N),  f = 0..N/2
+__global__ void __launch_bounds__(256)
+toeplitz_spectrum_kernel(const double* __restrict__ st, int nx, int nxi, int N, int j0, int nj, double* __restrict__ Gh)
+{
+    const int nfreq = N / 2 + 1;
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)nfreq * nj * nxi) return;
+    const int f = (int)(t % nfreq);
+    const int jl = (int)((t / nfreq) % nj);
+    const int l = (int)(t / ((size_t)nfreq * nj));
+    const double* s = st + (size_t)nx * ((j0 + jl) + (size_t)nxi * l);
+    double acc = 0.0;
+    for (int m = nx - 1; m >= 1; --m) {
+        const int fm = (int)(((long long)f * m) % N);
+        acc = fma(s[m], cospi(2.0 * (double)fm / (double)N), acc);
+    }
+    Gh[t] = s[0] + 2.0 * acc;
+}
+
+// R[l][f] = FFT_N(zero-padded relv[:, l])[f],  f = 0..N/2
+__global__ void __launch_bounds__(256)
+fft_forward_kernel(const double* relv0, size_t relv_stride, PeerWait pw, int nx, int N, cplx* __restrict__ Rh)
+{
+    extern __shared__ __align__(16) unsigned char fsm[];
+    cplx* a = reinterpret_cast<cplx*>(fsm);
+    cplx* b = a + N;
+    const double* relv = relv0 + consumer_parity(pw) * relv_stride;
+    const int l = blockIdx.x;
+    for (int k = threadIdx.x; k < N; k += blockDim.x) a[k] = {k < nx ? relv[k + (size_t)nx * l] : 0.0, 0.0};
+    __syncthreads();
+    const cplx* r = stockham_fft(a, b, N);
+    const int nfreq = N / 2 + 1;
+    for (int f = threadIdx.x; f < nfreq; f += blockDim.x) Rh[(size_t)l * nfreq + f] = r[f];
+}
+
+// T[jl][f] = Σ_l Ĝ[l][jl][f] R[l][f]
+__global__ void __launch_bounds__(256)
+spectral_contract_kernel(const double* __restrict__ Gh, const cplx* __restrict__ Rh, int nxi, int nj, int nfreq,
+                         cplx* __restrict__ Th)
+{
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)nfreq * nj) return;
+    const int f = (int)(t % nfreq);
+    double re = 0.0, im = 0.0;
+#pragma unroll 4
+    for (int l = 0; l < nxi; ++l) {
+        const double g = Gh[(size_t)l * nfreq * nj + t];
+        const cplx r = Rh[(size_t)l * nfreq + f];
+        re = fma(g, r.re, re);
+        im = fma(g, r.im, im);
+    }
+    Th[t] = {re, im};
+}
+
+// dτ[i, j0+jl] = real(IFFT_N(Hermitian extension of T[jl][:]))[i], i < nx; rows outside [f0, f0+nfl) are dropped
+__global__ void __launch_bounds__(256)
+fft_inverse_kernel(const cplx* __restrict__ Th, int nx, int N, int j0, int f0, int nfl, double* __restrict__ dtau,
+                   int fuse_epilogue, FaultEpilogue fe)
+{
+    extern __shared__ __align__(16) unsigned char fsm[];
+    cplx* a = reinterpret_cast<cplx*>(fsm);
+    cplx* b = a + N;
+    const int jl = blockIdx.x;
+    const int nfreq = N / 2 + 1;
+    const cplx* T = Th + (size_t)jl * nfreq;
+    // ifft(X) = conj(fft(conj(X))) / N; X[N-f] = conj(X[f])
+    for (int k = threadIdx.x; k < N; k += blockDim.x) {
+        const cplx x = k < nfreq ? T[k] : cplx{T[N - k].re, -T[N - k].im};
+        a[k] = {x.re, -x.im};
+    }
+    __syncthreads();
+    const cplx* r = stockham_fft(a, b, N);
+    const double inv = 1.0 / (double)N;
+    for (int i = threadIdx.x; i < nx; i += blockDim.x) {
+        const int row = i + nx * (j0 + jl) - f0;
+        if (row >= 0 && row < nfl) {
+            const double v = r[i].re * inv;
+            if (fuse_epilogue) update_fault_row(fe, row, v);
+            else dtau[row] = v;
+        }
+    }
+}
+
+}  // namespace oq
