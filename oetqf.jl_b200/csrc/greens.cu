@@ -192,11 +192,13 @@ gf_mantle_fault_kernel(Hex8Geom a, FaultGeom f, double mu, double nu, int slip, 
     const int fl = (int)(t / a.n);
     const int fc = r0 + fl;
     const int q1 = fc % f.nx, q2 = fc / f.nx;
-    double S[6][6];
-    hex8_stress_all(f.x[q1], f.y[q2], f.z[q2], a.qx[e], a.qy[e], a.qz[e], a.dx[e], a.dy[e], a.dz[e], mu, nu, S);
-#pragma unroll
-    for (int pc = 0; pc < 6; ++pc)
-        G[(size_t)fl * ld + (size_t)pc * a.n + e] = shear_traction_stress(slip, S[pc], s1, c1, s2, c2);
+    extern __shared__ double hex8_acc[];
+    double* row = G + (size_t)fl * ld + e;
+    const size_t ne = a.n;
+    hex8_stress_emit(f.x[q1], f.y[q2], f.z[q2], a.qx[e], a.qy[e], a.qz[e], a.dx[e], a.dy[e], a.dz[e], mu, nu,
+                     hex8_acc + threadIdx.x, [&](int pc, const double (&S)[6]) {
+                         row[(size_t)pc * ne] = shear_traction_stress(slip, S, s1, c1, s2, c2);
+                     });
 }
 
 // ---- K4: mantle -> mantle (GF.jl:250-290) ----------------------------------------------------------
@@ -214,28 +216,23 @@ gf_mantle_mantle_kernel(Hex8Geom a, double mu, double nu, const double* __restri
     const double cx = a.cx[j], cy = a.cy[j], cz = a.cz[j];
     const double hx = a.dx[j] / 2, hy = a.dy[j] / 2, hz = a.dz[j] / 2;
     const double qx = a.qx[i], qy = a.qy[i], qz = a.qz[i], ex = a.dx[i], ey = a.dy[i], ez = a.dz[i];
-    double acc[6][6];
-#pragma unroll
-    for (int pc = 0; pc < 6; ++pc)
-#pragma unroll
-        for (int k = 0; k < 6; ++k) acc[pc][k] = 0.0;
+    extern __shared__ double hex8_acc[];
+    const size_t ne = a.n;
     for (int w = 0; w < nq; ++w) {
         const double rx = cx + qc[3 * w] * hx;
         const double ry = cy + qc[3 * w + 1] * hy;
         const double rz = cz + qc[3 * w + 2] * hz;
-        double S[6][6];
-        hex8_stress_all(rx, ry, rz, qx, qy, qz, ex, ey, ez, mu, nu, S);
         const double wt = qw[w];
+        // the thread owns its 36 entries: the first quadrature point stores, later ones accumulate in place
+        hex8_stress_emit(rx, ry, rz, qx, qy, qz, ex, ey, ez, mu, nu, hex8_acc + threadIdx.x,
+                         [&](int pc, const double (&S)[6]) {
 #pragma unroll
-        for (int pc = 0; pc < 6; ++pc)
-#pragma unroll
-            for (int k = 0; k < 6; ++k) acc[pc][k] += S[pc][k] * wt;
+                             for (int k = 0; k < 6; ++k) {
+                                 double* dst = G + ((size_t)k * nel + jl) * ld + (size_t)pc * ne + i;
+                                 *dst = (w == 0) ? S[k] * wt : *dst + S[k] * wt;
+                             }
+                         });
     }
-#pragma unroll
-    for (int pc = 0; pc < 6; ++pc)
-#pragma unroll
-        for (int k = 0; k < 6; ++k)
-            G[((size_t)k * nel + jl) * ld + (size_t)pc * a.n + i] = acc[pc][k];
 }
 
 // ---- batched direct evaluations (parity probes of the two closed forms) --------------------------
@@ -259,15 +256,15 @@ __global__ void hex8_stress_kernel(int n, const double* x, const double* y, cons
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
-    double S[6][6];
-    hex8_stress_all(x[t], y[t], z[t], qx, qy, qz, dx, dy, dz, mu, nu, S);
+    extern __shared__ double hex8_acc[];
+    double v[6] = {0, 0, 0, 0, 0, 0};
+    hex8_stress_emit(x[t], y[t], z[t], qx, qy, qz, dx, dy, dz, mu, nu, hex8_acc + threadIdx.x,
+                     [&](int pc, const double (&S)[6]) {
 #pragma unroll
-    for (int k = 0; k < 6; ++k) {
-        double v = 0.0;
+                         for (int k = 0; k < 6; ++k) v[k] += eps[pc] * S[k];
+                     });
 #pragma unroll
-        for (int pc = 0; pc < 6; ++pc) v += eps[pc] * S[pc][k];
-        out[(size_t)t * 6 + k] = v;
-    }
+    for (int k = 0; k < 6; ++k) out[(size_t)t * 6 + k] = v[k];
 }
 
 // row-major [rows x ld] -> column-major [rows x cols]
@@ -555,6 +552,18 @@ int oq_gf_fault_mantle(const OqFaultMesh* mf, const OqHex8Mesh* ma, const OqQuad
     return rc;
 }
 
+static int hex8_smem_optin()
+{
+    static bool done = false;
+    if (!done) {
+        OQ_CUDA(cudaFuncSetAttribute(gf_mantle_fault_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHex8SmemBytes));
+        OQ_CUDA(cudaFuncSetAttribute(gf_mantle_mantle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHex8SmemBytes));
+        OQ_CUDA(cudaFuncSetAttribute(hex8_stress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHex8SmemBytes));
+        done = true;
+    }
+    return 0;
+}
+
 static int build_mantle_fault(const OqHex8Mesh* ma, const OqFaultMesh* mf, double lambda, double mu, int ftype,
                               int row_begin, int row_end, OqMatrix** out)
 {
@@ -566,6 +575,7 @@ static int build_mantle_fault(const OqHex8Mesh* ma, const OqFaultMesh* mf, doubl
     OQ_CHECK(ftype == OQ_STRIKE_SLIP || ftype == OQ_DIP_SLIP, "unknown fault type %d", ftype);
     DevFaultMesh dmf;
     DevHex8Mesh dma;
+    OQ_TRY(hex8_smem_optin());
     OQ_TRY(dmf.upload(mf));
     OQ_TRY(dma.upload(ma));
     double s1, c1, s2, c2;
@@ -579,7 +589,7 @@ static int build_mantle_fault(const OqHex8Mesh* ma, const OqFaultMesh* mf, doubl
         EventTimer tm;
         int rc = tm.start();
         if (!rc) {
-            gf_mantle_fault_kernel<<<(unsigned)((total + 127) / 128), 128>>>(dma.g, dmf.g, mu, nu, ftype, s1, c1, s2, c2,
+            gf_mantle_fault_kernel<<<(unsigned)((total + 127) / 128), kHex8Threads, kHex8SmemBytes>>>(dma.g, dmf.g, mu, nu, ftype, s1, c1, s2, c2,
                                                                              row_begin, M->local_rows, M->ld, M->d.p);
             g_launches.fetch_add(1);
             rc = tm.stop(&M->kernel_ms);
@@ -617,6 +627,7 @@ static int build_mantle_mantle(const OqHex8Mesh* ma, const OqQuadrature* quad, d
              e_end, ma->n);
     DevHex8Mesh dma;
     DevQuad dq;
+    OQ_TRY(hex8_smem_optin());
     OQ_TRY(dma.upload(ma));
     OQ_TRY(dq.upload(quad));
     const double nu = lambda / 2 / (lambda + mu);   // GF.jl:259
@@ -628,7 +639,7 @@ static int build_mantle_mantle(const OqHex8Mesh* ma, const OqQuadrature* quad, d
         EventTimer tm;
         int rc = tm.start();
         if (!rc) {
-            gf_mantle_mantle_kernel<<<(unsigned)((total + 127) / 128), 128>>>(dma.g, mu, nu, dq.c.p, dq.w.p, dq.nq,
+            gf_mantle_mantle_kernel<<<(unsigned)((total + 127) / 128), kHex8Threads, kHex8SmemBytes>>>(dma.g, mu, nu, dq.c.p, dq.w.p, dq.nq,
                                                                               e_begin, nel, M->ld, M->d.p);
             g_launches.fetch_add(1);
             rc = tm.stop(&M->kernel_ms);
@@ -686,10 +697,11 @@ int oq_stress_vol_hex8(int n, const double* x, const double* y, const double* z,
     OQ_CHECK(n >= 0 && eps6 && (n == 0 || (x && y && z && out6)), "NULL argument");
     if (n == 0) return 0;
     OQ_TRY(enter());
+    OQ_TRY(hex8_smem_optin());
     DevBuf<double> bx, by, bz, be, dout;
     OQ_TRY(bx.upload(x, n)); OQ_TRY(by.upload(y, n)); OQ_TRY(bz.upload(z, n)); OQ_TRY(be.upload(eps6, 6));
     OQ_TRY(dout.alloc((size_t)n * 6));
-    hex8_stress_kernel<<<(n + 127) / 128, 128>>>(n, bx.p, by.p, bz.p, qx, qy, qz, dx, dy, dz, be.p, mu, nu, dout.p);
+    hex8_stress_kernel<<<(n + 127) / 128, kHex8Threads, kHex8SmemBytes>>>(n, bx.p, by.p, bz.p, qx, qy, qz, dx, dy, dz, be.p, mu, nu, dout.p);
     OQ_LAUNCHED();
     OQ_CUDA(cudaMemcpy(out6, dout.p, dout.n * sizeof(double), cudaMemcpyDeviceToHost));
     return 0;

@@ -2,13 +2,18 @@
 //
 // Replaces `stress_vol_hex8!(out, x,y,z, qx,qy,qz, Δx,Δy,Δz, 0, ε..., μ, ν)` as called at
 // /root/reference/src/BEM/GF.jl:215-221 and :277-283 (GeoGreensFunctions.jl, Barbot et al. 2017; un-vendored).
-// The closed form is this repository's own derivation from the kernel's definition
-// (derive/hex8_derive.py generates hex8_gen.cuh): the strain is a signed sum over the 8 corners of
-// the cuboid, for the real and the image source, of explicit functions of the corner vector.
+// The closed form is this repository's own derivation from the kernel's definition (derive/hex8_derive.py
+// generates hex8_gen.cuh): the strain is a linear combination -- with coefficients that depend only on the
+// elastic constant α and the receiver depth -- of 8-corner signed sums of 21 (real source) + 70 (image source)
+// basis functions, each a derivative of the triple antiderivative of 1/R, R or R - R3 ln(R+R3).
 //
-// B200-first restructuring: the field is linear in the eigenstrain, so ONE geometry evaluation (36 strain
-// kernels Q[(il),(jk)]) serves all six unit strains; the reference re-evaluates the whole kernel six times
-// (GF.jl:206-208, :262-264).
+// B200-first restructuring:
+//   * the field is linear in the eigenstrain, so ONE geometry evaluation serves all six unit strains (the
+//     reference re-evaluates the whole kernel six times, GF.jl:206-208, :262-264);
+//   * per corner only the basis functions are evaluated (polynomials in the corner vector, 7 reciprocals,
+//     3 logs, 3+2 atans); the 36 x 91 combination is applied once per pair, after the corner sums;
+//   * the 91 running sums live in shared memory (basis-major, conflict-free), which keeps the register file for
+//     the arithmetic: no spills.
 #pragma once
 #include <math.h>
 
@@ -16,9 +21,24 @@
 
 namespace oq {
 
+constexpr int kHex8Threads = 128;
+constexpr int kHex8Acc = HEX8_NB_REAL + HEX8_NB_IMAGE;
+constexpr size_t kHex8SmemBytes = (size_t)kHex8Acc * kHex8Threads * sizeof(double);
+
 struct Hex8Corner {
     double R, iR, w[3], q[3], iw[3], iq[3], L[3], A[3];
 };
+
+// The closed form is singular on the lines through the cuboid's edges (two components of the corner vector
+// vanish); the field itself is regular there outside the cuboid.  Receivers within `nudge` of such a line are
+// moved off it along ONE axis (keeping the other component exactly zero keeps the cancelling terms exactly
+// zero); the reference formulas return non-finite values at these points.
+__host__ __device__ inline void hex8_regularise(double& r1, double& r2, double& r3, double nudge)
+{
+    const bool t1 = fabs(r1) < nudge, t2 = fabs(r2) < nudge, t3 = fabs(r3) < nudge;
+    if (t1 && (t2 || t3)) r1 = nudge;
+    else if (t2 && t3) r2 = nudge;
+}
 
 __device__ __forceinline__ void hex8_corner_inputs(double r1, double r2, double r3, Hex8Corner& c)
 {
@@ -40,43 +60,81 @@ __device__ __forceinline__ void hex8_corner_inputs(double r1, double r2, double 
     }
 }
 
-// Q[36] (times 8πμ): strain component (il) per unit moment component (jk), pairs ordered xx,xy,xz,yy,yz,zz
-__device__ __forceinline__ void hex8_strain_kernels(double x, double y, double z, double qx, double qy, double qz,
-                                                    double dx, double dy, double dz, double alpha, double (&Q)[36])
+__device__ __forceinline__ void hex8_basis_real(double R1, double R2, double R3, const Hex8Corner& c, double sgn,
+                                                double* acc)
 {
-#pragma unroll
-    for (int k = 0; k < 36; ++k) Q[k] = 0.0;
+    const double R = c.R, iR = c.iR, w1 = c.w[0], w2 = c.w[1], w3 = c.w[2], q1 = c.q[0], q2 = c.q[1], q3 = c.q[2];
+    const double iw1 = c.iw[0], iw2 = c.iw[1], iw3 = c.iw[2], iq1 = c.iq[0], iq2 = c.iq[1], iq3 = c.iq[2];
+    const double L1 = c.L[0], L2 = c.L[1], L3 = c.L[2], A1 = c.A[0], A2 = c.A[1], A3 = c.A[2];
+    (void)R; (void)iR; (void)w1; (void)w2; (void)w3; (void)q1; (void)q2; (void)q3; (void)iw1; (void)iw2; (void)iw3;
+    (void)iq1; (void)iq2; (void)iq3; (void)L1; (void)L2; (void)L3; (void)A1; (void)A2; (void)A3;
+#define ACC(b) (*(volatile double*)&acc[(b) * kHex8Threads])   // volatile: keeps each load next to its use
+    HEX8_BASIS_REAL_BODY
+#undef ACC
+}
+
+__device__ __forceinline__ void hex8_basis_image(double R1, double R2, double R3, const Hex8Corner& c, double Ba,
+                                                 double Bb, double sgn, double* acc)
+{
+    const double R = c.R, iR = c.iR, w1 = c.w[0], w2 = c.w[1], w3 = c.w[2], q1 = c.q[0], q2 = c.q[1], q3 = c.q[2];
+    const double iw1 = c.iw[0], iw2 = c.iw[1], iw3 = c.iw[2], iq1 = c.iq[0], iq2 = c.iq[1], iq3 = c.iq[2];
+    const double L1 = c.L[0], L2 = c.L[1], L3 = c.L[2], A1 = c.A[0], A2 = c.A[1], A3 = c.A[2];
+    (void)R; (void)iR; (void)w1; (void)w2; (void)w3; (void)q1; (void)q2; (void)q3; (void)iw1; (void)iw2; (void)iw3;
+    (void)iq1; (void)iq2; (void)iq3; (void)L1; (void)L2; (void)L3; (void)A1; (void)A2; (void)A3; (void)Ba; (void)Bb;
+#define ACC(b) (*(volatile double*)&acc[(b) * kHex8Threads])   // volatile: keeps each load next to its use
+    HEX8_BASIS_IMAGE_BODY
+#undef ACC
+}
+
+// Q[36] (times 8πμ): strain component (il) per unit moment component (jk), pairs ordered xx,xy,xz,yy,yz,zz.
+// `acc` points at this thread's column of the CTA's shared accumulator array [kHex8Acc][kHex8Threads].
+__device__ __forceinline__ void hex8_strain_kernels(double x, double y, double z, double qx, double qy, double qz,
+                                                    double dx, double dy, double dz, double al, double* acc,
+                                                    double (&Q)[36])
+{
+#pragma unroll 1
+    for (int b = 0; b < kHex8Acc; ++b) acc[b * kHex8Threads] = 0.0;
     const double x0 = qx - 0.5 * dx;
+    const double nudge = 1e-6 * fmin(dx, fmin(dy, dz));
 #pragma unroll 1
     for (int corner = 0; corner < 8; ++corner) {
         const int c1 = corner & 1, c2 = (corner >> 1) & 1, c3 = corner >> 2;
         const double sgn = ((c1 + c2 + c3) & 1) ? 1.0 : -1.0;          // s1 s2 s3, s = -1 at the lower limit
-        const double r1 = x - (c1 ? x0 + dx : x0);
-        const double r2 = y - (c2 ? qy + dy : qy);
         const double zc = c3 ? qz : qz - dz;
         Hex8Corner c;
-        hex8_corner_inputs(r1, r2, z - zc, c);                          // real source
-        hex8_corner_real(r1, r2, z - zc, c.R, c.w[0], c.w[1], c.w[2], c.q[0], c.q[1], c.q[2], c.iR, c.iw[0], c.iw[1], c.iw[2],
-                         c.iq[0], c.iq[1], c.iq[2], c.L[0], c.L[1], c.L[2],
-                         c.A[0], c.A[1], c.A[2], alpha, sgn, Q);
-        const double r3 = -z - zc;                                      // image source
-        hex8_corner_inputs(r1, r2, r3, c);
-        hex8_corner_image(r1, r2, r3, c.R, c.w[0], c.w[1], c.w[2], c.q[0], c.q[1], c.q[2], c.iR, c.iw[0], c.iw[1], c.iw[2],
-                         c.iq[0], c.iq[1], c.iq[2], c.L[0], c.L[1], c.L[2],
-                          c.A[0], c.A[1], c.A[2], atan(r1 / r2), atan(r2 / r1), z, alpha, sgn, Q);
+        {
+            double r1 = x - (c1 ? x0 + dx : x0), r2 = y - (c2 ? qy + dy : qy), r3 = z - zc;   // real source
+            hex8_regularise(r1, r2, r3, nudge);
+            hex8_corner_inputs(r1, r2, r3, c);
+            hex8_basis_real(r1, r2, r3, c, sgn, acc);
+        }
+        {
+            double r1 = x - (c1 ? x0 + dx : x0), r2 = y - (c2 ? qy + dy : qy), r3 = -z - zc;  // image source
+            hex8_regularise(r1, r2, r3, nudge);
+            hex8_corner_inputs(r1, r2, r3, c);
+            hex8_basis_image(r1, r2, r3, c, atan(r1 / r2), atan(r2 / r1), sgn, acc + HEX8_NB_REAL * kHex8Threads);
+        }
     }
+    const double x3 = z, ial = 1.0 / al;
+#define ACCR(b) acc[(b) * kHex8Threads]
+#define ACCI(b) acc[(HEX8_NB_REAL + (b)) * kHex8Threads]
+    HEX8_COMBINE_BODY
+#undef ACCR
+#undef ACCI
 }
 
-// S[p][k]: stress component k (xx,xy,xz,yy,yz,zz) at (x,y,z) for unit eigenstrain component p of the cuboid
-// x∈[qx-dx/2,qx+dx/2], y∈[qy,qy+dy], z∈[qz-dz,qz]  (mesh.jl:181-183, GF.jl:218).
-__device__ __forceinline__ void hex8_stress_all(double x, double y, double z, double qx, double qy, double qz,
-                                                double dx, double dy, double dz, double mu, double nu,
-                                                double (&S)[6][6])
+// Calls out(p, S) with S[k] = stress component k (xx,xy,xz,yy,yz,zz) at (x,y,z) for unit eigenstrain component
+// p = 0..5 of the cuboid x∈[qx-dx/2,qx+dx/2], y∈[qy,qy+dy], z∈[qz-dz,qz]  (mesh.jl:181-183, GF.jl:218).
+// The six stresses of one p are handed over as soon as they exist, so callers never hold all 36.
+template <class Out>
+__device__ __forceinline__ void hex8_stress_emit(double x, double y, double z, double qx, double qy, double qz,
+                                                 double dx, double dy, double dz, double mu, double nu, double* acc,
+                                                 Out&& out)
 {
     const double lam = 2.0 * mu * nu / (1.0 - 2.0 * nu);
     const double alpha = (lam + mu) / (lam + 2.0 * mu);
     double Q[36];
-    hex8_strain_kernels(x, y, z, qx, qy, qz, dx, dy, dz, alpha, Q);
+    hex8_strain_kernels(x, y, z, qx, qy, qz, dx, dy, dz, alpha, acc, Q);
     const double pref = 1.0 / (8.0 * 3.14159265358979323846 * mu);
     const bool inside = x > qx - 0.5 * dx && x < qx + 0.5 * dx && y > qy && y < qy + dy && z > qz - dz && z < qz;
 #pragma unroll
@@ -92,12 +150,9 @@ __device__ __forceinline__ void hex8_stress_all(double x, double y, double z, do
         }
         if (inside) e[p] -= 1.0;
         const double ekk = e[0] + e[3] + e[5];
-        S[p][0] = lam * ekk + 2.0 * mu * e[0];
-        S[p][1] = 2.0 * mu * e[1];
-        S[p][2] = 2.0 * mu * e[2];
-        S[p][3] = lam * ekk + 2.0 * mu * e[3];
-        S[p][4] = 2.0 * mu * e[4];
-        S[p][5] = lam * ekk + 2.0 * mu * e[5];
+        const double S[6] = {lam * ekk + 2.0 * mu * e[0], 2.0 * mu * e[1], 2.0 * mu * e[2],
+                             lam * ekk + 2.0 * mu * e[3], 2.0 * mu * e[4], lam * ekk + 2.0 * mu * e[5]};
+        out(p, S);
     }
 }
 

@@ -34,7 +34,7 @@ q1, q2, q3 = sp.symbols("q1 q2 q3", real=True)          # q_c = R^2 - R_c^2
 L1, L2, L3 = sp.symbols("L1 L2 L3", real=True)          # ln(R + R_c)
 A1, A2, A3 = sp.symbols("A1 A2 A3", real=True)          # atan(R_a R_b / (R_c R))
 Ba, Bb = sp.symbols("Ba Bb", real=True)                 # atan(R1/R2), atan(R2/R1)
-x3, al = sp.symbols("x3 al", real=True)
+x3, al, ial = sp.symbols("x3 al ial", real=True)          # ial = 1/al
 iR = sp.Symbol("iR", real=True)                         # 1/R
 iw1, iw2, iw3 = sp.symbols("iw1 iw2 iw3", real=True)    # 1/w_c
 iq1, iq2, iq3 = sp.symbols("iq1 iq2 iq3", real=True)    # 1/q_c
@@ -129,35 +129,34 @@ def D0(c):
     return RS[a] * LS[b] + RS[b] * LS[a] - RS[c] * AS[c]
 
 
-def face_integral(pot, beta, k):
-    """antiderivative over the two in-face axes of  d^beta pot  (face normal k), as an expression"""
-    beta = list(beta)
+def TD(pot, gamma):
+    """d^gamma of the TRIPLE antiderivative T[pot] (gamma_c = 0 means "still integrated along c")."""
+    gamma = list(gamma)
+    missing = [c for c in range(3) if gamma[c] == 0]
+    if len(missing) == 0:
+        return Dn(P[pot], [g - 1 for g in gamma])
+    if len(missing) == 1:
+        c = missing[0]
+        return Dn(S(c, pot), [g - 1 if i != c else 0 for i, g in enumerate(gamma)])
+    assert len(missing) == 2, (pot, gamma)
+    k = [c for c in range(3) if gamma[c] > 0][0]
     a, b = others(k)
-    need = []
-    for ax in (a, b):
-        if beta[ax] > 0:
-            beta[ax] -= 1
-        else:
-            need.append(ax)
-    if len(need) == 0:
-        return Dn(P[pot], beta)
-    if len(need) == 1:
-        return Dn(S(need[0], pot), beta)
-    # both in-face axes still need integrating
     if pot == "P0":
+        beta = [0, 0, 0]
+        beta[k] = gamma[k] - 1
         return Dn(D0(k), beta)
-    assert beta[k] >= 2, (pot, beta, k)
-    # d_k^2 pot = c*P0 - d_a^2 pot - d_b^2 pot
-    rest = list(beta)
-    rest[k] -= 2
+    # d_k^2 T[pot] = c T[P0] - d_a^2 T[pot] - d_b^2 T[pot]   (lap P1 = 2 P0; P3 harmonic)
+    assert gamma[k] >= 3, (pot, gamma)
+    rest = [0, 0, 0]
+    rest[k] = gamma[k] - 2
     out = 0
     if LAPL[pot] is not None:
         p2, cst = LAPL[pot]
-        out += cst * face_integral(p2, rest, k)
+        out += cst * TD(p2, rest)
     for ax in (a, b):
-        bb = list(rest)
-        bb[ax] += 2
-        out -= face_integral(pot, bb, k)
+        g2 = list(rest)
+        g2[ax] = 2
+        out -= TD(pot, g2)
     return out
 
 
@@ -172,20 +171,20 @@ def add(*bs):
 
 
 def green_terms(i, j, image):
-    """8*pi*mu * G_ij as a list of (coefficient, potential, beta)"""
+    """8*pi*mu * G_ij as a list of (coefficient, potential, beta): coefficient * d^beta potential"""
     dij = 1 if i == j else 0
     t = []
     if not image:
         if dij:
-            t.append((2, "P0", [0, 0, 0]))
+            t.append((sp.Integer(2), "P0", [0, 0, 0]))
         t.append((-al, "P1", add(e(i), e(j))))
         return t
     # -uA(R) + uB(R) + x3 uC(R)
     if dij:
-        t.append((2, "P0", [0, 0, 0]))
+        t.append((sp.Integer(2), "P0", [0, 0, 0]))
     t.append((al - 2, "P1", add(e(i), e(j))))
     sj = -1 if j == 2 else 1
-    t.append((2 * (1 - al) / al * sj, "P3", add(e(i), e(j))))
+    t.append((2 * (1 - al) * ial * sj, "P3", add(e(i), e(j))))
     si = -1 if i == 2 else 1                                   # (1 - 2 delta_i3)
     if j == 2:
         t.append((-2 * si * (2 - al) * x3, "P0", e(i)))
@@ -200,35 +199,44 @@ def green_terms(i, j, image):
     return t
 
 
-def build(image):
-    """F[i][l][j][k] = d/dx_l of the face-k integral of 8*pi*mu*G_ij, per corner"""
-    F = {}
-    for i, j, k in itertools.product(range(3), repeat=3):
-        E = 0
-        for coef, pot, beta in green_terms(i, j, image):
-            E += coef * face_integral(pot, beta, k)
-        for l in range(3):
-            if image and l == 2:
-                d = -Dr(E, 2) + sp.diff(E, x3)
-            else:
-                d = Dr(E, l)
-            F[(i, l, j, k)] = d
-    return F
+def F_combo(i, l, j, k, image):
+    """d/dx_l of the face-k integral of 8*pi*mu*G_ij as a linear combination {(pot, gamma): coefficient} of
+    derivatives of triple antiderivatives, evaluated per corner"""
+    combo = {}
+
+    def put(key, c):
+        combo[key] = combo.get(key, 0) + c
+
+    for coef, pot, beta in green_terms(i, j, image):
+        gam = add(beta, e(k))
+        if not image or l != 2:
+            put((pot, tuple(add(gam, e(l)))), coef)
+        else:
+            # image source: R3 = -x3 - xi3, so d/dx3 = -d/dR3 + explicit x3-derivative of the coefficient
+            put((pot, tuple(add(gam, e(2)))), -coef)
+            dc = sp.diff(coef, x3)
+            if dc != 0:
+                put((pot, tuple(gam)), dc)
+    return combo
 
 
 PAIRS = [(0, 0), (0, 1), (0, 2), (1, 1), (1, 2), (2, 2)]      # xx, xy, xz, yy, yz, zz
 
 
-def strain_kernels(F):
-    """Q[(il),(jk)]: strain component (il) per unit moment component (jk) (symmetrised both ways)"""
-    Q = []
+def strain_combos(image):
+    """Q[(il),(jk)] as linear combinations of basis sums (symmetrised in (il) and in (jk))"""
+    out = []
     for (i, l) in PAIRS:
         for (j, k) in PAIRS:
-            v = (F[(i, l, j, k)] + F[(l, i, j, k)]) / 2
+            tot = {}
+            parts = [(F_combo(i, l, j, k, image), sp.Rational(1, 2)), (F_combo(l, i, j, k, image), sp.Rational(1, 2))]
             if j != k:
-                v += (F[(i, l, k, j)] + F[(l, i, k, j)]) / 2
-            Q.append(v)
-    return Q
+                parts += [(F_combo(i, l, k, j, image), sp.Rational(1, 2)), (F_combo(l, i, k, j, image), sp.Rational(1, 2))]
+            for combo, w in parts:
+                for key, c in combo.items():
+                    tot[key] = tot.get(key, 0) + w * c
+            out.append({k_: sp.expand(v) for k_, v in tot.items() if sp.expand(v) != 0})
+    return out
 
 
 # ---- numerical verification of every rule ---------------------------------------------------------
@@ -313,49 +321,86 @@ class MulPrinter(C99CodePrinter):
 _printer = MulPrinter()
 
 
-def emit(name, exprs, inputs, real_t="double"):
-    repl, red = sp.cse(exprs, symbols=sp.numbered_symbols("t"), optimizations="basic")
-    lines = []
-    for s, ex in repl:
-        lines.append(f"    const {real_t} {s} = {_printer.doprint(ex)};")
-    for n, ex in enumerate(red):
-        lines.append(f"    q[{n}] += sgn * ({_printer.doprint(ex)});")
-    body = "\n".join(lines)
+def cse_block(assigns, prefix):
+    """assigns: list of (target string, expr) -> C lines with common subexpressions hoisted"""
+    repl, red = sp.cse([ex for _, ex in assigns], symbols=sp.numbered_symbols(prefix), optimizations="basic")
+    lines = [f"        const double {s_} = {_printer.doprint(ex)};" for s_, ex in repl]
+    for (tgt, _), ex in zip(assigns, red):
+        lines.append(f"        {tgt} += sgn * ({_printer.doprint(ex)});")
     nops = count_ops([ex for _, ex in repl] + list(red))
-    return body, nops
+    return lines, nops
+
+
+def emit_basis(keys, index, prefix):
+    """code accumulating sgn * basis function into ACC(index[key]), grouped by (potential, order) so that each
+    group is a short block with its own common subexpressions (short live ranges, no spills)"""
+    groups = {}
+    for key in keys:
+        groups.setdefault((key[0], sum(key[1])), []).append(key)
+    lines, total = [], 0
+    for gi, (gname, gkeys) in enumerate(sorted(groups.items())):
+        assigns = [(f"ACC({index[key]})", TD(*key)) for key in gkeys]
+        blk, nops = cse_block(assigns, f"{prefix}{gi}_")
+        lines.append(f"    {{   /* {gname[0]}, derivative order {gname[1]}: {len(gkeys)} functions */")
+        lines += blk
+        lines.append("    }")
+        total += nops
+    return "\n".join(lines), total
+
+
+def emit_combine(combos_real, combos_img, idx_r, idx_i):
+    lines = []
+    exprs = []
+    accr = {k_: sp.Symbol(f"ACCR{n}") for k_, n in idx_r.items()}
+    acci = {k_: sp.Symbol(f"ACCI{n}") for k_, n in idx_i.items()}
+    for cr, ci in zip(combos_real, combos_img):
+        ex = sum(c * accr[k_] for k_, c in cr.items()) + sum(c * acci[k_] for k_, c in ci.items())
+        exprs.append(ex)
+    repl, red = sp.cse(exprs, symbols=sp.numbered_symbols("c"), optimizations="basic")
+    import re
+    def fix(txt):
+        txt = re.sub(r"ACCR(\d+)", r"ACCR(\1)", txt)
+        return re.sub(r"ACCI(\d+)", r"ACCI(\1)", txt)
+    for s_, ex in repl:
+        lines.append(f"    const double {s_} = {fix(_printer.doprint(ex))};")
+    for n, ex in enumerate(red):
+        lines.append(f"    Q[{n}] = {fix(_printer.doprint(ex))};")
+    return "\n".join(lines), count_ops([ex for _, ex in repl] + list(red))
 
 
 def main():
     verify()
     here = os.path.dirname(os.path.abspath(__file__))
     root = os.path.dirname(os.path.dirname(here))   # <repo>/oetqf.jl_b200/derive -> <repo>
-    out = {}
-    for image in (False, True):
-        F = build(image)
-        Q = [sp.together(sp.expand(v)) if False else v for v in strain_kernels(F)]
-        body, nops = emit("img" if image else "real", Q, None)
-        out[image] = (body, nops)
-        print("image" if image else "real", "ops after CSE:", nops, file=sys.stderr)
+    cr, ci = strain_combos(False), strain_combos(True)
+    keys_r = sorted({k_ for c in cr for k_ in c})
+    keys_i = sorted({k_ for c in ci for k_ in c})
+    idx_r = {k_: n for n, k_ in enumerate(keys_r)}
+    idx_i = {k_: n for n, k_ in enumerate(keys_i)}
+    body_r, ops_r = emit_basis(keys_r, idx_r, "r")
+    body_i, ops_i = emit_basis(keys_i, idx_i, "m")
+    body_c, ops_c = emit_combine(cr, ci, idx_r, idx_i)
+    print(f"real basis: {len(keys_r)} functions, {ops_r} ops/corner; image basis: {len(keys_i)} functions, "
+          f"{ops_i} ops/corner; combination: {ops_c} ops/pair", file=sys.stderr)
     header = ("// GENERATED by oetqf.jl_b200/derive/hex8_derive.py -- do not edit.\n"
-              "// q[36] += sgn * Q[(il),(jk)] for one corner; (il),(jk) in the order xx,xy,xz,yy,yz,zz.\n"
-              "// Inputs: R1,R2,R3 corner vector, R its norm, w_c = R+R_c, q_c = R^2-R_c^2, iR/iw_c/iq_c their reciprocals, L_c = ln(w_c),\n"
-              "// A_c = atan(R_a R_b/(R_c R)), Ba = atan(R1/R2), Bb = atan(R2/R1), x3 receiver depth (<= 0), al = alpha.\n")
+              "// The strain of a uniformly strained cuboid is a linear combination (coefficients in alpha and the\n"
+              "// receiver depth x3 only) of corner sums of BASIS functions = derivatives of the triple antiderivatives\n"
+              "// of P0 = 1/R, P1 = R, P3 = R - R3 ln(R+R3).  hex8_basis_* accumulate sgn * basis into ACC(b) for one\n"
+              "// corner; hex8_combine turns the 8-corner sums into Q[(il),(jk)] (times 8*pi*mu), pairs xx,xy,xz,yy,yz,zz.\n"
+              "// The includer defines ACC(b) (accumulator b of the current function), ACCR(b)/ACCI(b) (real/image sums).\n"
+              "// Inputs: R1,R2,R3 corner vector, R its norm, w_c = R+R_c, q_c = R^2-R_c^2, iR/iw_c/iq_c reciprocals,\n"
+              "// L_c = ln(w_c), A_c = atan(R_a R_b/(R_c R)), Ba = atan(R1/R2), Bb = atan(R2/R1).\n"
+              f"#define HEX8_NB_REAL {len(keys_r)}\n#define HEX8_NB_IMAGE {len(keys_i)}\n")
+    sig_common = ("double R1, double R2, double R3, double R, double w1, double w2, double w3, double q1, double q2, "
+                  "double q3, double iR, double iw1, double iw2, double iw3, double iq1, double iq2, double iq3, "
+                  "double L1, double L2, double L3, double A1, double A2, double A3")
     for path, qual in ((os.path.join(root, "oracle", "hex8_gen.inc"), "static inline"),
                        (os.path.join(root, "oetqf.jl_b200", "csrc", "hex8_gen.cuh"), "__device__ __forceinline__")):
         with open(path, "w") as fh:
             fh.write(header)
-            fh.write(f"{qual} void hex8_corner_real(double R1, double R2, double R3, double R, double w1, double w2, "
-                     "double w3, double q1, double q2, double q3, double iR, double iw1, double iw2, double iw3, "
-                     "double iq1, double iq2, double iq3, double L1, double L2, double L3, double A1, "
-                     "double A2, double A3, double al, double sgn, double* q)\n{\n")
-            fh.write(out[False][0])
-            fh.write("\n}\n\n")
-            fh.write(f"{qual} void hex8_corner_image(double R1, double R2, double R3, double R, double w1, double w2, "
-                     "double w3, double q1, double q2, double q3, double iR, double iw1, double iw2, double iw3, "
-                     "double iq1, double iq2, double iq3, double L1, double L2, double L3, double A1, "
-                     "double A2, double A3, double Ba, double Bb, double x3, double al, double sgn, double* q)\n{\n")
-            fh.write(out[True][0])
-            fh.write("\n}\n")
+            fh.write(f"#define HEX8_BASIS_REAL_BODY \\\n" + " \\\n".join(body_r.split("\n")) + "\n\n")
+            fh.write(f"#define HEX8_BASIS_IMAGE_BODY \\\n" + " \\\n".join(body_i.split("\n")) + "\n\n")
+            fh.write(f"#define HEX8_COMBINE_BODY \\\n" + " \\\n".join(body_c.split("\n")) + "\n")
         print("wrote", path)
 
 

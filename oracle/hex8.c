@@ -38,30 +38,76 @@ static void corner_inputs(double r1, double r2, double r3, double *R, double *w,
     }
 }
 
-/* Q[(il),(jk)] summed over the 8 corners, real + image parts (times 8*pi*mu) */
-static void hex8_strain_kernels(double x, double y, double z, double qx, double qy, double qz,
-                                double dx, double dy, double dz, double alpha, double *Q)
+/* The closed form is singular on the lines through the cuboid's edges; receivers within `nudge` of such a
+ * line are moved off it along one axis (same rule as the product kernel, hex8_dev.cuh). */
+static void regularise(double *r1, double *r2, double *r3, double nudge)
 {
-    memset(Q, 0, 36 * sizeof(double));
+    const int t1 = fabs(*r1) < nudge, t2 = fabs(*r2) < nudge, t3 = fabs(*r3) < nudge;
+    if (t1 && (t2 || t3)) *r1 = nudge;
+    else if (t2 && t3) *r2 = nudge;
+}
+
+static void basis_real(double R1, double R2, double R3, double R, double w1, double w2, double w3, double q1,
+                       double q2, double q3, double iR, double iw1, double iw2, double iw3, double iq1, double iq2,
+                       double iq3, double L1, double L2, double L3, double A1, double A2, double A3, double sgn,
+                       double *acc)
+{
+    (void)w1; (void)w2; (void)w3; (void)q1; (void)q2; (void)q3; (void)iw1; (void)iw2; (void)iw3;
+    (void)iq1; (void)iq2; (void)iq3; (void)L1; (void)L2; (void)L3; (void)A1; (void)A2; (void)A3; (void)R; (void)iR;
+#define ACC(b) acc[b]
+    HEX8_BASIS_REAL_BODY
+#undef ACC
+}
+
+static void basis_image(double R1, double R2, double R3, double R, double w1, double w2, double w3, double q1,
+                        double q2, double q3, double iR, double iw1, double iw2, double iw3, double iq1, double iq2,
+                        double iq3, double L1, double L2, double L3, double A1, double A2, double A3, double Ba,
+                        double Bb, double sgn, double *acc)
+{
+    (void)w1; (void)w2; (void)w3; (void)q1; (void)q2; (void)q3; (void)iw1; (void)iw2; (void)iw3;
+    (void)iq1; (void)iq2; (void)iq3; (void)L1; (void)L2; (void)L3; (void)A1; (void)A2; (void)A3; (void)Ba; (void)Bb;
+#define ACC(b) acc[b]
+    HEX8_BASIS_IMAGE_BODY
+#undef ACC
+}
+
+/* Q[(il),(jk)] (times 8*pi*mu) from the 8-corner sums of the basis functions */
+static void hex8_strain_kernels(double x, double y, double z, double qx, double qy, double qz,
+                                double dx, double dy, double dz, double al, double *Q)
+{
+    double accr[HEX8_NB_REAL], acci[HEX8_NB_IMAGE];
+    memset(accr, 0, sizeof(accr));
+    memset(acci, 0, sizeof(acci));
     const double xs[2] = {qx - dx / 2, qx + dx / 2};
     const double ys[2] = {qy, qy + dy};
     const double zs[2] = {qz - dz, qz};
+    const double nudge = 1e-6 * fmin(dx, fmin(dy, dz));
     for (int c3 = 0; c3 < 2; ++c3)
         for (int c2 = 0; c2 < 2; ++c2)
             for (int c1 = 0; c1 < 2; ++c1) {
                 const double sgn = ((c1 + c2 + c3) & 1) ? 1.0 : -1.0;   /* s1*s2*s3 with s = -1 at the lower limit */
-                const double r1 = x - xs[c1], r2 = y - ys[c2];
+                double r1 = x - xs[c1], r2 = y - ys[c2], r3r = z - zs[c3];
                 double R, w[3], q[3], L[3], A[3], iR, iw[3], iq[3];
                 /* real source */
-                corner_inputs(r1, r2, z - zs[c3], &R, w, q, L, A, &iR, iw, iq);
-                hex8_corner_real(r1, r2, z - zs[c3], R, w[0], w[1], w[2], q[0], q[1], q[2], iR, iw[0], iw[1], iw[2], iq[0], iq[1], iq[2], L[0], L[1], L[2],
-                                 A[0], A[1], A[2], alpha, sgn, Q);
+                regularise(&r1, &r2, &r3r, nudge);
+                corner_inputs(r1, r2, r3r, &R, w, q, L, A, &iR, iw, iq);
+                basis_real(r1, r2, r3r, R, w[0], w[1], w[2], q[0], q[1], q[2], iR, iw[0], iw[1], iw[2],
+                           iq[0], iq[1], iq[2], L[0], L[1], L[2], A[0], A[1], A[2], sgn, accr);
                 /* image source */
-                const double r3 = -z - zs[c3];
+                r1 = x - xs[c1]; r2 = y - ys[c2];
+                double r3 = -z - zs[c3];
+                regularise(&r1, &r2, &r3, nudge);
                 corner_inputs(r1, r2, r3, &R, w, q, L, A, &iR, iw, iq);
-                hex8_corner_image(r1, r2, r3, R, w[0], w[1], w[2], q[0], q[1], q[2], iR, iw[0], iw[1], iw[2], iq[0], iq[1], iq[2], L[0], L[1], L[2],
-                                  A[0], A[1], A[2], atan(r1 / r2), atan(r2 / r1), z, alpha, sgn, Q);
+                basis_image(r1, r2, r3, R, w[0], w[1], w[2], q[0], q[1], q[2], iR, iw[0], iw[1], iw[2],
+                            iq[0], iq[1], iq[2], L[0], L[1], L[2], A[0], A[1], A[2], atan(r1 / r2), atan(r2 / r1),
+                            sgn, acci);
             }
+    const double x3 = z, ial = 1.0 / al;
+#define ACCR(b) accr[b]
+#define ACCI(b) acci[b]
+    HEX8_COMBINE_BODY
+#undef ACCR
+#undef ACCI
 }
 
 void oq_ref_stress_vol_hex8(double x, double y, double z, double qx, double qy, double qz,

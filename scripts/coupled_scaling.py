@@ -1,0 +1,113 @@
+"""Coupled fault + mantle problem at BASELINE configs[3] scale (as far as HBM allows): assembly straight into
+row shards, RHS throughput, roofline.  Run directly (1 GPU) or under torchrun (N GPUs).
+
+  python scripts/coupled_scaling.py --nx 250 --nxi 80 --mantle 40 20 24     # 20k fault cells + 19.2k hex8 cells
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import oetqf_b200 as oq  # noqa: E402
+import workloads as W  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--nx", type=int, default=250)
+    ap.add_argument("--nxi", type=int, default=80)
+    ap.add_argument("--mantle", type=int, nargs=3, default=[40, 21, 23])   # odd ny: the fault plane y = 0 is not a cell face
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--out", default="")
+    args = ap.parse_args()
+    rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
+    torch.cuda.set_device(local)
+    oq.init(local)
+    if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    fs = W.FaultSpec(args.nx * 250.0, args.nxi * 250.0, 250.0, 250.0)
+    mx, my, mz = args.mantle
+    bs = W.BoxSpec(-fs.x / 2, -10e3, -fs.xi, fs.x, 20e3, -40e3, mx, my, mz, tuple(np.cumprod(np.ones(mz) * 1.1)))
+    mf = oq.gen_mesh("RectOkada", fs.x, fs.xi, fs.dx, fs.dxi, fs.dip)
+    ma = oq.gen_mesh("BEMHex8Mesh", *bs.args())
+    nf, ne = mf.nx * mf.nxi, len(ma)
+    rows = oq.dist.shard_range(nf, world, rank, align=4)
+    elems = oq.dist.shard_range(ne, world, rank)
+    t0 = time.perf_counter()
+    import ctypes as C
+
+    def kms(m):
+        ms = C.c_double()
+        oq._lib.check(oq._lib.load().oq_matrix_kernel_ms(m.handle, C.byref(ms)))
+        return ms.value
+
+    d11 = oq.device_fault_fault(mf, W.LAM, W.MU, buffer_ratio=1.0, rows=rows)
+    d12 = oq.device_fault_mantle(mf, ma, W.LAM, W.MU, buffer_ratio=1.0, elems=elems)
+    d21 = oq.device_mantle_fault(ma, mf, W.LAM, W.MU, rows=rows)
+    d22 = oq.device_mantle_mantle(ma, W.LAM, W.MU, elems=elems)
+    torch.cuda.synchronize()
+    asm_wall = time.perf_counter() - t0
+    asm = {"gf11_ms": kms(d11), "gf12_ms": kms(d12), "gf21_ms": kms(d21), "gf22_ms": kms(d22),
+           "gf12_entries_per_s": d12.local_rows * d12.cols / (kms(d12) * 1e-3),
+           "gf21_entries_per_s": d21.local_rows * d21.cols / (kms(d21) * 1e-3),
+           "gf22_entries_per_s": d22.local_rows * d22.cols / (kms(d22) * 1e-3)}
+    a, b, L, sig = W.fault_properties(mf.x, mf.z, mf.nx, mf.nxi)
+    g, n, d0 = W.mantle_properties(ma.cz)
+    v, th, eps, sg, dl = W.initial_state(mf.nx, mf.nxi, L, ma.cz, g, n, rng=np.random.default_rng(42))
+    pf = oq.RateStateQuasiDynamicProperty(a, b, L, sig, W.ETA, W.VPL, W.F0, W.V0)
+    pa = oq.PowerLawViscosityProperty(g, n, d0)
+    u0 = oq.ArrayPartition(v, th, eps, sg, dl)
+    prob = oq.assemble(d11, d12, d21, d22, pf, pa, u0, (0.0, 1.0))
+    p = prob.p
+    if world > 1:
+        oq.dist.connect(p)
+    p.set_state(oq.dist.local_state(u0.x, rows, elems, kind="viscoelastic"))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    p.rhs_resident(args.warmup)
+    barrier()
+    ms = p.rhs_resident(args.steps)
+    barrier()
+    p.profile_enable(True)
+    ms2 = p.rhs_resident(args.steps)
+    mv_ms, mv_n = p.profile_read()
+    p.profile_enable(False)
+    t = torch.tensor([ms, asm["gf22_ms"], asm["gf21_ms"], asm["gf12_ms"]], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    du = [np.zeros(k) for k in p.local_lengths]
+    p.get_du(du)
+    finite = all(np.all(np.isfinite(x)) for x in du)
+    if rank == 0:
+        byts = p.rhs_bytes()
+        line = {"workload": f"coupled: {nf} fault cells + {ne} hex8 cells ({6 * ne} mantle rows)", "n_gpus": world,
+                "rhs_evals_per_s": args.steps / (float(t[0]) * 1e-3), "ms_per_eval": float(t[0]) / args.steps,
+                "matrix_bytes_per_rank": byts, "matvec_ms": mv_ms / max(1, mv_n),
+                "matvec_gbs": byts / (mv_ms / max(1, mv_n) * 1e-3) / 1e9, "finite": bool(finite),
+                "assembly_ms_max_over_ranks": {"gf22": float(t[1]), "gf21": float(t[2]), "gf12": float(t[3])},
+                "assembly_rank0": asm, "assembly_wall_s": asm_wall}
+        print(json.dumps(line))
+        if args.out:
+            with open(args.out, "w") as fh:
+                json.dump(line, fh, indent=1)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
