@@ -176,3 +176,28 @@ def test_rhs_large_linearity(gpu):
     G = prob.p._keep[0]
     y = G.gemv(relv.reshape(-1, order="F"))
     assert _close(y[rows], dtau, 1e-11)
+
+
+def test_fft_form_non_power_of_two_and_shard(gpu):
+    """FFT form with nx = 250 (transform length 512 > 2nx-1 = 499) and on a row shard: identical dτ/dt rows"""
+    oq = gpu
+    spec = W.FaultSpec(250 * 250.0, 16 * 250.0, 250.0, 250.0)
+    mf_o, mf_p, pf_o, pf_p, v, th, dl = _fault_setup(oq, spec, seed=9)
+    st = ref.gf_fault_fault(mf_o, W.LAM, W.MU, buffer_ratio=1.0)
+    want = ref.rhs_fault(pf_o, st, v, th, form="toeplitz")
+    u0 = oq.ArrayPartition(v, th, dl)
+    prob = oq.assemble(st, pf_p, u0, (0.0, 1.0), gf11_form="fft")
+    du = u0.similar()
+    prob.f(du, u0, prob.p, 0.0)
+    for g, w in zip(du.x, want):
+        assert _close(g, w, 1.5e-8)          # FFT round-off, the reference's own sqrt(eps) criterion
+    # dense shard of the same problem: rows [1000, 3000)
+    r0, r1 = 1000, 3000
+    g11 = oq.device_fault_fault(mf_p, W.LAM, W.MU, buffer_ratio=1.0, rows=(r0, r1))
+    probs = oq.assemble(g11, pf_p, u0, (0.0, 1.0))
+    loc = oq.dist.local_state(u0.x, (r0, r1))
+    dul = [np.zeros_like(a) for a in loc]
+    probs.p.rhs(dul, loc, 0.0)          # world = 1: the forcing vector only holds this shard's rows
+    # (a single-rank shard sees zero forcing from the rows it does not own, so only the pointwise parts compare)
+    assert np.allclose(dul[1], want[1].reshape(-1, order="F")[r0:r1], rtol=1e-12)
+    assert np.array_equal(dul[2], v.reshape(-1, order="F")[r0:r1])
