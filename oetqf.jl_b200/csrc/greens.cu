@@ -182,6 +182,7 @@ gf_fault_mantle_kernel(FaultGeom f, Hex8Geom a, OkadaParams p, const double* __r
 // ---- K3: mantle -> fault (GF.jl:194-227) -----------------------------------------------------------
 // One geometry evaluation serves all six unit strains (the reference re-evaluates six times).
 // thread t -> (source element e fastest, receiver fault cell); writes G[fl, p*ne + e].
+template <int SLIP>
 __global__ void __launch_bounds__(128)
 gf_mantle_fault_kernel(Hex8Geom a, FaultGeom f, double mu, double nu, int slip, double s1, double c1,
                        double s2, double c2, int r0, int nrows, size_t ld, double* __restrict__ G)
@@ -195,7 +196,9 @@ gf_mantle_fault_kernel(Hex8Geom a, FaultGeom f, double mu, double nu, int slip, 
     extern __shared__ double hex8_acc[];
     double* row = G + (size_t)fl * ld + e;
     const size_t ne = a.n;
-    hex8_stress_emit(f.x[q1], f.y[q2], f.z[q2], a.qx[e], a.qy[e], a.qz[e], a.dx[e], a.dy[e], a.dz[e], mu, nu,
+    // strike-slip traction needs only the xy,xz strain rows; dip-slip only yy,yz,zz (GF.jl:89-96)
+    constexpr int kNeed = SLIP == kStrikeSlip ? 0x06 : 0x38;
+    hex8_stress_emit<kNeed>(f.x[q1], f.y[q2], f.z[q2], a.qx[e], a.qy[e], a.qz[e], a.dx[e], a.dy[e], a.dz[e], mu, nu,
                      hex8_acc + threadIdx.x, [&](int pc, const double (&S)[6]) {
                          row[(size_t)pc * ne] = shear_traction_stress(slip, S, s1, c1, s2, c2);
                      });
@@ -556,7 +559,8 @@ static int hex8_smem_optin()
 {
     static bool done = false;
     if (!done) {
-        OQ_CUDA(cudaFuncSetAttribute(gf_mantle_fault_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHex8SmemBytes));
+        OQ_CUDA(cudaFuncSetAttribute(gf_mantle_fault_kernel<kStrikeSlip>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHex8SmemBytes));
+        OQ_CUDA(cudaFuncSetAttribute(gf_mantle_fault_kernel<kDipSlip>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHex8SmemBytes));
         OQ_CUDA(cudaFuncSetAttribute(gf_mantle_mantle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHex8SmemBytes));
         OQ_CUDA(cudaFuncSetAttribute(hex8_stress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHex8SmemBytes));
         done = true;
@@ -589,8 +593,13 @@ static int build_mantle_fault(const OqHex8Mesh* ma, const OqFaultMesh* mf, doubl
         EventTimer tm;
         int rc = tm.start();
         if (!rc) {
-            gf_mantle_fault_kernel<<<(unsigned)((total + 127) / 128), kHex8Threads, kHex8SmemBytes>>>(dma.g, dmf.g, mu, nu, ftype, s1, c1, s2, c2,
-                                                                             row_begin, M->local_rows, M->ld, M->d.p);
+            const unsigned nb = (unsigned)((total + 127) / 128);
+            if (ftype == OQ_STRIKE_SLIP)
+                gf_mantle_fault_kernel<kStrikeSlip><<<nb, kHex8Threads, kHex8SmemBytes>>>(
+                    dma.g, dmf.g, mu, nu, ftype, s1, c1, s2, c2, row_begin, M->local_rows, M->ld, M->d.p);
+            else
+                gf_mantle_fault_kernel<kDipSlip><<<nb, kHex8Threads, kHex8SmemBytes>>>(
+                    dma.g, dmf.g, mu, nu, ftype, s1, c1, s2, c2, row_begin, M->local_rows, M->ld, M->d.p);
             g_launches.fetch_add(1);
             rc = tm.stop(&M->kernel_ms);
         }

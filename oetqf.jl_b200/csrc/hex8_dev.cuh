@@ -60,6 +60,7 @@ __device__ __forceinline__ void hex8_corner_inputs(double r1, double r2, double 
     }
 }
 
+template <int NEED>
 __device__ __forceinline__ void hex8_basis_real(double R1, double R2, double R3, const Hex8Corner& c, double sgn,
                                                 double* acc)
 {
@@ -69,10 +70,13 @@ __device__ __forceinline__ void hex8_basis_real(double R1, double R2, double R3,
     (void)R; (void)iR; (void)w1; (void)w2; (void)w3; (void)q1; (void)q2; (void)q3; (void)iw1; (void)iw2; (void)iw3;
     (void)iq1; (void)iq2; (void)iq3; (void)L1; (void)L2; (void)L3; (void)A1; (void)A2; (void)A3;
 #define ACC(b) (*(volatile double*)&acc[(b) * kHex8Threads])   // volatile: keeps each load next to its use
+#define HEX8_NEED(mask) (((mask) & NEED) != 0)
     HEX8_BASIS_REAL_BODY
+#undef HEX8_NEED
 #undef ACC
 }
 
+template <int NEED>
 __device__ __forceinline__ void hex8_basis_image(double R1, double R2, double R3, const Hex8Corner& c, double Ba,
                                                  double Bb, double sgn, double* acc)
 {
@@ -82,12 +86,16 @@ __device__ __forceinline__ void hex8_basis_image(double R1, double R2, double R3
     (void)R; (void)iR; (void)w1; (void)w2; (void)w3; (void)q1; (void)q2; (void)q3; (void)iw1; (void)iw2; (void)iw3;
     (void)iq1; (void)iq2; (void)iq3; (void)L1; (void)L2; (void)L3; (void)A1; (void)A2; (void)A3; (void)Ba; (void)Bb;
 #define ACC(b) (*(volatile double*)&acc[(b) * kHex8Threads])   // volatile: keeps each load next to its use
+#define HEX8_NEED(mask) (((mask) & NEED) != 0)
     HEX8_BASIS_IMAGE_BODY
+#undef HEX8_NEED
 #undef ACC
 }
 
 // Q[36] (times 8πμ): strain component (il) per unit moment component (jk), pairs ordered xx,xy,xz,yy,yz,zz.
 // `acc` points at this thread's column of the CTA's shared accumulator array [kHex8Acc][kHex8Threads].
+// NEED: bit mask of the strain rows (il) the caller will read; the other rows of Q are left unspecified.
+template <int NEED>
 __device__ __forceinline__ void hex8_strain_kernels(double x, double y, double z, double qx, double qy, double qz,
                                                     double dx, double dy, double dz, double al, double* acc,
                                                     double (&Q)[36])
@@ -106,13 +114,13 @@ __device__ __forceinline__ void hex8_strain_kernels(double x, double y, double z
             double r1 = x - (c1 ? x0 + dx : x0), r2 = y - (c2 ? qy + dy : qy), r3 = z - zc;   // real source
             hex8_regularise(r1, r2, r3, nudge);
             hex8_corner_inputs(r1, r2, r3, c);
-            hex8_basis_real(r1, r2, r3, c, sgn, acc);
+            hex8_basis_real<NEED>(r1, r2, r3, c, sgn, acc);
         }
         {
             double r1 = x - (c1 ? x0 + dx : x0), r2 = y - (c2 ? qy + dy : qy), r3 = -z - zc;  // image source
             hex8_regularise(r1, r2, r3, nudge);
             hex8_corner_inputs(r1, r2, r3, c);
-            hex8_basis_image(r1, r2, r3, c, atan(r1 / r2), atan(r2 / r1), sgn, acc + HEX8_NB_REAL * kHex8Threads);
+            hex8_basis_image<NEED>(r1, r2, r3, c, atan(r1 / r2), atan(r2 / r1), sgn, acc + HEX8_NB_REAL * kHex8Threads);
         }
     }
     const double x3 = z, ial = 1.0 / al;
@@ -125,8 +133,10 @@ __device__ __forceinline__ void hex8_strain_kernels(double x, double y, double z
 
 // Calls out(p, S) with S[k] = stress component k (xx,xy,xz,yy,yz,zz) at (x,y,z) for unit eigenstrain component
 // p = 0..5 of the cuboid x∈[qx-dx/2,qx+dx/2], y∈[qy,qy+dy], z∈[qz-dz,qz]  (mesh.jl:181-183, GF.jl:218).
-// The six stresses of one p are handed over as soon as they exist, so callers never hold all 36.
-template <class Out>
+// The six stresses of one p are handed over as soon as they exist, so callers never hold all 36.  With NEED a
+// subset of strain rows, only S[k] for those rows k is meaningful (off-diagonal rows are independent; the
+// diagonal rows 0,3,5 need each other through the trace).
+template <int NEED = 0x3f, class Out>
 __device__ __forceinline__ void hex8_stress_emit(double x, double y, double z, double qx, double qy, double qz,
                                                  double dx, double dy, double dz, double mu, double nu, double* acc,
                                                  Out&& out)
@@ -134,7 +144,7 @@ __device__ __forceinline__ void hex8_stress_emit(double x, double y, double z, d
     const double lam = 2.0 * mu * nu / (1.0 - 2.0 * nu);
     const double alpha = (lam + mu) / (lam + 2.0 * mu);
     double Q[36];
-    hex8_strain_kernels(x, y, z, qx, qy, qz, dx, dy, dz, alpha, acc, Q);
+    hex8_strain_kernels<NEED>(x, y, z, qx, qy, qz, dx, dy, dz, alpha, acc, Q);
     const double pref = 1.0 / (8.0 * 3.14159265358979323846 * mu);
     const bool inside = x > qx - 0.5 * dx && x < qx + 0.5 * dx && y > qy && y < qy + dy && z > qz - dz && z < qz;
 #pragma unroll

@@ -106,8 +106,18 @@ struct OqProblem {
 
 namespace oq {
 
+// Runge-Kutta stage combination fused into the forcing kernel: y = u + dt * sum_{j<nk} a[j] k[j]
+struct StageSpec {
+    int nk = 0;
+    const double* u = nullptr;
+    const double* k[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    double a[6] = {0, 0, 0, 0, 0, 0};
+    const double* dt = nullptr;      // device scalar (the controller's current step)
+};
+
 StateView view_of(const OqProblem* p, double* base);
-// one full RHS evaluation on the device: du = f(uin).  Enqueues on p->stream.
-int rhs_device(OqProblem* p, const double* uin, double* du);
+// one full RHS evaluation on the device: du = f(uin).  Enqueues on p->stream.  With a stage spec, uin is first
+// filled with the stage state (each thread combines exactly the entries its forcing needs).
+int rhs_device(OqProblem* p, const double* uin, double* du, const StageSpec* stage = nullptr);
 
 }  // namespace oq

@@ -28,6 +28,11 @@ struct ForcingArgs {
     const double* v;       // [nfl]
     const double* sig;     // [6*nel] or null
     double* deps_out;      // du.eps [6*nel] or null
+    StageSpec stage;       // optional fused Runge-Kutta stage combination
+    double* y;             // stage state to fill (base of the state-shaped buffer) when stage.nk > 0
+    size_t off_fault[4];   // offsets of v, θ, δ, 𝓅 inside a state-shaped buffer
+    size_t off_eps, off_sig;
+    int n_fault_parts;     // 3, or 4 with dilatancy
     PeerTargets peers;     // every rank's window (own included)
     WindowLayout wl;
     unsigned long long* epochs;   // local counters
@@ -43,15 +48,41 @@ __global__ void __launch_bounds__(1024) forcing_kernel(const __grid_constant__ F
     const size_t par = (size_t)(ep & 1ull);
     const int world = a.peers.world;
     const int stride = gridDim.x * blockDim.x;
+    const bool staged = a.stage.nk > 0;
+    const double dt = staged ? *a.stage.dt : 0.0;
+    auto combine = [&](size_t idx) {
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < 6; ++j)
+            if (j < a.stage.nk) acc = fma(a.stage.a[j], a.stage.k[j][idx], acc);
+        const double y = fma(dt, acc, a.stage.u[idx]);
+        a.y[idx] = y;
+        return y;
+    };
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < a.nfl; t += stride) {
-        const double rv = a.v[t] - a.vpl;                                    // equation.jl:38
+        double vt;
+        if (staged) {
+            vt = combine(a.off_fault[0] + t);
+            for (int q = 1; q < a.n_fault_parts; ++q) combine(a.off_fault[q] + t);
+        } else {
+            vt = a.v[t];
+        }
+        const double rv = vt - a.vpl;                                        // equation.jl:38
         const size_t off = a.wl.off_relv + par * a.wl.relv_len + a.f0 + t;
         for (int r = 0; r < world; ++r) a.peers.base[r][off] = rv;           // local + NVLink peer stores
     }
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < a.nel; t += stride) {
         const size_t n = a.nel;
-        const double s1 = a.sig[t], s2 = a.sig[t + n], s3 = a.sig[t + 2 * n];
-        const double s4 = a.sig[t + 3 * n], s5 = a.sig[t + 4 * n], s6 = a.sig[t + 5 * n];
+        double s1, s2, s3, s4, s5, s6;
+        if (staged) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) combine(a.off_eps + t + k * n);
+            s1 = combine(a.off_sig + t); s2 = combine(a.off_sig + t + n); s3 = combine(a.off_sig + t + 2 * n);
+            s4 = combine(a.off_sig + t + 3 * n); s5 = combine(a.off_sig + t + 4 * n); s6 = combine(a.off_sig + t + 5 * n);
+        } else {
+            s1 = a.sig[t]; s2 = a.sig[t + n]; s3 = a.sig[t + 2 * n];
+            s4 = a.sig[t + 3 * n]; s5 = a.sig[t + 4 * n]; s6 = a.sig[t + 5 * n];
+        }
         const double skk = (s1 + s4 + s6) / 3;                               // equation.jl:209
         const double sxx = s1 - skk, syy = s4 - skk, szz = s6 - skk;
         const double tn = sqrt(sxx * sxx + syy * syy + szz * szz + 2 * (s2 * s2 + s3 * s3 + s5 * s5));
@@ -479,7 +510,7 @@ StateView view_of(const OqProblem* p, double* b)
     return s;
 }
 
-int rhs_device(OqProblem* p, const double* uin, double* du)
+int rhs_device(OqProblem* p, const double* uin, double* du, const StageSpec* stage)
 {
     cudaStream_t st = p->stream;
     const StateView in = view_of(p, const_cast<double*>(uin));
@@ -490,6 +521,17 @@ int rhs_device(OqProblem* p, const double* uin, double* du)
     fa.peers = comm_targets(p); fa.wl = p->wl; fa.epochs = p->epochs;
     fa.nfl = p->nfl; fa.f0 = p->f0; fa.nel = p->kind == kViscoelastic ? p->nel : 0; fa.e0 = p->e0; fa.ne = p->ne;
     fa.vpl = p->fp.vpl; fa.mp = p->mp;
+    if (stage) fa.stage = *stage;
+    fa.y = const_cast<double*>(uin);
+    fa.n_fault_parts = p->kind == kDilatancy ? 4 : 3;
+    fa.off_fault[0] = p->part_off[0]; fa.off_fault[1] = p->part_off[1];
+    if (p->kind == kViscoelastic) {
+        fa.off_fault[2] = p->part_off[4]; fa.off_fault[3] = 0;
+        fa.off_eps = p->part_off[2]; fa.off_sig = p->part_off[3];
+    } else {
+        fa.off_fault[2] = p->part_off[2]; fa.off_fault[3] = p->kind == kDilatancy ? p->part_off[3] : 0;
+        fa.off_eps = fa.off_sig = 0;
+    }
     const int nthr = p->nfl > fa.nel ? p->nfl : fa.nel;
     // small shards: ONE block (no cross-block handshake before the publication); large ones: 256-thread blocks
     if (nthr <= 4096) forcing_kernel<<<1, 1024, 0, st>>>(fa);

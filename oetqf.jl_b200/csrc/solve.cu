@@ -26,6 +26,15 @@ __constant__ double cBtilde[7] = {-0.00178001105222577714, -0.000816434459656746
                                   -0.1447110071732629,     0.5823571654525552,     -0.45808210592918697,
                                   0.015151515151515152};
 
+static const double hA[7][6] = {
+    {0, 0, 0, 0, 0, 0},
+    {0.161, 0, 0, 0, 0, 0},
+    {-0.008480655492356989, 0.335480655492357, 0, 0, 0, 0},
+    {2.8971530571054935, -6.359448489975075, 4.3622954328695815, 0, 0, 0},
+    {5.325864828439257, -11.748883564062828, 7.4955393428898365, -0.09249506636175525, 0, 0},
+    {5.86145544294642, -12.92096931784711, 8.159367898576159, -0.071584973281401, -0.028269050394068383, 0},
+    {0.09646076681806523, 0.01, 0.4798896504144996, 1.379008574103742, -3.290069515436081, 2.324710524099774}};
+
 struct StepCtl {
     double t, dt, qold, eest, tstop, dtmax, reltol, abstol;
     double dt_last;
@@ -188,10 +197,12 @@ static int enqueue_step(OqProblem* p)
     Stages ks;
     for (int j = 0; j < 7; ++j) ks.k[j] = p->k[j].p;
     for (int s = 1; s <= 6; ++s) {
+        // stage combination y = u + dt Σ a_sj k_j is fused into the forcing kernel of the RHS evaluation
         double* y = s < 6 ? p->utmp.p : p->unew.p;
-        stage_kernel<<<blocks, 256, 0, st>>>(p->u.p, ks, s, s, ctl, n, y);
-        OQ_LAUNCHED();
-        OQ_TRY(rhs_device(p, y, p->k[s].p));
+        StageSpec sp;
+        sp.nk = s; sp.u = p->u.p; sp.dt = &ctl->dt;
+        for (int j = 0; j < s; ++j) { sp.k[j] = p->k[j].p; sp.a[j] = hA[s][j]; }
+        OQ_TRY(rhs_device(p, y, p->k[s].p, &sp));
     }
     ErrArgs ea{};
     ea.u = p->u.p; ea.unew = p->unew.p; ea.ks = ks; ea.ctl = ctl; ea.n = n; ea.errpart = p->errpart.p;

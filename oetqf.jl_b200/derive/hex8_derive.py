@@ -322,16 +322,27 @@ _printer = MulPrinter()
 
 
 def cse_block(assigns, prefix):
-    """assigns: list of (target string, expr) -> C lines with common subexpressions hoisted"""
-    repl, red = sp.cse([ex for _, ex in assigns], symbols=sp.numbered_symbols(prefix), optimizations="basic")
+    """assigns: list of (target string, expr, row mask) -> C lines with common subexpressions hoisted; each
+    accumulation is guarded by HEX8_NEED(mask) (rows of Q the function feeds) so that a caller needing only some
+    strain components compiles the rest away"""
+    repl, red = sp.cse([ex for _, ex, _ in assigns], symbols=sp.numbered_symbols(prefix), optimizations="basic")
     lines = [f"        const double {s_} = {_printer.doprint(ex)};" for s_, ex in repl]
-    for (tgt, _), ex in zip(assigns, red):
-        lines.append(f"        {tgt} += sgn * ({_printer.doprint(ex)});")
+    for (tgt, _, mask), ex in zip(assigns, red):
+        lines.append(f"        if (HEX8_NEED({mask})) {tgt} += sgn * ({_printer.doprint(ex)});")
     nops = count_ops([ex for _, ex in repl] + list(red))
     return lines, nops
 
 
-def emit_basis(keys, index, prefix):
+def row_masks(combos):
+    """bit a of the mask of a basis function is set if it contributes to strain row a (xx,xy,xz,yy,yz,zz)"""
+    m = {}
+    for n, c in enumerate(combos):
+        for key in c:
+            m[key] = m.get(key, 0) | (1 << (n // 6))
+    return m
+
+
+def emit_basis(keys, index, prefix, masks):
     """code accumulating sgn * basis function into ACC(index[key]), grouped by (potential, order) so that each
     group is a short block with its own common subexpressions (short live ranges, no spills)"""
     groups = {}
@@ -339,7 +350,7 @@ def emit_basis(keys, index, prefix):
         groups.setdefault((key[0], sum(key[1])), []).append(key)
     lines, total = [], 0
     for gi, (gname, gkeys) in enumerate(sorted(groups.items())):
-        assigns = [(f"ACC({index[key]})", TD(*key)) for key in gkeys]
+        assigns = [(f"ACC({index[key]})", TD(*key), masks[key]) for key in gkeys]
         blk, nops = cse_block(assigns, f"{prefix}{gi}_")
         lines.append(f"    {{   /* {gname[0]}, derivative order {gname[1]}: {len(gkeys)} functions */")
         lines += blk
@@ -377,8 +388,8 @@ def main():
     keys_i = sorted({k_ for c in ci for k_ in c})
     idx_r = {k_: n for n, k_ in enumerate(keys_r)}
     idx_i = {k_: n for n, k_ in enumerate(keys_i)}
-    body_r, ops_r = emit_basis(keys_r, idx_r, "r")
-    body_i, ops_i = emit_basis(keys_i, idx_i, "m")
+    body_r, ops_r = emit_basis(keys_r, idx_r, "r", row_masks(cr))
+    body_i, ops_i = emit_basis(keys_i, idx_i, "m", row_masks(ci))
     body_c, ops_c = emit_combine(cr, ci, idx_r, idx_i)
     print(f"real basis: {len(keys_r)} functions, {ops_r} ops/corner; image basis: {len(keys_i)} functions, "
           f"{ops_i} ops/corner; combination: {ops_c} ops/pair", file=sys.stderr)
@@ -387,7 +398,8 @@ def main():
               "// receiver depth x3 only) of corner sums of BASIS functions = derivatives of the triple antiderivatives\n"
               "// of P0 = 1/R, P1 = R, P3 = R - R3 ln(R+R3).  hex8_basis_* accumulate sgn * basis into ACC(b) for one\n"
               "// corner; hex8_combine turns the 8-corner sums into Q[(il),(jk)] (times 8*pi*mu), pairs xx,xy,xz,yy,yz,zz.\n"
-              "// The includer defines ACC(b) (accumulator b of the current function), ACCR(b)/ACCI(b) (real/image sums).\n"
+              "// The includer defines ACC(b) (accumulator b of the current function), ACCR(b)/ACCI(b) (real/image sums) and\n"
+              "// HEX8_NEED(mask) (non-zero if any strain row xx,xy,xz,yy,yz,zz = bit 0..5 of mask is wanted).\n"
               "// Inputs: R1,R2,R3 corner vector, R its norm, w_c = R+R_c, q_c = R^2-R_c^2, iR/iw_c/iq_c reciprocals,\n"
               "// L_c = ln(w_c), A_c = atan(R_a R_b/(R_c R)), Ba = atan(R1/R2), Bb = atan(R2/R1).\n"
               f"#define HEX8_NB_REAL {len(keys_r)}\n#define HEX8_NB_IMAGE {len(keys_i)}\n")

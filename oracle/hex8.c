@@ -17,6 +17,7 @@
 #include <string.h>
 
 #include "hex8_gen.inc"
+#define HEX8_NEED(mask) 1
 
 static void corner_inputs(double r1, double r2, double r3, double *R, double *w, double *q, double *L, double *A,
                           double *iR, double *iw, double *iq)

@@ -146,7 +146,7 @@ def test_edge_line_regularisation(gpu):
     nu = lam / 2 / (lam + mu)
     g = (781.25, 0.0, -20000.0, 1562.5, 1000.0, 1500.0)      # x in [0,1562.5], y in [0,1000], z in [-21500,-20000]
     eps = [0.3, 1.0, -0.2, 0.4, 0.5, -0.7]
-    pts = np.array([[0.0, 0.0, -125.0], [0.0, 0.0, -19875.0], [1562.5, 1000.0, -300.0], [0.0, 500.0, -20000.0]])
+    pts = np.array([[0.0, 0.0, -125.0], [0.0, 0.0, -19875.0], [1562.5, 1000.0, -300.0], [0.0, -500.0, -20000.0]])   # all on edge EXTENSIONS, none on an edge
     got = oq.stress_vol_hex8(pts[:, 0], pts[:, 1], pts[:, 2], *g, eps, mu, nu)
     assert np.all(np.isfinite(got))
     for p, s in zip(pts, got):
