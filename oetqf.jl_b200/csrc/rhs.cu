@@ -533,10 +533,15 @@ int rhs_device(OqProblem* p, const double* uin, double* du, const StageSpec* sta
         fa.off_eps = fa.off_sig = 0;
     }
     const int nthr = p->nfl > fa.nel ? p->nfl : fa.nel;
+    // single-rank, FFT form, no dense operand: the forward transform forms v - vpl itself (one launch fewer)
+    const bool direct_fft = p->gf11_form == OQ_GF11_FFT && p->kind != kViscoelastic && p->world == 1 && !stage &&
+                            !use_direct_toeplitz();
+    if (!direct_fft) {
     // small shards: ONE block (no cross-block handshake before the publication); large ones: 256-thread blocks
     if (nthr <= 4096) forcing_kernel<<<1, 1024, 0, st>>>(fa);
     else forcing_kernel<<<(nthr + 255) / 256, 256, 0, st>>>(fa);
     OQ_LAUNCHED();
+    }
     PeerWait pw{p->flags, p->epochs, p->world, p->rank};
     // 2. fault-fault interaction in its translation-invariant form (the reference's algorithm) when requested
     FaultEpilogue fe{};
@@ -554,18 +559,15 @@ int rhs_device(OqProblem* p, const double* uin, double* du, const StageSpec* sta
         } else {
             const int N = p->fftN, nfreq = N / 2 + 1;
             const size_t fsmem = 2 * (size_t)N * sizeof(cplx);
-            fft_forward_kernel<<<p->nxi, 256, fsmem, st>>>(p->relv, p->wl.relv_len, pw, p->nx, N,
-                                                         reinterpret_cast<cplx*>(p->Rhat.p));
-            OQ_LAUNCHED();
-            const size_t nt = (size_t)nfreq * p->fnj;
-            spectral_contract_kernel<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(
-                p->Ghat.p, reinterpret_cast<const cplx*>(p->Rhat.p), p->nxi, p->fnj, nfreq,
-                reinterpret_cast<cplx*>(p->That.p));
+            fft_forward_kernel<<<p->nxi, 256, fsmem, st>>>(p->relv, p->wl.relv_len, pw, direct_fft ? in.v : nullptr,
+                                                         p->fp.vpl, p->nx, N, reinterpret_cast<cplx*>(p->Rhat.p));
             OQ_LAUNCHED();
             // with no dense operand on the fault rows the pointwise physics is fused into the inverse transform
             const bool fuse = p->kind != kViscoelastic;
-            fft_inverse_kernel<<<p->fnj, 256, fsmem, st>>>(reinterpret_cast<const cplx*>(p->That.p), p->nx, N, p->fj0,
-                                                         p->f0, p->nfl, p->dtau0.p, fuse ? 1 : 0, fe);
+            (void)nfreq;
+            fft_inverse_kernel<<<p->fnj, 256, fsmem, st>>>(p->Ghat.p, reinterpret_cast<const cplx*>(p->Rhat.p), p->nxi,
+                                                         p->fnj, p->nx, N, p->fj0, p->f0, p->nfl, p->dtau0.p,
+                                                         fuse ? 1 : 0, fe);
             OQ_LAUNCHED();
             epilogue_done = fuse;
         }

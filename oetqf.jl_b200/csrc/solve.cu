@@ -6,6 +6,7 @@
 // run on the GPU; the host reads one small control record per step.  Semantics follow OrdinaryDiffEq:
 //   EEst = sqrt( mean_i ( err_i / (abstol + reltol*max(|uprev_i|,|u_i|)) )^2 ) over ALL state scalars,
 //   PI controller beta1 = 7/50, beta2 = 2/25, gamma = 0.9, qmin = 0.2, qmax = 10, qoldinit = 1e-4.
+#include <chrono>
 #include <cmath>
 
 #include "comm.cuh"
@@ -275,15 +276,33 @@ extern "C" int oq_solve(OqProblem* p, double t0, const OqSolveOptions* o, int64_
 
     const int64_t maxiters = o->maxiters > 0 ? o->maxiters : 1000000;
     int64_t iters = 0;
+    int64_t batch_cap = 1;
     while (!stop && !h.done && iters < maxiters) {
-        ce = cudaGraphLaunch(exec, p->stream);
+        // Launch as many steps as can pass before the next snapshot is due (all decisions are taken on the
+        // device; steps enqueued after completion are no-ops for the state), then read the control record once.
+        int64_t batch = fn ? stride - (h.naccept % stride) : 64;
+        if (batch > 64) batch = 64;
+        if (batch > batch_cap) batch = batch_cap;     // bound the work wasted past tstop to ~2 ms
+        if (batch > maxiters - iters) batch = maxiters - iters;
+        if (batch < 1) batch = 1;
+        const auto t_batch = std::chrono::steady_clock::now();
+        for (int64_t b = 0; b < batch && ce == cudaSuccess; ++b) {
+            ce = cudaGraphLaunch(exec, p->stream);
+            g_launches.fetch_add(per_step);
+        }
         if (ce != cudaSuccess) { rc = fail("cudaGraphLaunch: %s", cudaGetErrorString(ce)); break; }
-        g_launches.fetch_add(per_step);
+        const int64_t acc_before = h.naccept;
         ce = cudaMemcpyAsync(&h, p->ctl.p, sizeof(h), cudaMemcpyDeviceToHost, p->stream);
         if (ce == cudaSuccess) ce = cudaStreamSynchronize(p->stream);
         if (ce != cudaSuccess) { rc = fail("step failed: %s", cudaGetErrorString(ce)); break; }
-        ++iters;
-        if (h.accepted && (h.naccept % stride == 0 || h.done)) {
+        iters += batch;
+        {
+            const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_batch).count();
+            const double per_step = ms / (double)batch;
+            batch_cap = per_step > 0 ? (int64_t)(2.0 / per_step) : 64;
+            if (batch_cap < 1) batch_cap = 1;
+        }
+        if (h.naccept > acc_before && (h.naccept % stride == 0 || h.done)) {
             stop = snapshot(h.t, h.naccept);
             if (stop < 0) { rc = 1; break; }
         }

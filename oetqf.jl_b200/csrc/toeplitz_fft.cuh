@@ -57,15 +57,23 @@ toeplitz_spectrum_kernel(const double* __restrict__ st, int nx, int nxi, int N, 
 }
 
 // R[l][f] = FFT_N(zero-padded relv[:, l])[f],  f = 0..N/2
+// `v_direct` != nullptr (single rank, no dense operand needs the forcing vector): the forcing v - vpl is formed
+// here from the state and the separate forcing kernel is skipped.
 __global__ void __launch_bounds__(256)
-fft_forward_kernel(const double* relv0, size_t relv_stride, PeerWait pw, int nx, int N, cplx* __restrict__ Rh)
+fft_forward_kernel(const double* relv0, size_t relv_stride, PeerWait pw, const double* __restrict__ v_direct,
+                   double vpl, int nx, int N, cplx* __restrict__ Rh)
 {
     extern __shared__ __align__(16) unsigned char fsm[];
     cplx* a = reinterpret_cast<cplx*>(fsm);
     cplx* b = a + N;
-    const double* relv = relv0 + consumer_parity(pw) * relv_stride;
     const int l = blockIdx.x;
-    for (int k = threadIdx.x; k < N; k += blockDim.x) a[k] = {k < nx ? relv[k + (size_t)nx * l] : 0.0, 0.0};
+    if (v_direct) {
+        for (int k = threadIdx.x; k < N; k += blockDim.x)
+            a[k] = {k < nx ? v_direct[k + (size_t)nx * l] - vpl : 0.0, 0.0};
+    } else {
+        const double* relv = relv0 + consumer_parity(pw) * relv_stride;
+        for (int k = threadIdx.x; k < N; k += blockDim.x) a[k] = {k < nx ? relv[k + (size_t)nx * l] : 0.0, 0.0};
+    }
     __syncthreads();
     const cplx* r = stockham_fft(a, b, N);
     const int nfreq = N / 2 + 1;
@@ -91,21 +99,30 @@ spectral_contract_kernel(const double* __restrict__ Gh, const cplx* __restrict__
     Th[t] = {re, im};
 }
 
-// dτ[i, j0+jl] = real(IFFT_N(Hermitian extension of T[jl][:]))[i], i < nx; rows outside [f0, f0+nfl) are dropped
+// dτ[i, j0+jl] = real(IFFT_N(Hermitian extension of T[jl][:]))[i], i < nx; rows outside [f0, f0+nfl) are dropped.
+// The per-frequency contraction T[jl][f] = Σ_l Ĝ[l][jl][f] R[l][f] is done here by the CTA that transforms the
+// row (Ĝ is read exactly once per evaluation; R comes from L2).
 __global__ void __launch_bounds__(256)
-fft_inverse_kernel(const cplx* __restrict__ Th, int nx, int N, int j0, int f0, int nfl, double* __restrict__ dtau,
-                   int fuse_epilogue, FaultEpilogue fe)
+fft_inverse_kernel(const double* __restrict__ Gh, const cplx* __restrict__ Rh, int nxi, int nj, int nx, int N, int j0,
+                   int f0, int nfl, double* __restrict__ dtau, int fuse_epilogue, FaultEpilogue fe)
 {
     extern __shared__ __align__(16) unsigned char fsm[];
     cplx* a = reinterpret_cast<cplx*>(fsm);
     cplx* b = a + N;
     const int jl = blockIdx.x;
     const int nfreq = N / 2 + 1;
-    const cplx* T = Th + (size_t)jl * nfreq;
-    // ifft(X) = conj(fft(conj(X))) / N; X[N-f] = conj(X[f])
-    for (int k = threadIdx.x; k < N; k += blockDim.x) {
-        const cplx x = k < nfreq ? T[k] : cplx{T[N - k].re, -T[N - k].im};
-        a[k] = {x.re, -x.im};
+    for (int f = threadIdx.x; f < nfreq; f += blockDim.x) {
+        double re = 0.0, im = 0.0;
+#pragma unroll 4
+        for (int l = 0; l < nxi; ++l) {
+            const double g = Gh[((size_t)l * nj + jl) * nfreq + f];
+            const cplx r = Rh[(size_t)l * nfreq + f];
+            re = fma(g, r.re, re);
+            im = fma(g, r.im, im);
+        }
+        // ifft(X) = conj(fft(conj(X))) / N; X[N-f] = conj(X[f])
+        a[f] = {re, -im};
+        if (f > 0 && f < N - f) a[N - f] = {re, im};
     }
     __syncthreads();
     const cplx* r = stockham_fft(a, b, N);
