@@ -384,6 +384,10 @@ static int alloc_matrix(OqMatrix* M, int row_kind, int row_begin, int row_end, i
     M->global_rows = global_rows; M->cols = cols;
     M->local_rows = (row_kind == OQ_ROWS_MANTLE ? 6 : 1) * (row_end - row_begin);
     M->ld = round_up((size_t)cols, 16);
+    // A leading dimension that is a multiple of 8 KB makes every row of a chunk (and every CTA's stream) start
+    // on the same HBM channel phase; one extra 128-byte line per row spreads them (OQ_LD_PAD=0 disables).
+    static const bool pad = [] { const char* e = getenv("OQ_LD_PAD"); return !(e && e[0] == '0'); }();
+    if (pad && M->ld % 1024 == 0) M->ld += 16;
     return M->d.alloc((size_t)M->local_rows * M->ld);
 }
 

@@ -108,13 +108,18 @@ __global__ void __launch_bounds__(1024) forcing_kernel(const __grid_constant__ F
     __shared__ int last;
     __syncthreads();
     if (threadIdx.x == 0) {
-        if (world > 1) __threadfence_system(); else __threadfence();
-        const unsigned long long prev = atomicAdd(&a.epochs[kEpBlocksF], 1ull);
-        last = (prev == (unsigned long long)gridDim.x - 1ull);
+        if (gridDim.x == 1) {
+            last = 1;                                  // single block: no cross-block handshake
+            if (world > 1) __threadfence_system();
+        } else {
+            if (world > 1) __threadfence_system(); else __threadfence();
+            const unsigned long long prev = atomicAdd(&a.epochs[kEpBlocksF], 1ull);
+            last = (prev == (unsigned long long)gridDim.x - 1ull);
+        }
     }
     __syncthreads();
     if (last && threadIdx.x == 0) {
-        a.epochs[kEpBlocksF] = 0ull;
+        if (gridDim.x > 1) a.epochs[kEpBlocksF] = 0ull;
         if (world > 1) {
             if (gridDim.x > 1) __threadfence_system();     // acquire the other blocks' publications
             for (int r = 0; r < world; ++r) {
@@ -123,8 +128,8 @@ __global__ void __launch_bounds__(1024) forcing_kernel(const __grid_constant__ F
                 publish_flag(f + a.peers.rank, ep + 1ull);
             }
         }
-        __threadfence();
-        a.epochs[kEpForcing] = ep + 1ull;
+        if (gridDim.x > 1) __threadfence();
+        a.epochs[kEpForcing] = ep + 1ull;              // read by the next kernel in stream order
     }
 }
 
