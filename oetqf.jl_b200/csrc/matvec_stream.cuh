@@ -2,13 +2,17 @@
 //
 // One CTA per SM.  The work of a launch is the flat sequence of CHUNKS (kStR rows x kStCH columns of one
 // operand) of every row block of both row sets (fault rows: G11|G21, mantle rows: G12|G22); CTA b owns the
-// contiguous span [b*T/G, (b+1)*T/G) of it, so the load is balanced to one chunk.  A producer warp streams each
-// chunk -- kStR row pieces of the matrix plus the matching piece of the forcing vector -- into a ring of
-// kStStages shared-memory stages with 1-D bulk TMA copies (cp.async.bulk -> SASS UBLKCP) completing on
-// mbarriers; 8 consumer warps multiply-accumulate out of shared memory.  In-flight HBM bytes live in shared
-// memory (kStStages x 40 KB per SM), not in registers, and the pipeline never drains between row blocks.
-// Row blocks that straddle two CTAs write partial sums; the last arriver folds them in a fixed order
-// (deterministic) and applies the pointwise physics (rhs.cu: update_fault_row / stress-rate store).
+// contiguous span [b*T/G, (b+1)*T/G) of it, so the load is balanced to one chunk.  Three roles per CTA:
+//   producer warp   streams each chunk -- kStR row pieces of the matrix plus the matching piece of the forcing
+//                   vector -- into a ring of kStStages shared-memory stages with 1-D bulk TMA copies
+//                   (cp.async.bulk -> SASS UBLKCP) completing on mbarriers;
+//   8 consumer warps multiply-accumulate out of shared memory; at the end of a row block they only drop their
+//                   partial sums into a double-buffered slot and keep streaming;
+//   epilogue warp   folds the 8 partial sums (fixed order), merges row blocks that straddle two CTAs (the last
+//                   arriver sums the slots in a fixed order: bitwise deterministic) and applies the pointwise
+//                   physics (rhs.cu: update_fault_row / stress-rate store) off the streaming path.
+// In-flight HBM bytes live in shared memory (kStStages x 40 KB per SM), not in registers, and neither the
+// reduction nor the physics ever drains the pipeline.
 #pragma once
 
 namespace oq {
@@ -16,27 +20,32 @@ namespace oq {
 constexpr int kStR = 4;            // rows per row block
 constexpr int kStCH = 1024;        // columns per chunk
 constexpr int kStStages = 5;
-constexpr int kStConsumers = 256;  // 8 consumer warps; warp 8 is the producer
-constexpr int kStThreads = kStConsumers + 32;
+constexpr int kStConsumers = 256;  // 8 consumer warps; warp 8 = producer, warp 9 = epilogue
+constexpr int kStCWarps = kStConsumers / 32;
+constexpr int kStThreads = kStConsumers + 64;
 constexpr int kStStageDoubles = (kStR + 1) * kStCH;
 constexpr size_t kStSmemBytes = (size_t)kStStages * kStStageDoubles * sizeof(double) + 1024;
 
-struct ChunkRef {
-    int job, rb, op, ch;       // row set, row block, operand, chunk index inside the operand
+// position in the flat chunk sequence, advanced incrementally (no per-chunk 64-bit divisions)
+struct ChunkCursor {
+    int job, rb, rem;          // row set, row block, chunk index inside the row block
+    __device__ __forceinline__ void seek(const MatvecArgs& a, long long g)
+    {
+        job = (g >= a.job[1].chunk_begin && a.job[1].nrb > 0) ? 1 : 0;
+        if (a.job[0].nrb == 0) job = 1;
+        const MatvecJob& j = a.job[job];
+        const long long loc = g - j.chunk_begin;
+        rb = (int)(loc / j.chunks_per_rb);
+        rem = (int)(loc - (long long)rb * j.chunks_per_rb);
+    }
+    __device__ __forceinline__ void next(const MatvecArgs& a)
+    {
+        if (++rem == a.job[job].chunks_per_rb) {
+            rem = 0;
+            if (++rb == a.job[job].nrb) { rb = 0; job = 1; }
+        }
+    }
 };
-
-__device__ __forceinline__ ChunkRef decode_chunk(const MatvecArgs& a, long long g)
-{
-    ChunkRef c;
-    c.job = g >= a.job[1].chunk_begin && a.job[1].nrb > 0 ? 1 : 0;
-    const MatvecJob& j = a.job[c.job];
-    const long long loc = g - j.chunk_begin;
-    c.rb = (int)(loc / j.chunks_per_rb);
-    int rem = (int)(loc - (long long)c.rb * j.chunks_per_rb);
-    c.op = rem < j.nch[0] ? 0 : 1;
-    c.ch = c.op ? rem - j.nch[0] : rem;
-    return c;
-}
 
 __device__ __forceinline__ long long span_begin(long long total, int grid, int b)
 {
@@ -52,19 +61,15 @@ __device__ __forceinline__ int owner_of(long long total, int grid, long long g)
     return b;
 }
 
-__device__ __forceinline__ void consumer_sync()
-{
-    asm volatile("bar.sync 1, %0;" ::"n"(kStConsumers) : "memory");
-}
-
 __global__ void __launch_bounds__(kStThreads, 1)
 matvec_stream_kernel(const __grid_constant__ MatvecArgs args)
 {
     extern __shared__ __align__(128) double smem[];
     __shared__ __align__(8) uint64_t full_bar[kStStages];
     __shared__ __align__(8) uint64_t empty_bar[kStStages];
-    __shared__ double red[kStConsumers / 32][kStR];
-    __shared__ int is_last;
+    __shared__ __align__(8) uint64_t red_full[2];
+    __shared__ __align__(8) uint64_t red_empty[2];
+    __shared__ double red[2][kStCWarps][kStR];
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -77,24 +82,25 @@ matvec_stream_kernel(const __grid_constant__ MatvecArgs args)
 #pragma unroll
         for (int s = 0; s < kStStages; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], kStConsumers / 32);
+            mbar_init(&empty_bar[s], kStCWarps);
         }
+        mbar_init(&red_full[0], kStCWarps); mbar_init(&red_full[1], kStCWarps);
+        mbar_init(&red_empty[0], 1); mbar_init(&red_empty[1], 1);
         fence_mbar_init();
     }
     __syncthreads();
+    if (g_begin >= g_end) return;
 
-    if (warp == kStConsumers / 32) {
+    if (warp == kStCWarps) {
         // ------------------------------------------------------------------ producer warp
         if (lane == 0) {
             // The matrix does not depend on this evaluation's forcing vector: the first ring of matrix pieces is
-            // requested BEFORE waiting for the peers' publication, so the flag latency hides behind HBM traffic.
-            int stage = 0;
-            unsigned phase = 0;
-            auto issue = [&](long long g, int stg, bool matrix, bool vector, size_t par) {
-                const ChunkRef c = decode_chunk(args, g);
+            // requested BEFORE waiting for the forcing kernel / the peers' publication.
+            auto issue = [&](const ChunkCursor& c, int stg, bool matrix, bool vector, size_t par) {
                 const MatvecJob& j = args.job[c.job];
-                const MatOperand& op = j.op[c.op];
-                const int c0 = c.ch * kStCH;
+                const int osel = c.rem < j.nch[0] ? 0 : 1;
+                const MatOperand& op = j.op[osel];
+                const int c0 = (osel ? c.rem - j.nch[0] : c.rem) * kStCH;
                 const int ncol = min(kStCH, (int)op.ld - c0);
                 const unsigned bytes = (unsigned)(ncol * sizeof(double));
                 double* dst = smem + (size_t)stg * kStStageDoubles;
@@ -108,9 +114,12 @@ matvec_stream_kernel(const __grid_constant__ MatvecArgs args)
                 }
                 if (vector) tma_load_1d(dst + kStR * kStCH, op.x + par * op.x_stride + c0, bytes, &full_bar[stg]);
             };
-            long long g = g_begin;
-            const long long g_pre = min(g_end, g_begin + kStStages);
-            for (; g < g_pre; ++g) issue(g, (int)(g - g_begin), true, false, 0);
+            ChunkCursor cur, pre;
+            cur.seek(args, g_begin);
+            pre = cur;
+            const int npre = (int)min((long long)kStStages, g_end - g_begin);
+            for (int s = 0; s < npre; ++s) { issue(cur, s, true, false, 0); cur.next(args); }
+            pdl_wait();                               // the forcing kernel (predecessor) is complete from here on
             size_t par = 0;
             if (args.pw.epochs) {
                 const unsigned long long ep = *(volatile unsigned long long*)(args.pw.epochs + kEpForcing);
@@ -120,14 +129,81 @@ matvec_stream_kernel(const __grid_constant__ MatvecArgs args)
                 }
                 par = (size_t)((ep - 1ull) & 1ull);
             }
-            for (long long h = g_begin; h < g_pre; ++h) issue(h, (int)(h - g_begin), false, true, par);
-            stage = (int)((g_pre - g_begin) % kStStages);
-            phase = (g_pre - g_begin) >= kStStages ? 1u : 0u;
-            for (; g < g_end; ++g) {
+            for (int s = 0; s < npre; ++s) { issue(pre, s, false, true, par); pre.next(args); }
+            int stage = npre % kStStages;
+            unsigned phase = npre >= kStStages ? 1u : 0u;
+            for (long long g = g_begin + npre; g < g_end; ++g) {
                 mbar_wait(&empty_bar[stage], phase ^ 1u);
-                issue(g, stage, true, true, par);
+                issue(cur, stage, true, true, par);
+                cur.next(args);
                 if (++stage == kStStages) { stage = 0; phase ^= 1u; }
             }
+        }
+        return;
+    }
+
+    if (warp == kStCWarps + 1) {
+        // ------------------------------------------------------------------ epilogue warp
+        pdl_wait();                                   // the physics reads the predecessor's state
+        ChunkCursor c;
+        c.seek(args, g_begin);
+        long long g = g_begin;
+        int buf = 0;
+        unsigned rphase[2] = {0u, 0u};
+        while (g < g_end) {
+            const int jb = c.job, rb = c.rb;
+            const MatvecJob& j = args.job[jb];
+            // chunks of this row block inside my span
+            const long long rb_g0 = j.chunk_begin + (long long)rb * j.chunks_per_rb;
+            const long long rb_g1 = rb_g0 + j.chunks_per_rb;
+            const long long my_end = rb_g1 < g_end ? rb_g1 : g_end;
+            mbar_wait(&red_full[buf], rphase[buf]);   // all consumer warps have dropped their partial sums
+            rphase[buf] ^= 1u;
+            const int myrow = rb * kStR + lane;
+            const bool active = lane < kStR && myrow < j.nrows;
+            double mine = 0.0;
+            if (lane < kStR) {
+#pragma unroll
+                for (int w = 0; w < kStCWarps; ++w) mine += red[buf][w][lane];
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&red_empty[buf]);          // consumers may reuse the slot
+            buf ^= 1;
+            // contributors: only a row block cut by a span boundary has more than one
+            int first = blockIdx.x, last = blockIdx.x;
+            if (rb_g0 < g_begin) first = owner_of(total, grid, rb_g0);
+            if (rb_g1 > g_end) last = owner_of(total, grid, rb_g1 - 1);
+            const int ncontrib = last - first + 1;
+            bool do_epilogue = true;
+            if (ncontrib > 1) {
+                const int slot = (int)blockIdx.x - first;
+                if (active) j.partial[((size_t)myrow) * j.slots + slot] = mine;
+                __threadfence();
+                __syncwarp();
+                unsigned prev = 0;
+                if (lane == 0) {
+                    prev = atomicAdd(&j.counters[rb], 1u);
+                    if (prev == (unsigned)ncontrib - 1u) j.counters[rb] = 0u;   // re-arm for the next evaluation
+                }
+                prev = __shfl_sync(0xffffffffu, prev, 0);
+                do_epilogue = (prev == (unsigned)ncontrib - 1u);
+                if (do_epilogue) {
+                    __threadfence();
+                    if (active) {
+                        mine = 0.0;
+                        const double* pp = j.partial + (size_t)myrow * j.slots;
+                        for (int q = 0; q < ncontrib; ++q) mine += ld_cg(pp + q);   // fixed order: deterministic
+                    }
+                }
+            }
+            if (do_epilogue && active) {
+                if (j.y0) mine += j.y0[myrow];
+                if (j.epilogue == kEpiFault) update_fault_row(args.fe, myrow, mine);
+                else j.yout[myrow] = mine;
+            }
+            // advance to the next row block of my span
+            g = my_end;
+            if (g < g_end) c.seek(args, g);
         }
         return;
     }
@@ -136,74 +212,17 @@ matvec_stream_kernel(const __grid_constant__ MatvecArgs args)
     double acc[kStR];
 #pragma unroll
     for (int r = 0; r < kStR; ++r) acc[r] = 0.0;
-    int cur_job = -1, cur_rb = -1;
-    int stage = 0;
+    ChunkCursor c;
+    c.seek(args, g_begin);
+    int stage = 0, buf = 0;
     unsigned phase = 0;
-
-    auto finalize = [&](int jb, int rb) {
-        const MatvecJob& j = args.job[jb];
-#pragma unroll
-        for (int r = 0; r < kStR; ++r) {
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], off);
-        }
-        if (lane == 0) {
-#pragma unroll
-            for (int r = 0; r < kStR; ++r) red[warp][r] = acc[r];
-        }
-        consumer_sync();
-        const int myrow = rb * kStR + tid;
-        const bool active = tid < kStR && myrow < j.nrows;
-        double mine = 0.0;
-        if (active) {
-#pragma unroll
-            for (int w = 0; w < kStConsumers / 32; ++w) mine += red[w][tid];
-        }
-        // which CTAs contribute to this row block?
-        const long long rb_g0 = j.chunk_begin + (long long)rb * j.chunks_per_rb;
-        const long long rb_g1 = rb_g0 + j.chunks_per_rb;
-        const int first = owner_of(total, grid, rb_g0), last = owner_of(total, grid, rb_g1 - 1);
-        const int ncontrib = last - first + 1;
-        bool do_epilogue = true;
-        if (ncontrib > 1) {
-            const int slot = (int)blockIdx.x - first;
-            if (active) j.partial[((size_t)myrow) * j.slots + slot] = mine;
-            __threadfence();
-            consumer_sync();
-            if (tid == 0) {
-                const unsigned prev = atomicAdd(&j.counters[rb], 1u);
-                is_last = (prev == (unsigned)ncontrib - 1u);
-                if (is_last) j.counters[rb] = 0u;                 // re-arm for the next evaluation
-            }
-            consumer_sync();
-            do_epilogue = is_last != 0;
-            if (do_epilogue) {
-                __threadfence();
-                if (active) {
-                    mine = 0.0;
-                    const double* pp = j.partial + (size_t)myrow * j.slots;
-                    for (int q = 0; q < ncontrib; ++q) mine += ld_cg(pp + q);   // fixed order: deterministic
-                }
-            }
-        }
-        if (do_epilogue && active) {
-            if (j.y0) mine += j.y0[myrow];
-            if (j.epilogue == kEpiFault) update_fault_row(args.fe, myrow, mine);
-            else j.yout[myrow] = mine;
-        }
-        consumer_sync();                                           // red[] / is_last are reused
-#pragma unroll
-        for (int r = 0; r < kStR; ++r) acc[r] = 0.0;
-    };
+    unsigned ephase[2] = {0u, 0u};
 
     for (long long g = g_begin; g < g_end; ++g) {
-        const ChunkRef c = decode_chunk(args, g);
-        if (c.job != cur_job || c.rb != cur_rb) {
-            if (cur_rb >= 0) finalize(cur_job, cur_rb);
-            cur_job = c.job; cur_rb = c.rb;
-        }
-        const MatOperand& op = args.job[c.job].op[c.op];
-        const int ncol = min(kStCH, (int)op.ld - c.ch * kStCH);
+        const MatvecJob& j = args.job[c.job];
+        const int osel = c.rem < j.nch[0] ? 0 : 1;
+        const MatOperand& op = j.op[osel];
+        const int ncol = min(kStCH, (int)op.ld - (osel ? c.rem - j.nch[0] : c.rem) * kStCH);
         mbar_wait(&full_bar[stage], phase);
         const double2* s2 = reinterpret_cast<const double2*>(smem + (size_t)stage * kStStageDoubles);
 #pragma unroll
@@ -222,8 +241,27 @@ matvec_stream_kernel(const __grid_constant__ MatvecArgs args)
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty_bar[stage]);
         if (++stage == kStStages) { stage = 0; phase ^= 1u; }
+        // end of the row block (or of my span): hand the partial sums to the epilogue warp and keep streaming
+        const bool rb_end = (c.rem + 1 == j.chunks_per_rb) || (g + 1 == g_end);
+        if (rb_end) {
+#pragma unroll
+            for (int r = 0; r < kStR; ++r) {
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], off);
+            }
+            if (lane == 0) {
+                mbar_wait(&red_empty[buf], ephase[buf] ^ 1u);     // slot free (always, except pathologically)
+#pragma unroll
+                for (int r = 0; r < kStR; ++r) red[buf][warp][r] = acc[r];
+                mbar_arrive(&red_full[buf]);                      // release: the stores above are visible
+            }
+            ephase[buf] ^= 1u;
+            buf ^= 1;
+#pragma unroll
+            for (int r = 0; r < kStR; ++r) acc[r] = 0.0;
+        }
+        c.next(args);
     }
-    if (cur_rb >= 0) finalize(cur_job, cur_rb);
 }
 
 }  // namespace oq

@@ -43,6 +43,7 @@ struct ForcingArgs {
 
 __global__ void __launch_bounds__(1024) forcing_kernel(const __grid_constant__ ForcingArgs a)
 {
+    pdl_launch_dependents();       // the matvec may start (and prefetch its matrix chunks) while we compute
     // buffer copy for this evaluation: parity of the number of publications so far
     const unsigned long long ep = a.epochs[kEpForcing];
     const size_t par = (size_t)(ep & 1ull);
@@ -487,7 +488,16 @@ int launch_matvec(MatvecArgs& a, cudaStream_t stream)
                                          (int)kStSmemBytes));
             stream_attr_set = true;
         }
-        matvec_stream_kernel<<<grid, kStThreads, kStSmemBytes, stream>>>(a);
+        // programmatic dependent launch: start while the forcing kernel still runs; the kernel prefetches its
+        // first ring of matrix chunks and only then waits for the predecessor (pdl_wait)
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kStThreads);
+        cfg.dynamicSmemBytes = kStSmemBytes; cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        OQ_CUDA(cudaLaunchKernelEx(&cfg, matvec_stream_kernel, a));
         OQ_LAUNCHED();
         return 0;
     }

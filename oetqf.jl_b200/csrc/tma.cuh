@@ -63,6 +63,19 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
         : "memory");
 }
 
+// Programmatic dependent launch: a kernel launched with programmatic stream serialisation may start while its
+// predecessor still runs; it must execute pdl_wait() before touching anything the predecessor produces.
+__device__ __forceinline__ void pdl_wait()
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+// lets the dependent kernel of this grid start launching now (its pdl_wait still waits for our completion)
+__device__ __forceinline__ void pdl_launch_dependents()
+{
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // streaming 128-bit load of matrix data: read-only path, do not allocate in L1 (each byte is used once)
 __device__ __forceinline__ double2 ldg_stream(const double* p)
 {
