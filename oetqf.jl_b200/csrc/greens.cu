@@ -59,8 +59,11 @@ __device__ __forceinline__ double shear_traction_stress(int slip, const double (
 // ---- K1: fault -> fault, Toeplitz-unique entries st[i,j,l] (GF.jl:41-58) -------------------------
 // thread t -> (i, j, l) with i fastest: writes are coalesced, the receiver depth (j) and the source
 // row (l) are warp-uniform for nx >= 32 so the EPS / edge branches of the closed form do not diverge.
+#ifndef OQ_OKADA_MINB
+#define OQ_OKADA_MINB 4      // resident CTAs per SM the Okada kernels are compiled for (caps registers at 128; measured fastest)
+#endif
 template <int SLIP>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, OQ_OKADA_MINB)
 gf_fault_fault_kernel(FaultGeom f, OkadaParams p, double* __restrict__ st)
 {
     extern __shared__ double sm[];
@@ -137,7 +140,7 @@ toeplitz_dft_kernel(const double* __restrict__ st, int nx, int npairs, double* _
 // ---- K2: fault -> mantle (GF.jl:123-174) -----------------------------------------------------------
 // thread t -> (source fault cell j fastest, receiver element e); writes row-major G[(k*nel+el), j].
 template <int SLIP>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, OQ_OKADA_MINB)
 gf_fault_mantle_kernel(FaultGeom f, Hex8Geom a, OkadaParams p, const double* __restrict__ qc,
                        const double* __restrict__ qw, int nq, int e_begin, int nel, size_t ld,
                        double* __restrict__ G)

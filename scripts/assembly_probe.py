@@ -9,7 +9,7 @@ from oetqf_b200 import gf as gfmod
 oq.init(0)
 fs = W.C3_FAULT
 mf = oq.gen_mesh("RectOkada", fs.x, fs.xi, fs.dx, fs.dxi, fs.dip)
-for ft in (oq.StrikeSlip(), oq.DipSlip()):
+for ft in (oq.StrikeSlip(), oq.DipSlip(), oq.StrikeSlip(), oq.DipSlip()):
     st = oq.stress_greens_function(mf, W.LAM, W.MU, buffer_ratio=1.0, fourier=False, ftype=ft)
     print("K1", type(ft).__name__, gfmod.last_kernel_ms["value"], "ms", st.size / gfmod.last_kernel_ms["value"] * 1e3, "entries/s")
 fsm = W.FaultSpec(64e3, 16e3, 1000.0, 1000.0)
