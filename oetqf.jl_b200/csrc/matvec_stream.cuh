@@ -71,6 +71,7 @@ matvec_stream_kernel(const __grid_constant__ MatvecArgs args)
     __shared__ __align__(8) uint64_t red_empty[2];
     __shared__ double red[2][kStCWarps][kStR];
 
+    if (args.done && *reinterpret_cast<const volatile int*>(args.done)) return;   // integration already complete
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const long long total = args.total_chunks;

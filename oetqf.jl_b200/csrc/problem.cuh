@@ -113,6 +113,7 @@ struct StageSpec {
     const double* k[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     double a[6] = {0, 0, 0, 0, 0, 0};
     const double* dt = nullptr;      // device scalar (the controller's current step)
+    const int* done = nullptr;       // device flag: the integration is complete, the evaluation is skipped
 };
 
 StateView view_of(const OqProblem* p, double* base);

@@ -43,6 +43,9 @@ struct ForcingArgs {
 
 __global__ void __launch_bounds__(1024) forcing_kernel(const __grid_constant__ ForcingArgs a)
 {
+    // steps enqueued past the end of the integration do nothing -- identically on every rank, so the epoch
+    // protocol stays in lockstep
+    if (a.stage.nk > 0 && a.stage.done && *a.stage.done) return;
     pdl_launch_dependents();       // the matvec may start (and prefetch its matrix chunks) while we compute
     // buffer copy for this evaluation: parity of the number of publications so far
     const unsigned long long ep = a.epochs[kEpForcing];
@@ -258,6 +261,7 @@ struct MatvecArgs {
     FaultEpilogue fe;
     PeerWait pw;
     long long total_chunks;
+    const int* done;      // optional device flag: skip the evaluation (integration complete)
 };
 
 __global__ void __launch_bounds__(kMvThreads)
@@ -592,6 +596,7 @@ int rhs_device(OqProblem* p, const double* uin, double* du, const StageSpec* sta
     MatvecArgs a{};
     a.fe = fe;
     a.pw = pw;
+    a.done = stage ? stage->done : nullptr;
     a.job[0].op[0] = p->opf[0]; a.job[0].op[1] = p->opf[1];
     a.job[0].partial = p->partial_f.p; a.job[0].counters = p->counters.p;
     a.job[0].y0 = y0; a.job[0].epilogue = kEpiFault;

@@ -6,7 +6,6 @@
 // run on the GPU; the host reads one small control record per step.  Semantics follow OrdinaryDiffEq:
 //   EEst = sqrt( mean_i ( err_i / (abstol + reltol*max(|uprev_i|,|u_i|)) )^2 ) over ALL state scalars,
 //   PI controller beta1 = 7/50, beta2 = 2/25, gamma = 0.9, qmin = 0.2, qmax = 10, qoldinit = 1e-4.
-#include <chrono>
 #include <cmath>
 
 #include "comm.cuh"
@@ -79,6 +78,7 @@ __global__ void __launch_bounds__(256) error_kernel(const __grid_constant__ ErrA
 {
     __shared__ double red[8];
     __shared__ int last;
+    if (a.ctl->done) return;          // steps enqueued past completion do nothing (identically on every rank)
     const double dt = a.ctl->dt, atol = a.ctl->abstol, rtol = a.ctl->reltol;
     double s = 0.0;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (size_t)gridDim.x * blockDim.x) {
@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(256)
 accept_kernel(const StepCtl* __restrict__ ctl, size_t n, const double* __restrict__ unew,
               const double* __restrict__ k7, double* __restrict__ u, double* __restrict__ k1)
 {
-    if (!ctl->accepted) return;
+    if (!ctl->accepted) return;      // (the controller clears `accepted` for steps enqueued past completion)
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { u[i] = unew[i]; k1[i] = k7[i]; }
 }
@@ -201,7 +201,7 @@ static int enqueue_step(OqProblem* p)
         // stage combination y = u + dt Σ a_sj k_j is fused into the forcing kernel of the RHS evaluation
         double* y = s < 6 ? p->utmp.p : p->unew.p;
         StageSpec sp;
-        sp.nk = s; sp.u = p->u.p; sp.dt = &ctl->dt;
+        sp.nk = s; sp.u = p->u.p; sp.dt = &ctl->dt; sp.done = &ctl->done;
         for (int j = 0; j < s; ++j) { sp.k[j] = p->k[j].p; sp.a[j] = hA[s][j]; }
         OQ_TRY(rhs_device(p, y, p->k[s].p, &sp));
     }
@@ -276,16 +276,16 @@ extern "C" int oq_solve(OqProblem* p, double t0, const OqSolveOptions* o, int64_
 
     const int64_t maxiters = o->maxiters > 0 ? o->maxiters : 1000000;
     int64_t iters = 0;
-    int64_t batch_cap = 1;
+    const int64_t kMaxBatch = 16;    // steps enqueued after completion exit at their first instruction (ctl.done)
     while (!stop && !h.done && iters < maxiters) {
         // Launch as many steps as can pass before the next snapshot is due (all decisions are taken on the
         // device; steps enqueued after completion are no-ops for the state), then read the control record once.
-        int64_t batch = fn ? stride - (h.naccept % stride) : 64;
-        if (batch > 64) batch = 64;
-        if (batch > batch_cap) batch = batch_cap;     // bound the work wasted past tstop to ~2 ms
+        // (the batch size must be a pure function of the control record: every rank of a multi-GPU run has to
+        // enqueue exactly the same sequence of kernels, or the peers' epoch flags would never match)
+        int64_t batch = fn ? stride - (h.naccept % stride) : kMaxBatch;
+        if (batch > kMaxBatch) batch = kMaxBatch;
         if (batch > maxiters - iters) batch = maxiters - iters;
         if (batch < 1) batch = 1;
-        const auto t_batch = std::chrono::steady_clock::now();
         for (int64_t b = 0; b < batch && ce == cudaSuccess; ++b) {
             ce = cudaGraphLaunch(exec, p->stream);
             g_launches.fetch_add(per_step);
@@ -296,12 +296,6 @@ extern "C" int oq_solve(OqProblem* p, double t0, const OqSolveOptions* o, int64_
         if (ce == cudaSuccess) ce = cudaStreamSynchronize(p->stream);
         if (ce != cudaSuccess) { rc = fail("step failed: %s", cudaGetErrorString(ce)); break; }
         iters += batch;
-        {
-            const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_batch).count();
-            const double per_step = ms / (double)batch;
-            batch_cap = per_step > 0 ? (int64_t)(2.0 / per_step) : 64;
-            if (batch_cap < 1) batch_cap = 1;
-        }
         if (h.naccept > acc_before && (h.naccept % stride == 0 || h.done)) {
             stop = snapshot(h.t, h.naccept);
             if (stop < 0) { rc = 1; break; }
