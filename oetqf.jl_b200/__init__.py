@@ -7,7 +7,9 @@ include/oetqf_b200.h.  There is no CPU fallback.
 from . import _lib, dist
 from ._lib import OqError, init, kernel_launch_count, measure_fp64_peak, measure_hbm_copy
 from .equation import ArrayPartition, DeviceProblem, ODEProblem, ODESolution, Tsit5, assemble, ode, solve
-from .gf import (DeviceMatrix, DipSlip, StrikeSlip, dc3d_gradient, device_fault_fault, device_fault_mantle,
+from . import io
+from .io import wsolve
+from .gf import (max_real_eigval, DeviceMatrix, DipSlip, StrikeSlip, dc3d_gradient, device_fault_fault, device_fault_mantle,
                  device_from_host, device_mantle_fault, device_mantle_mantle, gauss_legendre_hex,
                  get_quadrature, stress_greens_function, stress_vol_hex8)
 from .mesh import BEMHex8Mesh, RectOkadaMesh, gen_box_hex8, gen_mesh

@@ -249,3 +249,17 @@ def stress_vol_hex8(x, y, z, qx, qy, qz, dx, dy, dz, eps, mu, nu):
     _lib.check(_lib.load().oq_stress_vol_hex8(x.size, _lib.dptr(x), _lib.dptr(y), _lib.dptr(z), d(qx), d(qy), d(qz),
                                               d(dx), d(dy), d(dz), _lib.dptr(e), d(mu), d(nu), _lib.dptr(out)))
     return out
+
+
+def max_real_eigval(dm: "DeviceMatrix", k: int = 1, tol: float = 1e-6, maxiter: int = 300) -> float:
+    """Largest real part of the spectrum of a square device matrix by implicitly restarted Arnoldi
+    (scipy.sparse.linalg.eigs, which='LR') with the matvecs on the GPU (oq_gemv).
+
+    Replaces the reference's O(n^3) `maximum(real, eigvals(st))` print (GF.jl:291-294), which is unusable
+    beyond ~1e4 rows; needs the full matrix on this rank (local_rows == cols)."""
+    from scipy.sparse.linalg import LinearOperator, eigs
+    assert dm.local_rows == dm.cols == dm.global_rows, "needs the whole square matrix on this rank"
+    op = LinearOperator((dm.cols, dm.cols), matvec=lambda x: dm.gemv(np.ascontiguousarray(x, dtype=np.float64)),
+                        dtype=np.float64)
+    vals = eigs(op, k=k, which="LR", tol=tol, maxiter=maxiter, return_eigenvectors=False)
+    return float(np.max(vals.real))

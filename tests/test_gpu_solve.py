@@ -110,3 +110,53 @@ def test_stride_and_callback(gpu):
         want.append(full.t[-1])            # the final state is always delivered
     np.testing.assert_allclose([s[0] for s in seen], want, rtol=0)
     assert np.array_equal(strided.u[0].x[0], full.u[0].x[0])
+
+
+def test_wsolve_store_append_stride(gpu, tmp_path):
+    """test/tests.jl:1-42 restated: wsolve output == solve output, appended storage, strided storage"""
+    oq = gpu
+    nx, nxi = 4, 3
+    rng = np.random.default_rng(2)
+    a, b, L, sig = (rng.uniform(0.5, 1.5, (nx, nxi)) for _ in range(4))
+    v, th, dl = (rng.uniform(0.5, 1.5, (nx, nxi)) for _ in range(3))
+    st = np.zeros((nx, nxi, nxi), order="F")
+    pf = oq.RateStateQuasiDynamicProperty(a, b, L, sig, 0.7, 0.3, 0.6, 0.9)
+    u0 = oq.ArrayPartition(v, th, dl)
+    kw = dict(reltol=1e-8, abstol=1e-10, dt=1e-3)
+    prob = oq.assemble(st, pf, u0, (0.0, 2.0))
+    sol = oq.solve(prob, oq.Tsit5(), **kw)
+    f = str(tmp_path / "out")
+    names = ["u1", "u2", "u3"]
+    oq.wsolve(prob, oq.Tsit5(), f, 7, oq.io.VThetaDelta, names, "t", **kw)
+    assert np.array_equal(oq.io.read(f, "t"), np.array(sol.t))
+    for m, n in enumerate(names):
+        x = np.stack([u.x[m] for u in sol.u], axis=-1)
+        assert np.array_equal(oq.io.read(f, n), x)
+    # refusing to overwrite without force (io.jl:119-123)
+    assert oq.wsolve(prob, oq.Tsit5(), f, 7, oq.io.VThetaDelta, names, "t", **kw) is None
+    # appended storage
+    u1 = oq.ArrayPartition(*[x.copy() for x in sol.u[-1].x])
+    prob2 = oq.assemble(st, pf, u1, (2.0, 3.0))
+    sol2 = oq.solve(prob2, oq.Tsit5(), **kw)
+    oq.wsolve(prob2, oq.Tsit5(), f, 7, oq.io.VThetaDelta, names, "t", append=True, **kw)
+    assert np.array_equal(oq.io.read(f, "t"), np.concatenate([sol.t, sol2.t]))
+    assert oq.io.read(f, "u2").shape == (nx, nxi, len(sol.t) + len(sol2.t))
+    # strided storage
+    stride = 11
+    oq.wsolve(prob, oq.Tsit5(), f, 50, oq.io.VThetaDelta, names, "t", stride=stride, force=True, **kw)
+    tt = oq.io.read(f, "t")
+    want = [sol.t[i] for i in range(0, len(sol.t), stride)]
+    if (len(sol.t) - 1) % stride != 0:
+        want.append(sol.t[-1])
+    assert np.array_equal(tt, np.array(want))
+
+
+def test_max_real_eigval(gpu):
+    """replacement of the reference's eigvals print (GF.jl:291-294): Arnoldi with GPU matvecs == LAPACK"""
+    oq = gpu
+    _, _, _, ma_p = meshes(oq, W.C2_FAULT, W.C2_BOX)
+    full = oq.stress_greens_function(ma_p, W.LAM, W.MU)
+    want = float(np.max(np.linalg.eigvals(full).real))
+    d22 = oq.device_mantle_mantle(ma_p, W.LAM, W.MU)
+    got = oq.max_real_eigval(d22)
+    assert abs(got - want) <= 1e-5 * max(abs(want), np.max(np.abs(full)) * 1e-6)
