@@ -101,18 +101,18 @@ expand_toeplitz_kernel(const double* __restrict__ st, int nx, int nxi, int r0, i
                        double* __restrict__ G)
 {
     const int nf = nx * nxi;
-    const int row = blockIdx.y;
-    if (row >= nrows) return;
-    const int f = r0 + row;
-    const int i = f % nx, j = f / nx;
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < (int)ld; c += gridDim.x * blockDim.x) {
-        double v = 0.0;
-        if (c < nf) {
-            const int k = c % nx, l = c / nx;
-            const int dk = i > k ? i - k : k - i;
-            v = st[dk + (size_t)nx * (j + (size_t)nxi * l)];
+    for (int row = blockIdx.y; row < nrows; row += gridDim.y) {      // grid.y is capped at 65535
+        const int f = r0 + row;
+        const int i = f % nx, j = f / nx;
+        for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < (int)ld; c += gridDim.x * blockDim.x) {
+            double v = 0.0;
+            if (c < nf) {
+                const int k = c % nx, l = c / nx;
+                const int dk = i > k ? i - k : k - i;
+                v = st[dk + (size_t)nx * (j + (size_t)nxi * l)];
+            }
+            G[(size_t)row * ld + c] = v;
         }
-        G[(size_t)row * ld + c] = v;
     }
 }
 
@@ -469,7 +469,7 @@ int oq_matrix_fault_fault(const OqFaultMesh* mf, double lambda, double mu, int f
     if (alloc_matrix(M, OQ_ROWS_FAULT, row_begin, row_end, nf, nf)) { delete M; return 1; }
     M->kernel_ms = ms;
     if (M->local_rows > 0) {
-        dim3 grid((unsigned)((M->ld + 255) / 256), M->local_rows);
+        dim3 grid((unsigned)((M->ld + 255) / 256), M->local_rows > 65535 ? 65535 : M->local_rows);
         if (grid.x > 64) grid.x = 64;
         expand_toeplitz_kernel<<<grid, 256>>>(st.p, mf->nx, mf->nxi, row_begin, M->local_rows, M->ld, M->d.p);
         g_launches.fetch_add(1);
@@ -492,7 +492,7 @@ int oq_matrix_from_toeplitz(const double* st_host, int nx, int nxi, int row_begi
     OqMatrix* M = new OqMatrix();
     if (alloc_matrix(M, OQ_ROWS_FAULT, row_begin, row_end, nf, nf)) { delete M; return 1; }
     if (M->local_rows > 0) {
-        dim3 grid((unsigned)((M->ld + 255) / 256), M->local_rows);
+        dim3 grid((unsigned)((M->ld + 255) / 256), M->local_rows > 65535 ? 65535 : M->local_rows);
         if (grid.x > 64) grid.x = 64;
         expand_toeplitz_kernel<<<grid, 256>>>(st.p, nx, nxi, row_begin, M->local_rows, M->ld, M->d.p);
         g_launches.fetch_add(1);
