@@ -160,3 +160,16 @@ def test_max_real_eigval(gpu):
     d22 = oq.device_mantle_mantle(ma_p, W.LAM, W.MU)
     got = oq.max_real_eigval(d22)
     assert abs(got - want) <= 1e-5 * max(abs(want), np.max(np.abs(full)) * 1e-6)
+
+
+def test_example_script_runs(gpu, tmp_path):
+    """docs/make.jl:5-10 runs the example as the reference's integration test; same here (short window)"""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("otf_example", os.path.join(root, "examples", "otf_with_mantle.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    sol, tt, vv = mod.main(years=0.02, out=str(tmp_path / "otf"), quiet=True)
+    assert sol.retcode == "Success" and tt[0] == 0.0 and abs(tt[-1] - 0.02 * W.YEAR) < 1e-6
+    assert vv.shape[:2] == (8, 4) and np.all(np.isfinite(vv)) and np.all(vv > 0)
