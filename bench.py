@@ -388,7 +388,8 @@ def run_ours(args):
                    "matrix_bytes_per_rank": mat_bytes, "l2": "inputs larger than L2 (2.15 GB fp64 matrix vs 126 MB)",
                    "parallelism": f"row-sharded x{world}, peer-store all-gather" if world > 1 else "single GPU"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                     "frac": achieved / peak_gbs, "traffic": traffic, "kernel": "matvec_fused_kernel",
+                     "frac": achieved / peak_gbs, "traffic": traffic,
+                     "kernel": "matvec_fused_kernel" if os.environ.get("OQ_MATVEC") == "ldg" else "matvec_stream_kernel",
                      "kernel_ms": mv_avg_ms, "algorithmic_bytes_per_launch": rhs_bytes, "peak_source": peak_src,
                      "kernel_share_of_step": mv_ms / ms_prof if ms_prof > 0 else None,
                      "timing": "CUDA events around each matvec launch, second pass of the same K steps"},
