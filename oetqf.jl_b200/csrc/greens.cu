@@ -186,7 +186,7 @@ gf_fault_mantle_kernel(FaultGeom f, Hex8Geom a, OkadaParams p, const double* __r
 // One geometry evaluation serves all six unit strains (the reference re-evaluates six times).
 // thread t -> (source element e fastest, receiver fault cell); writes G[fl, p*ne + e].
 template <int SLIP>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kHex8Threads, OQ_HEX8_MINB)
 gf_mantle_fault_kernel(Hex8Geom a, FaultGeom f, double mu, double nu, int slip, double s1, double c1,
                        double s2, double c2, int r0, int nrows, size_t ld, double* __restrict__ G)
 {
@@ -209,7 +209,7 @@ gf_mantle_fault_kernel(Hex8Geom a, FaultGeom f, double mu, double nu, int slip, 
 
 // ---- K4: mantle -> mantle (GF.jl:250-290) ----------------------------------------------------------
 // thread t -> (source element i fastest, receiver element j); 36 outputs G[(k*nel + jl), p*ne + i].
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kHex8Threads, OQ_HEX8_MINB)
 gf_mantle_mantle_kernel(Hex8Geom a, double mu, double nu, const double* __restrict__ qc,
                         const double* __restrict__ qw, int nq, int e_begin, int nel, size_t ld,
                         double* __restrict__ G)
@@ -600,7 +600,7 @@ static int build_mantle_fault(const OqHex8Mesh* ma, const OqFaultMesh* mf, doubl
         EventTimer tm;
         int rc = tm.start();
         if (!rc) {
-            const unsigned nb = (unsigned)((total + 127) / 128);
+            const unsigned nb = (unsigned)((total + kHex8Threads - 1) / kHex8Threads);
             if (ftype == OQ_STRIKE_SLIP)
                 gf_mantle_fault_kernel<kStrikeSlip><<<nb, kHex8Threads, kHex8SmemBytes>>>(
                     dma.g, dmf.g, mu, nu, ftype, s1, c1, s2, c2, row_begin, M->local_rows, M->ld, M->d.p);
@@ -655,7 +655,7 @@ static int build_mantle_mantle(const OqHex8Mesh* ma, const OqQuadrature* quad, d
         EventTimer tm;
         int rc = tm.start();
         if (!rc) {
-            gf_mantle_mantle_kernel<<<(unsigned)((total + 127) / 128), kHex8Threads, kHex8SmemBytes>>>(dma.g, mu, nu, dq.c.p, dq.w.p, dq.nq,
+            gf_mantle_mantle_kernel<<<(unsigned)((total + kHex8Threads - 1) / kHex8Threads), kHex8Threads, kHex8SmemBytes>>>(dma.g, mu, nu, dq.c.p, dq.w.p, dq.nq,
                                                                               e_begin, nel, M->ld, M->d.p);
             g_launches.fetch_add(1);
             rc = tm.stop(&M->kernel_ms);
@@ -717,7 +717,7 @@ int oq_stress_vol_hex8(int n, const double* x, const double* y, const double* z,
     DevBuf<double> bx, by, bz, be, dout;
     OQ_TRY(bx.upload(x, n)); OQ_TRY(by.upload(y, n)); OQ_TRY(bz.upload(z, n)); OQ_TRY(be.upload(eps6, 6));
     OQ_TRY(dout.alloc((size_t)n * 6));
-    hex8_stress_kernel<<<(n + 127) / 128, kHex8Threads, kHex8SmemBytes>>>(n, bx.p, by.p, bz.p, qx, qy, qz, dx, dy, dz, be.p, mu, nu, dout.p);
+    hex8_stress_kernel<<<(n + kHex8Threads - 1) / kHex8Threads, kHex8Threads, kHex8SmemBytes>>>(n, bx.p, by.p, bz.p, qx, qy, qz, dx, dy, dz, be.p, mu, nu, dout.p);
     OQ_LAUNCHED();
     OQ_CUDA(cudaMemcpy(out6, dout.p, dout.n * sizeof(double), cudaMemcpyDeviceToHost));
     return 0;

@@ -19,9 +19,24 @@
 
 #include "hex8_gen.cuh"
 
+// Optimisation barrier expanded at the start of every group of basis functions: the inputs pass through an empty
+// asm, so temporaries of one group cannot be kept alive for the next (each group is register-allocated on its
+// own; the hoisting/sharing across groups is what pushed the image basis to 250 registers).
+#ifndef HEX8_GROUP_BARRIER
+#define HEX8_GROUP_BARRIER                                                                                         \
+    asm volatile("" : "+d"(R1), "+d"(R2), "+d"(R3), "+d"(R), "+d"(iR), "+d"(iw1), "+d"(iw2), "+d"(iw3), "+d"(iq1),  \
+                 "+d"(iq2), "+d"(iq3), "+d"(q1), "+d"(q2), "+d"(q3));
+#endif
+
 namespace oq {
 
-constexpr int kHex8Threads = 128;
+#ifndef OQ_HEX8_THREADS
+#define OQ_HEX8_THREADS 128
+#endif
+#ifndef OQ_HEX8_MINB
+#define OQ_HEX8_MINB 2
+#endif
+constexpr int kHex8Threads = OQ_HEX8_THREADS;
 constexpr int kHex8Acc = HEX8_NB_REAL + HEX8_NB_IMAGE;
 constexpr size_t kHex8SmemBytes = (size_t)kHex8Acc * kHex8Threads * sizeof(double);
 
@@ -64,8 +79,8 @@ template <int NEED>
 __device__ __forceinline__ void hex8_basis_real(double R1, double R2, double R3, const Hex8Corner& c, double sgn,
                                                 double* acc)
 {
-    const double R = c.R, iR = c.iR, w1 = c.w[0], w2 = c.w[1], w3 = c.w[2], q1 = c.q[0], q2 = c.q[1], q3 = c.q[2];
-    const double iw1 = c.iw[0], iw2 = c.iw[1], iw3 = c.iw[2], iq1 = c.iq[0], iq2 = c.iq[1], iq3 = c.iq[2];
+    double R = c.R, iR = c.iR, w1 = c.w[0], w2 = c.w[1], w3 = c.w[2], q1 = c.q[0], q2 = c.q[1], q3 = c.q[2];
+    double iw1 = c.iw[0], iw2 = c.iw[1], iw3 = c.iw[2], iq1 = c.iq[0], iq2 = c.iq[1], iq3 = c.iq[2];
     const double L1 = c.L[0], L2 = c.L[1], L3 = c.L[2], A1 = c.A[0], A2 = c.A[1], A3 = c.A[2];
     (void)R; (void)iR; (void)w1; (void)w2; (void)w3; (void)q1; (void)q2; (void)q3; (void)iw1; (void)iw2; (void)iw3;
     (void)iq1; (void)iq2; (void)iq3; (void)L1; (void)L2; (void)L3; (void)A1; (void)A2; (void)A3;
@@ -80,8 +95,8 @@ template <int NEED>
 __device__ __forceinline__ void hex8_basis_image(double R1, double R2, double R3, const Hex8Corner& c, double Ba,
                                                  double Bb, double sgn, double* acc)
 {
-    const double R = c.R, iR = c.iR, w1 = c.w[0], w2 = c.w[1], w3 = c.w[2], q1 = c.q[0], q2 = c.q[1], q3 = c.q[2];
-    const double iw1 = c.iw[0], iw2 = c.iw[1], iw3 = c.iw[2], iq1 = c.iq[0], iq2 = c.iq[1], iq3 = c.iq[2];
+    double R = c.R, iR = c.iR, w1 = c.w[0], w2 = c.w[1], w3 = c.w[2], q1 = c.q[0], q2 = c.q[1], q3 = c.q[2];
+    double iw1 = c.iw[0], iw2 = c.iw[1], iw3 = c.iw[2], iq1 = c.iq[0], iq2 = c.iq[1], iq3 = c.iq[2];
     const double L1 = c.L[0], L2 = c.L[1], L3 = c.L[2], A1 = c.A[0], A2 = c.A[1], A3 = c.A[2];
     (void)R; (void)iR; (void)w1; (void)w2; (void)w3; (void)q1; (void)q2; (void)q3; (void)iw1; (void)iw2; (void)iw3;
     (void)iq1; (void)iq2; (void)iq3; (void)L1; (void)L2; (void)L3; (void)A1; (void)A2; (void)A3; (void)Ba; (void)Bb;

@@ -349,10 +349,18 @@ def emit_basis(keys, index, prefix, masks):
     for key in keys:
         groups.setdefault((key[0], sum(key[1])), []).append(key)
     lines, total = [], 0
-    for gi, (gname, gkeys) in enumerate(sorted(groups.items())):
+    # large groups are cut into blocks of at most MAXF functions: a block is register-allocated on its own
+    # (HEX8_GROUP_BARRIER), at the price of recomputing a few shared powers
+    MAXF = int(os.environ.get('HEX8_MAXF', '99'))   # measured: splitting costs more (recomputed powers) than it saves
+    blocks = []
+    for gname, gkeys in sorted(groups.items()):
+        for i0 in range(0, len(gkeys), MAXF):
+            blocks.append((gname, gkeys[i0:i0 + MAXF]))
+    for gi, (gname, gkeys) in enumerate(blocks):
         assigns = [(f"ACC({index[key]})", TD(*key), masks[key]) for key in gkeys]
         blk, nops = cse_block(assigns, f"{prefix}{gi}_")
         lines.append(f"    {{   /* {gname[0]}, derivative order {gname[1]}: {len(gkeys)} functions */")
+        lines.append("        HEX8_GROUP_BARRIER")
         lines += blk
         lines.append("    }")
         total += nops
@@ -399,7 +407,9 @@ def main():
               "// of P0 = 1/R, P1 = R, P3 = R - R3 ln(R+R3).  hex8_basis_* accumulate sgn * basis into ACC(b) for one\n"
               "// corner; hex8_combine turns the 8-corner sums into Q[(il),(jk)] (times 8*pi*mu), pairs xx,xy,xz,yy,yz,zz.\n"
               "// The includer defines ACC(b) (accumulator b of the current function), ACCR(b)/ACCI(b) (real/image sums) and\n"
-              "// HEX8_NEED(mask) (non-zero if any strain row xx,xy,xz,yy,yz,zz = bit 0..5 of mask is wanted).\n"
+              "// HEX8_NEED(mask) (non-zero if any strain row xx,xy,xz,yy,yz,zz = bit 0..5 of mask is wanted) and\n"
+              "// HEX8_GROUP_BARRIER (expanded at the start of every group; may be empty, or an optimisation barrier\n"
+              "// on the inputs that stops the compiler from sharing temporaries across groups).\n"
               "// Inputs: R1,R2,R3 corner vector, R its norm, w_c = R+R_c, q_c = R^2-R_c^2, iR/iw_c/iq_c reciprocals,\n"
               "// L_c = ln(w_c), A_c = atan(R_a R_b/(R_c R)), Ba = atan(R1/R2), Bb = atan(R2/R1).\n"
               f"#define HEX8_NB_REAL {len(keys_r)}\n#define HEX8_NB_IMAGE {len(keys_i)}\n")

@@ -18,6 +18,7 @@
 
 #include "hex8_gen.inc"
 #define HEX8_NEED(mask) 1
+#define HEX8_GROUP_BARRIER
 
 static void corner_inputs(double r1, double r2, double r3, double *R, double *w, double *q, double *L, double *A,
                           double *iR, double *iw, double *iq)
