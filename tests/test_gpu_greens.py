@@ -162,3 +162,18 @@ def test_matrix_roundtrip_and_gemv(gpu):
         part = oq.device_from_host(A, rows=(r0, r1))
         # a shard splits its row blocks across CTAs differently from the full matrix: same sums, other order
         assert np.max(np.abs(part.gemv(x) - got[r0:r1]) / scale[r0:r1]) < 1e-14
+
+
+@pytest.mark.parametrize("ftype", [0, 1])
+def test_fault_mantle_dipping_gauss3(gpu, ftype):
+    """test/BEM/tests.jl:85-95 geometry with a 60-degree fault, Gauss3 product rule, no periodic images"""
+    oq = gpu
+    fs = W.FaultSpec(100.0, 100.0, 10.0, 20.0, 60.0)
+    bs = W.BoxSpec(-100.0, -50.0, -120.0, 200.0, 100.0, -30.0, 2, 3, 4)
+    mf_o, mf_p, ma_o, ma_p = meshes(oq, fs, bs)
+    q = ref.gauss_quadrature(3)
+    want = ref.gf_fault_mantle(mf_o, ma_o, 1.0, 1.0, ftype=ftype, quad=q, nrept=0, buffer_ratio=0.0)
+    ft = oq.StrikeSlip() if ftype == 0 else oq.DipSlip()
+    got = oq.stress_greens_function(mf_p, ma_p, 1.0, 1.0, ftype=ft, qtype="Gauss3", nrept=0, buffer_ratio=0.0)
+    assert got.shape == (144, 50)
+    assert scaled_err(got, want, axis=0) < TOL
