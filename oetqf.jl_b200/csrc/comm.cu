@@ -143,6 +143,8 @@ int oq_comm_connect(OqProblem* p, const uint8_t* all)
         return fail("row shards do not cover the problem (fault %d/%d, mantle %d/%d)", fcover, p->nf, ecover, p->ne);
     }
     p->peers = pw;
+    // a resident-RHS graph captured before the peers were mapped bakes single-rank targets into its kernels
+    if (p->rhs_graph) { cudaGraphExecDestroy(p->rhs_graph); p->rhs_graph = nullptr; }
     return 0;
 }
 
