@@ -84,7 +84,8 @@ int oq_gf_fault_mantle(const OqFaultMesh *mf, const OqHex8Mesh *ma, const OqQuad
 int oq_gf_mantle_fault(const OqHex8Mesh *ma, const OqFaultMesh *mf, double lambda, double mu, int ftype,
                        double *out, double *kernel_ms);
 
-/* src/BEM/GF.jl:250-296 (without the O(n^3) eigvals print; see oq_matrix_max_real_eig_estimate).
+/* src/BEM/GF.jl:250-296 (without the O(n^3) eigvals print of :291-294; the host side offers an Arnoldi
+ * estimate of the largest real part built on oq_gemv instead).
  * out: double[6*ne * 6*ne] */
 int oq_gf_mantle_mantle(const OqHex8Mesh *ma, const OqQuadrature *quad, double lambda, double mu,
                         double *out, double *kernel_ms);

@@ -47,3 +47,21 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".jl", "Makefile")):
                 with open(os.path.join(base, f), errors="replace") as fh:
                     assert not bad.search(fh.read()), f"{f} reaches into oracle/"
+
+
+def test_argument_validation_precedes_device_use(oq):
+    """every export returns non-zero with a message instead of crashing on NULL / malformed arguments
+    (checked without a GPU: validation happens before the device is touched)"""
+    import ctypes as C
+    lib = oq._lib.load()
+    d = C.c_double(0)
+    assert lib.oq_gf_fault_fault(None, C.c_double(1), C.c_double(1), 0, 0, 2, C.c_double(0), None, None) != 0
+    assert b"NULL" in lib.oq_last_error()
+    assert lib.oq_gemv(None, None, None, 0) != 0
+    assert lib.oq_matrix_to_host(None, None) != 0
+    assert lib.oq_problem_layout(None, None, None) != 0
+    assert lib.oq_solve(None, C.c_double(0), None, 1, C.cast(None, oq._lib.SNAPSHOT_FN), None, None) != 0
+    assert lib.oq_dc3d_gradient(-1, None, None, None, d, d, d, d, d, d, d, 0, None) != 0
+    assert lib.oq_dc3d_gradient(0, None, None, None, d, d, d, d, d, d, d, 7, None) != 0
+    assert b"fault type" in lib.oq_last_error()
+    assert lib.oq_matrix_destroy(None) == 0 and lib.oq_problem_destroy(None) == 0     # destroying NULL is a no-op
