@@ -48,6 +48,7 @@ class DeviceProblem:
     def __init__(self, handle, keep, shapes):
         self._h = handle
         self._keep = keep
+        self._ptr_cache = {}
         self.shapes = shapes            # global shapes of the state partitions (reference layout)
         n, lens = C.c_int(), (C.c_int * 5)()
         _lib.check(_lib.load().oq_problem_layout(handle, C.byref(n), lens))
@@ -61,6 +62,19 @@ class DeviceProblem:
         return self._h
 
     def _ptrs(self, arrays: Sequence[np.ndarray], writable: bool):
+        # the integrator calls f(du, u, p, t) with the same buffers over and over: cache the pointer tables
+        key = tuple((id(a), a.ctypes.data if isinstance(a, np.ndarray) else 0) for a in arrays) + (writable,)
+        hit = self._ptr_cache.get(key)
+        if hit is not None:
+            return hit
+        res = self._ptrs_build(arrays, writable)
+        if all(k is a for k, a in zip(res[1], arrays)):      # only cache when no temporary copy was made
+            if len(self._ptr_cache) > 64:
+                self._ptr_cache.clear()
+            self._ptr_cache[key] = res
+        return res
+
+    def _ptrs_build(self, arrays: Sequence[np.ndarray], writable: bool):
         assert len(arrays) == self.nparts, f"expected {self.nparts} state partitions"
         out = (_lib.c_double_p * self.nparts)()
         keep = []
