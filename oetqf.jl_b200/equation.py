@@ -63,7 +63,7 @@ class DeviceProblem:
 
     def _ptrs(self, arrays: Sequence[np.ndarray], writable: bool):
         # the integrator calls f(du, u, p, t) with the same buffers over and over: cache the pointer tables
-        key = tuple((id(a), a.ctypes.data if isinstance(a, np.ndarray) else 0) for a in arrays) + (writable,)
+        key = tuple((id(a), a.ctypes.data, a.size) if isinstance(a, np.ndarray) else (id(a), 0, 0) for a in arrays) + (writable,)
         hit = self._ptr_cache.get(key)
         if hit is not None:
             return hit
