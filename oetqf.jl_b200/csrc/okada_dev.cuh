@@ -67,13 +67,13 @@ __device__ __forceinline__ void corner_terms(const OkadaMedium& m, double xi, do
     if (kxi) { c.x11 = 0.0; c.x32 = 0.0; }
     else {
         const double rxi = r + xi;
-        c.x11 = c.ri / rxi;
+        c.x11 = c.ri * (1.0 / rxi);        // reciprocal + multiply: cheaper than a full fp64 division
         c.x32 = (r + rxi) * c.x11 * c.x11 * c.ri;
     }
     if (ket) { c.y11 = 0.0; c.y32 = 0.0; }
     else {
         const double ret = r + et;
-        c.y11 = c.ri / ret;
+        c.y11 = c.ri * (1.0 / ret);
         c.y32 = (r + ret) * c.y11 * c.y11 * c.ri;
     }
     c.ey = m.sd * c.ri - c.y * q * c.r3i;

@@ -79,7 +79,7 @@ struct OqProblem {
     oq::DevBuf<double> dtau0;                       // Toeplitz-form traction rate [nfl]
     // FFT form (toeplitz_fft.cuh): transform length, local receiver-row range, spectrum and work arrays
     int fftN = 0, fj0 = 0, fnj = 0;
-    oq::DevBuf<double> Ghat, Rhat, That;
+    oq::DevBuf<double> Ghat, Rhat, That, Wtw;      // Wtw: N/2 complex twiddles
     int nseg_f = 0, nseg_m = 0;
     oq::MatOperand opf[2], opm[2];
 

@@ -577,16 +577,17 @@ int rhs_device(OqProblem* p, const double* uin, double* du, const StageSpec* sta
             OQ_LAUNCHED();
         } else {
             const int N = p->fftN, nfreq = N / 2 + 1;
-            const size_t fsmem = 2 * (size_t)N * sizeof(cplx);
+            const size_t fsmem = (2 * (size_t)N + N / 2) * sizeof(cplx);
+            const size_t ismem = fsmem + (size_t)kFftLGroups * nfreq * sizeof(cplx);
+            const cplx* Wtw = reinterpret_cast<const cplx*>(p->Wtw.p);
             fft_forward_kernel<<<p->nxi, 256, fsmem, st>>>(p->relv, p->wl.relv_len, pw, direct_fft ? in.v : nullptr,
-                                                         p->fp.vpl, p->nx, N, reinterpret_cast<cplx*>(p->Rhat.p));
+                                                         p->fp.vpl, p->nx, N, Wtw, reinterpret_cast<cplx*>(p->Rhat.p));
             OQ_LAUNCHED();
             // with no dense operand on the fault rows the pointwise physics is fused into the inverse transform
             const bool fuse = p->kind != kViscoelastic;
-            (void)nfreq;
-            fft_inverse_kernel<<<p->fnj, 256, fsmem, st>>>(p->Ghat.p, reinterpret_cast<const cplx*>(p->Rhat.p), p->nxi,
-                                                         p->fnj, p->nx, N, p->fj0, p->f0, p->nfl, p->dtau0.p,
-                                                         fuse ? 1 : 0, fe);
+            fft_inverse_kernel<<<p->fnj, kFftInvThreads, ismem, st>>>(
+                p->Ghat.p, reinterpret_cast<const cplx*>(p->Rhat.p), p->nxi, p->fnj, p->nx, N, p->fj0, p->f0, p->nfl,
+                Wtw, p->dtau0.p, fuse ? 1 : 0, fe);
             OQ_LAUNCHED();
             epilogue_done = fuse;
         }
@@ -735,7 +736,8 @@ static int finish_problem(OqProblem* p, const OqFaultProperty* pf, const OqDilat
         // FFT form: transform length = power of two >= 2nx-1; receiver rows j that intersect this rank's shard
         int N = 2;
         while (N < 2 * p->nx - 1) N <<= 1;
-        OQ_CHECK(2 * (size_t)N * 16 <= 200 * 1024, "nx = %d too large for the shared-memory FFT", p->nx);
+        OQ_CHECK((2 * (size_t)N + N / 2 + (size_t)kFftLGroups * (N / 2 + 1)) * 16 <= 200 * 1024,
+                 "nx = %d too large for the shared-memory FFT", p->nx);
         p->fftN = N;
         p->fj0 = nfl > 0 ? p->f0 / p->nx : 0;
         p->fnj = nfl > 0 ? (p->f1 - 1) / p->nx + 1 - p->fj0 : 0;
@@ -748,10 +750,14 @@ static int finish_problem(OqProblem* p, const OqFaultProperty* pf, const OqDilat
             toeplitz_spectrum_kernel<<<(unsigned)((nt + 255) / 256), 256>>>(p->st.p, p->nx, p->nxi, N, p->fj0, p->fnj,
                                                                             p->Ghat.p);
             OQ_LAUNCHED();
-            const size_t fsmem = 2 * (size_t)N * sizeof(cplx);
-            if (fsmem > 48 * 1024) {
+            OQ_TRY(p->Wtw.alloc((size_t)N + 2));
+            twiddle_kernel<<<(N / 2 + 255) / 256, 256>>>(N, reinterpret_cast<cplx*>(p->Wtw.p));
+            OQ_LAUNCHED();
+            const size_t fsmem = (2 * (size_t)N + N / 2) * sizeof(cplx);
+            const size_t ismem = fsmem + (size_t)kFftLGroups * nfreq * sizeof(cplx);
+            if (ismem > 48 * 1024) {
                 OQ_CUDA(cudaFuncSetAttribute(fft_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-                OQ_CUDA(cudaFuncSetAttribute(fft_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+                OQ_CUDA(cudaFuncSetAttribute(fft_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ismem));
             }
         }
     }

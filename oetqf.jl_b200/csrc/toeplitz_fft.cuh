@@ -15,18 +15,30 @@ namespace oq {
 
 struct cplx { double re, im; };
 
+// twiddle table W[j] = exp(-2 pi i j / N), j < N/2, built once per problem with sincospi (exact argument
+// reduction); the transforms read it through shared memory
+__global__ void __launch_bounds__(256) twiddle_kernel(int N, cplx* __restrict__ W)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= N / 2) return;
+    double s, c;
+    sincospi(-2.0 * (double)j / (double)N, &s, &c);
+    W[j] = {c, s};
+}
+
 // in-place-by-ping-pong Stockham radix-2 FFT of length N (power of two) in shared memory; returns the buffer
-// holding the result.  All threads of the CTA participate.
-__device__ __forceinline__ cplx* stockham_fft(cplx* a, cplx* b, int N)
+// holding the result.  All threads of the CTA participate; tw[] holds the N/2 twiddles in shared memory.
+__device__ __forceinline__ cplx* stockham_fft(cplx* a, cplx* b, const cplx* tw, int N)
 {
     const int half = N >> 1;
-    for (int Ns = 1; Ns < N; Ns <<= 1) {
+    int shift = 0;
+    while ((1 << shift) < half) ++shift;                 // log2(N/2)
+    for (int Ns = 1, ls = 0; Ns < N; Ns <<= 1, ++ls) {
         for (int j = threadIdx.x; j < half; j += blockDim.x) {
             const int k = j & (Ns - 1);
-            double s, c;
-            sincospi(-(double)k / (double)Ns, &s, &c);
+            const cplx w = tw[k << (shift - ls)];          // exp(-i pi k / Ns) = W[k * (N/2) / Ns]
             const cplx u0 = a[j], v = a[j + half];
-            const cplx u1 = {v.re * c - v.im * s, v.re * s + v.im * c};
+            const cplx u1 = {v.re * w.re - v.im * w.im, v.re * w.im + v.im * w.re};
             const int j0 = ((j - k) << 1) + k;
             b[j0] = {u0.re + u1.re, u0.im + u1.im};
             b[j0 + Ns] = {u0.re - u1.re, u0.im - u1.im};
@@ -61,11 +73,13 @@ toeplitz_spectrum_kernel(const double* __restrict__ st, int nx, int nxi, int N, 
 // here from the state and the separate forcing kernel is skipped.
 __global__ void __launch_bounds__(256)
 fft_forward_kernel(const double* relv0, size_t relv_stride, PeerWait pw, const double* __restrict__ v_direct,
-                   double vpl, int nx, int N, cplx* __restrict__ Rh)
+                   double vpl, int nx, int N, const cplx* __restrict__ W, cplx* __restrict__ Rh)
 {
     extern __shared__ __align__(16) unsigned char fsm[];
     cplx* a = reinterpret_cast<cplx*>(fsm);
     cplx* b = a + N;
+    cplx* tw = b + N;
+    for (int k = threadIdx.x; k < N / 2; k += blockDim.x) tw[k] = W[k];
     const int l = blockIdx.x;
     if (v_direct) {
         for (int k = threadIdx.x; k < N; k += blockDim.x)
@@ -75,7 +89,7 @@ fft_forward_kernel(const double* relv0, size_t relv_stride, PeerWait pw, const d
         for (int k = threadIdx.x; k < N; k += blockDim.x) a[k] = {k < nx ? relv[k + (size_t)nx * l] : 0.0, 0.0};
     }
     __syncthreads();
-    const cplx* r = stockham_fft(a, b, N);
+    const cplx* r = stockham_fft(a, b, tw, N);
     const int nfreq = N / 2 + 1;
     for (int f = threadIdx.x; f < nfreq; f += blockDim.x) Rh[(size_t)l * nfreq + f] = r[f];
 }
@@ -101,31 +115,50 @@ spectral_contract_kernel(const double* __restrict__ Gh, const cplx* __restrict__
 
 // dτ[i, j0+jl] = real(IFFT_N(Hermitian extension of T[jl][:]))[i], i < nx; rows outside [f0, f0+nfl) are dropped.
 // The per-frequency contraction T[jl][f] = Σ_l Ĝ[l][jl][f] R[l][f] is done here by the CTA that transforms the
-// row (Ĝ is read exactly once per evaluation; R comes from L2).
-__global__ void __launch_bounds__(256)
+// row (Ĝ is read exactly once per evaluation; R comes from L2): the source index l is split over kFftLGroups
+// thread groups so that many independent loads are in flight, partial sums are folded in a fixed order.
+constexpr int kFftLGroups = 4;
+constexpr int kFftInvThreads = 1024;
+
+__global__ void __launch_bounds__(kFftInvThreads)
 fft_inverse_kernel(const double* __restrict__ Gh, const cplx* __restrict__ Rh, int nxi, int nj, int nx, int N, int j0,
-                   int f0, int nfl, double* __restrict__ dtau, int fuse_epilogue, FaultEpilogue fe)
+                   int f0, int nfl, const cplx* __restrict__ W, double* __restrict__ dtau, int fuse_epilogue,
+                   FaultEpilogue fe)
 {
     extern __shared__ __align__(16) unsigned char fsm[];
     cplx* a = reinterpret_cast<cplx*>(fsm);
     cplx* b = a + N;
+    cplx* tw = b + N;
+    cplx* part = tw + N / 2;                       // [kFftLGroups][nfreq]
     const int jl = blockIdx.x;
     const int nfreq = N / 2 + 1;
-    for (int f = threadIdx.x; f < nfreq; f += blockDim.x) {
+    for (int k = threadIdx.x; k < N / 2; k += blockDim.x) tw[k] = W[k];
+    const int per = blockDim.x / kFftLGroups;      // threads per l-group
+    const int grp = threadIdx.x / per, tf = threadIdx.x % per;
+    const int lchunk = (nxi + kFftLGroups - 1) / kFftLGroups;
+    const int l0 = grp * lchunk, l1 = min(nxi, l0 + lchunk);
+    for (int f = tf; f < nfreq; f += per) {
         double re = 0.0, im = 0.0;
-#pragma unroll 4
-        for (int l = 0; l < nxi; ++l) {
+#pragma unroll 8
+        for (int l = l0; l < l1; ++l) {
             const double g = Gh[((size_t)l * nj + jl) * nfreq + f];
             const cplx r = Rh[(size_t)l * nfreq + f];
             re = fma(g, r.re, re);
             im = fma(g, r.im, im);
         }
+        part[grp * nfreq + f] = {re, im};
+    }
+    __syncthreads();
+    for (int f = threadIdx.x; f < nfreq; f += blockDim.x) {
+        double re = 0.0, im = 0.0;
+#pragma unroll
+        for (int g = 0; g < kFftLGroups; ++g) { re += part[g * nfreq + f].re; im += part[g * nfreq + f].im; }
         // ifft(X) = conj(fft(conj(X))) / N; X[N-f] = conj(X[f])
         a[f] = {re, -im};
         if (f > 0 && f < N - f) a[N - f] = {re, im};
     }
     __syncthreads();
-    const cplx* r = stockham_fft(a, b, N);
+    const cplx* r = stockham_fft(a, b, tw, N);
     const double inv = 1.0 / (double)N;
     for (int i = threadIdx.x; i < nx; i += blockDim.x) {
         const int row = i + nx * (j0 + jl) - f0;
