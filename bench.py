@@ -113,6 +113,7 @@ def cpu_reference(fs, budget_s=12.0, steps=None, warmup=1):
     """The reference's own CPU algorithm for this path, restated (oracle port): FFT form of the fault-fault
     interaction (equation.jl:44-61) + update_fault! (equation.jl:233-246), all host threads."""
     from oracle import ref
+    ref.use_all_cores()
     mf = ref.fault_mesh(fs.x, fs.xi, fs.dx, fs.dxi, fs.dip)
     a, b, L, sig = W.fault_properties(mf.x, mf.z, mf.nx, mf.nxi)
     v, th, _ = W.initial_state(mf.nx, mf.nxi, L, rng=np.random.default_rng(42))

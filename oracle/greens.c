@@ -21,6 +21,16 @@ void oq_ref_stress_vol_hex8(double x, double y, double z, double qx, double qy, 
                             double dx, double dy, double dz, const double *eps,
                             double mu, double nu, double *sig);
 
+/* torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU baseline asks for all cores explicitly */
+void oq_ref_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int oq_ref_num_threads(void)
 {
 #ifdef _OPENMP

@@ -53,6 +53,13 @@ def num_threads() -> int:
     return int(lib().oq_ref_num_threads())
 
 
+def use_all_cores() -> int:
+    """Let OpenMP use every core this process may run on (launchers such as torchrun pin OMP_NUM_THREADS=1)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().oq_ref_set_num_threads(int(n))
+    return num_threads()
+
+
 # ----------------------------------------------------------------------------- meshes
 @dataclass
 class FaultMesh:
