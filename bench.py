@@ -259,9 +259,18 @@ def example_extra(oq):
                    save_everystep=False)
     wall = time.perf_counter() - t0
     steps = sol.stats["naccept"] + sol.stats["nreject"]
+    # the example's own algorithm (otf-with-mantle.jl:160): simulated time per wall second is what the user sees
+    year = {}
+    for name, alg in (("tsit5", oq.Tsit5()), ("vcabm5", oq.VCABM5())):
+        prob1 = oq.assemble(d11, d12, d21, d22, pf, pa, u0, (0.0, 1.0 * W.YEAR))
+        t0 = time.perf_counter()
+        s1 = oq.solve(prob1, alg, reltol=1e-6, abstol=1e-8, dt=1e-8, dtmax=0.2 * W.YEAR, maxiters=100000,
+                      save_everystep=False)
+        year[name] = {"wall_s": time.perf_counter() - t0, "steps": s1.stats["naccept"] + s1.stats["nreject"],
+                      "rhs_evals": s1.stats["nf"], "retcode": s1.retcode}
     return {"workload": "BASELINE configs[1]: examples/otf-with-mantle.jl (8x4 fault, 4x3x3 hex8 mantle), coupled RHS",
             "rhs_evals_per_s": 1e3 / ms, "rhs_us": 1e3 * ms, "tsit5_steps_per_s": steps / wall,
-            "tsit5_rhs_per_s": 6 * steps / wall}
+            "tsit5_rhs_per_s": 6 * steps / wall, "one_simulated_year": year}
 
 
 # ------------------------------------------------------------------------------------------ main arm

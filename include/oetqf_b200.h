@@ -206,10 +206,12 @@ int oq_profile_read(OqProblem *p, double *matvec_ms_total, int64_t *launches);
 int oq_rhs_bytes(const OqProblem *p, double *bytes);
 
 /* Adaptive integrator options (OrdinaryDiffEq semantics: examples/otf-with-mantle.jl:160-162). */
+#define OQ_ALG_TSIT5 0
+#define OQ_ALG_VCABM5 1 /* variable-coefficient Adams PECE, order 5, started with four Tsit5 steps */
 typedef struct OqSolveOptions {
     double reltol, abstol, dt0, dtmax, tstop;
     int64_t maxiters;
-    int32_t algorithm;      /* 0 = Tsit5 (test/tests.jl:11) */
+    int32_t algorithm;      /* OQ_ALG_TSIT5 (test/tests.jl:11) or OQ_ALG_VCABM5 (examples/otf-with-mantle.jl:160) */
     int32_t fixed_dt;       /* != 0: take fixed steps of dt0 (no error control) */
 } OqSolveOptions;
 

@@ -6,7 +6,7 @@ include/oetqf_b200.h.  There is no CPU fallback.
 """
 from . import _lib, dist
 from ._lib import OqError, init, kernel_launch_count, measure_fp64_peak, measure_hbm_copy
-from .equation import ArrayPartition, DeviceProblem, ODEProblem, ODESolution, Tsit5, assemble, ode, solve
+from .equation import ArrayPartition, DeviceProblem, ODEProblem, ODESolution, Tsit5, VCABM5, assemble, ode, solve
 from . import io
 from .io import wsolve
 from .gf import (max_real_eigval, DeviceMatrix, DipSlip, StrikeSlip, dc3d_gradient, device_fault_fault, device_fault_mantle,

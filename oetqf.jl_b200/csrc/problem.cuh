@@ -85,6 +85,7 @@ struct OqProblem {
 
     // resident state + integrator storage: u, du(k1), k2..k7, utmp, unew
     oq::DevBuf<double> u, k[7], utmp, unew;
+    oq::DevBuf<double> hist[4], abm_coef;           // multistep integrator: f(t_{n-1..n-4}), per-step weights
     oq::DevBuf<double> errpart;                     // per-block partial sums of the error norm
     oq::DevBuf<double> ctl;                         // device-side controller record (StepCtl)
 
@@ -106,13 +107,15 @@ struct OqProblem {
 
 namespace oq {
 
-// Runge-Kutta stage combination fused into the forcing kernel: y = u + dt * sum_{j<nk} a[j] k[j]
+// Runge-Kutta stage / Adams predictor-corrector combination fused into the forcing kernel:
+//   y = u + dt * sum_{j<nk} a[j] k[j]
 struct StageSpec {
     int nk = 0;
     const double* u = nullptr;
     const double* k[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     double a[6] = {0, 0, 0, 0, 0, 0};
-    const double* dt = nullptr;      // device scalar (the controller's current step)
+    const double* adev = nullptr;    // device coefficients replacing a[] (the multistep weights change every step)
+    const double* dt = nullptr;      // device scalar (the controller's current step); null: factor 1
     const int* done = nullptr;       // device flag: the integration is complete, the evaluation is skipped
 };
 

@@ -53,12 +53,13 @@ __global__ void __launch_bounds__(1024) forcing_kernel(const __grid_constant__ F
     const int world = a.peers.world;
     const int stride = gridDim.x * blockDim.x;
     const bool staged = a.stage.nk > 0;
-    const double dt = staged ? *a.stage.dt : 0.0;
+    const double dt = staged ? (a.stage.dt ? *a.stage.dt : 1.0) : 0.0;
+    const double* __restrict__ adev = a.stage.adev;
     auto combine = [&](size_t idx) {
         double acc = 0.0;
 #pragma unroll
         for (int j = 0; j < 6; ++j)
-            if (j < a.stage.nk) acc = fma(a.stage.a[j], a.stage.k[j][idx], acc);
+            if (j < a.stage.nk) acc = fma(adev ? adev[j] : a.stage.a[j], a.stage.k[j][idx], acc);
         const double y = fma(dt, acc, a.stage.u[idx]);
         a.y[idx] = y;
         return y;

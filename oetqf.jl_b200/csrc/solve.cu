@@ -1,4 +1,6 @@
-// solve.cu -- device-resident adaptive Runge-Kutta integrator (Tsit5) around the RHS of rhs.cu.
+// solve.cu -- device-resident adaptive integrators around the RHS of rhs.cu: Tsit5 (what the reference's tests
+// use) and a variable-coefficient Adams-Bashforth-Moulton PECE of order 5 (the VCABM5 class the reference's
+// example uses, examples/otf-with-mantle.jl:160-162): 2 RHS evaluations per step instead of 6.
 //
 // Takes the place of OrdinaryDiffEq's `solve(prob, Tsit5(); reltol, abstol, dtmax, dt, maxiters)` as the
 // reference drives it (/root/reference/src/io.jl:128-130, test/tests.jl:11, examples/otf-with-mantle.jl:160-162):
@@ -38,8 +40,10 @@ static const double hA[7][6] = {
 struct StepCtl {
     double t, dt, qold, eest, tstop, dtmax, reltol, abstol;
     double dt_last;
+    double hdt[4];                   // sizes of the last accepted steps, newest first (multistep history grid)
     long long naccept, nreject, nrhs;
     int accepted, done, retcode, fixed;
+    int nhist;                       // accepted steps recorded in the history so far (saturates at 4)
 };
 static_assert(sizeof(StepCtl) <= 32 * sizeof(double), "ctl buffer too small");
 
@@ -65,6 +69,7 @@ stage_kernel(const double* __restrict__ u, Stages ks, int s, int nk, const StepC
 struct ErrArgs {
     const double *u, *unew;
     Stages ks;
+    const double* wdev;              // multistep: 6 device weights (step size included); null: Tsit5's btilde * dt
     const StepCtl* ctl;
     size_t n;
     double* errpart;                 // [gridDim.x]
@@ -83,9 +88,14 @@ __global__ void __launch_bounds__(256) error_kernel(const __grid_constant__ ErrA
     double s = 0.0;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (size_t)gridDim.x * blockDim.x) {
         double e = 0.0;
+        if (a.wdev) {
 #pragma unroll
-        for (int j = 0; j < 7; ++j) e = fma(cBtilde[j], a.ks.k[j][i], e);
-        e *= dt;
+            for (int j = 0; j < 6; ++j) e = fma(a.wdev[j], a.ks.k[j][i], e);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 7; ++j) e = fma(cBtilde[j], a.ks.k[j][i], e);
+            e *= dt;
+        }
         const double sk = atol + rtol * fmax(fabs(a.u[i]), fabs(a.unew[i]));
         const double q = e / sk;
         s = fma(q, q, s);
@@ -132,6 +142,7 @@ struct CtlArgs {
     unsigned long long* epochs;
     int world, rank;
     double nglobal;
+    int nrhs_inc;                        // RHS evaluations this step spent
 };
 
 // one thread: error norm -> accept/reject -> next dt (OrdinaryDiffEq's PI controller)
@@ -147,10 +158,14 @@ __global__ void controller_kernel(CtlArgs a)
     for (int r = 0; r < a.world; ++r) tot += *(volatile const double*)(a.red_slots + par * kMaxWorld + r);
     const double eest = sqrt(tot / a.nglobal);
     c.eest = eest;
-    c.nrhs += 6;
+    c.nrhs += a.nrhs_inc;
+    auto record = [&c]() {               // the accepted step joins the history grid of the multistep method
+        c.hdt[3] = c.hdt[2]; c.hdt[2] = c.hdt[1]; c.hdt[1] = c.hdt[0]; c.hdt[0] = c.dt;
+        if (c.nhist < 4) c.nhist += 1;
+    };
     const double beta1 = 7.0 / 50.0, beta2 = 2.0 / 25.0, gamma = 0.9, qmin = 0.2, qmax = 10.0;
     if (c.fixed) {
-        c.accepted = 1; c.naccept += 1; c.t += c.dt; c.dt_last = c.dt;
+        c.accepted = 1; c.naccept += 1; c.t += c.dt; c.dt_last = c.dt; record();
         if (c.t + c.dt > c.tstop) c.dt = c.tstop - c.t;
         if (c.t >= c.tstop - 4e-16 * fabs(c.tstop) || c.dt <= 0.0) c.done = 1;
         return;
@@ -165,7 +180,7 @@ __global__ void controller_kernel(CtlArgs a)
     q = fmax(1.0 / qmax, fmin(1.0 / qmin, q / gamma));
     if (eest <= 1.0) {
         c.accepted = 1; c.naccept += 1;
-        c.t += c.dt; c.dt_last = c.dt;
+        c.t += c.dt; c.dt_last = c.dt; record();
         c.qold = fmax(eest, 1e-4);
         double dtn = c.dt / q;
         if (dtn > c.dtmax) dtn = c.dtmax;
@@ -189,11 +204,123 @@ accept_kernel(const StepCtl* __restrict__ ctl, size_t n, const double* __restric
     if (i < n) { u[i] = unew[i]; k1[i] = k7[i]; }
 }
 
-static int enqueue_step(OqProblem* p)
+// on acceptance, multistep bookkeeping included: u <- unew and the derivative history shifts by one step
+__global__ void __launch_bounds__(256)
+accept_hist_kernel(const StepCtl* __restrict__ ctl, size_t n, const double* __restrict__ unew,
+                   const double* __restrict__ fnew, double* __restrict__ u, double* __restrict__ f0,
+                   double* __restrict__ h0, double* __restrict__ h1, double* __restrict__ h2, double* __restrict__ h3)
+{
+    if (!ctl->accepted) return;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u[i] = unew[i];
+    h3[i] = h2[i]; h2[i] = h1[i]; h1[i] = h0[i]; h0[i] = f0[i]; f0[i] = fnew[i];
+}
+
+// Weights of the variable-coefficient Adams formulas for the step [t_n, t_n + dt] on the grid of the last
+// accepted steps: exact integrals of the Lagrange basis polynomials through the derivative samples
+// (3-point Gauss-Legendre integrates the degree <= 5 basis exactly).  Node 0 is t_n + dt (the predicted
+// derivative), nodes 1..5 are t_n, t_{n-1}, ..., t_{n-4}.
+//   coef[0..3]   predictor (Adams-Bashforth on nodes 1-4, order 4)
+//   coef[4..8]   corrector (Adams-Moulton on nodes 0-4, order 5): what the step advances with
+//   coef[10..15] error estimate: order-6 formula (nodes 0-5) minus the corrector
+// This is the Lagrange form of the divided-difference (g, phi, phi*) recurrences of Hairer, Norsett & Wanner
+// III.5 that oracle/integrator.py follows -- two formulations of one formula.
+constexpr int kCoefPred = 0, kCoefCorr = 4, kCoefErr = 10, kCoefLen = 16;
+
+__global__ void abm_coef_kernel(const StepCtl* __restrict__ ctl, double* __restrict__ coef)
+{
+    __shared__ double w[15];
+    if (ctl->done) return;
+    const int t = threadIdx.x;
+    const double dt = ctl->dt;
+    double tau[6];
+    tau[0] = dt; tau[1] = 0.0;
+    tau[2] = -ctl->hdt[0]; tau[3] = tau[2] - ctl->hdt[1]; tau[4] = tau[3] - ctl->hdt[2]; tau[5] = tau[4] - ctl->hdt[3];
+    if (t < 15) {
+        int lo, hi, m;                                     // node set [lo, hi], basis node m
+        if (t < 4) { lo = 1; hi = 4; m = 1 + t; }
+        else if (t < 9) { lo = 0; hi = 4; m = t - 4; }
+        else { lo = 0; hi = 5; m = t - 9; }
+        double den = 1.0;
+        for (int k = lo; k <= hi; ++k)
+            if (k != m) den *= tau[m] - tau[k];
+        const double gx[3] = {-0.7745966692414834, 0.0, 0.7745966692414834};
+        const double gw[3] = {5.0 / 9.0, 8.0 / 9.0, 5.0 / 9.0};
+        double acc = 0.0;
+        for (int q = 0; q < 3; ++q) {
+            const double x = 0.5 * dt * (1.0 + gx[q]);
+            double num = 1.0;
+            for (int k = lo; k <= hi; ++k)
+                if (k != m) num *= x - tau[k];
+            acc = fma(gw[q], num, acc);
+        }
+        w[t] = 0.5 * dt * acc / den;
+    }
+    __syncthreads();
+    if (t < 4) coef[kCoefPred + t] = w[t];
+    if (t >= 4 && t < 9) coef[kCoefCorr + (t - 4)] = w[t];
+    if (t >= 9 && t < 15) coef[kCoefErr + (t - 9)] = w[t] - (t - 9 < 5 ? w[4 + (t - 9)] : 0.0);
+}
+
+static int launch_error_and_control(OqProblem* p, const Stages& ks, const double* wdev, int nrhs_inc)
 {
     cudaStream_t st = p->stream;
     const size_t n = p->nstate;
     const unsigned blocks = (unsigned)((n + 255) / 256);
+    StepCtl* ctl = reinterpret_cast<StepCtl*>(p->ctl.p);
+    ErrArgs ea{};
+    ea.u = p->u.p; ea.unew = p->unew.p; ea.ks = ks; ea.wdev = wdev; ea.ctl = ctl; ea.n = n; ea.errpart = p->errpart.p;
+    ea.epochs = p->epochs; ea.peers = comm_targets(p); ea.wl = p->wl;
+    unsigned eblocks = blocks < 512 ? blocks : 512;
+    error_kernel<<<eblocks, 256, 0, st>>>(ea);
+    OQ_LAUNCHED();
+    CtlArgs ca{ctl, p->red_slots, p->flags, p->epochs, p->world, p->rank, (double)p->nstate_global, nrhs_inc};
+    controller_kernel<<<1, 32, 0, st>>>(ca);
+    OQ_LAUNCHED();
+    return 0;
+}
+
+static int launch_accept(OqProblem* p, bool with_history)
+{
+    const size_t n = p->nstate;
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    const StepCtl* ctl = reinterpret_cast<const StepCtl*>(p->ctl.p);
+    if (with_history)
+        accept_hist_kernel<<<blocks, 256, 0, p->stream>>>(ctl, n, p->unew.p, p->k[6].p, p->u.p, p->k[0].p,
+                                                          p->hist[0].p, p->hist[1].p, p->hist[2].p, p->hist[3].p);
+    else
+        accept_kernel<<<blocks, 256, 0, p->stream>>>(ctl, n, p->unew.p, p->k[6].p, p->u.p, p->k[0].p);
+    OQ_LAUNCHED();
+    return 0;
+}
+
+// one predictor-evaluate-corrector-evaluate step of the order-5 Adams pair; f(t_n) is k[0], older samples hist[]
+static int enqueue_abm_step(OqProblem* p)
+{
+    StepCtl* ctl = reinterpret_cast<StepCtl*>(p->ctl.p);
+    double* coef = p->abm_coef.p;
+    abm_coef_kernel<<<1, 32, 0, p->stream>>>(ctl, coef);
+    OQ_LAUNCHED();
+    StageSpec pred;                  // P: utmp = u + sum wp_m f_{n-m};  E: k[1] = f(utmp)
+    pred.nk = 4; pred.u = p->u.p; pred.adev = coef + kCoefPred; pred.done = &ctl->done;
+    pred.k[0] = p->k[0].p; pred.k[1] = p->hist[0].p; pred.k[2] = p->hist[1].p; pred.k[3] = p->hist[2].p;
+    OQ_TRY(rhs_device(p, p->utmp.p, p->k[1].p, &pred));
+    StageSpec corr;                  // C: unew = u + wc_0 f(utmp) + sum wc_m f_{n-m+1};  E: k[6] = f(unew)
+    corr.nk = 5; corr.u = p->u.p; corr.adev = coef + kCoefCorr; corr.done = &ctl->done;
+    corr.k[0] = p->k[1].p; corr.k[1] = p->k[0].p; corr.k[2] = p->hist[0].p; corr.k[3] = p->hist[1].p;
+    corr.k[4] = p->hist[2].p;
+    OQ_TRY(rhs_device(p, p->unew.p, p->k[6].p, &corr));
+    Stages ks{};
+    ks.k[0] = p->k[1].p; ks.k[1] = p->k[0].p;
+    for (int j = 0; j < 4; ++j) ks.k[2 + j] = p->hist[j].p;
+    ks.k[6] = p->k[0].p;             // unused
+    OQ_TRY(launch_error_and_control(p, ks, coef + kCoefErr, 2));
+    return launch_accept(p, true);
+}
+
+static int enqueue_step(OqProblem* p, bool with_history)
+{
     StepCtl* ctl = reinterpret_cast<StepCtl*>(p->ctl.p);
     Stages ks;
     for (int j = 0; j < 7; ++j) ks.k[j] = p->k[j].p;
@@ -205,18 +332,8 @@ static int enqueue_step(OqProblem* p)
         for (int j = 0; j < s; ++j) { sp.k[j] = p->k[j].p; sp.a[j] = hA[s][j]; }
         OQ_TRY(rhs_device(p, y, p->k[s].p, &sp));
     }
-    ErrArgs ea{};
-    ea.u = p->u.p; ea.unew = p->unew.p; ea.ks = ks; ea.ctl = ctl; ea.n = n; ea.errpart = p->errpart.p;
-    ea.epochs = p->epochs; ea.peers = comm_targets(p); ea.wl = p->wl;
-    unsigned eblocks = blocks < 512 ? blocks : 512;
-    error_kernel<<<eblocks, 256, 0, st>>>(ea);
-    OQ_LAUNCHED();
-    CtlArgs ca{ctl, p->red_slots, p->flags, p->epochs, p->world, p->rank, (double)p->nstate_global};
-    controller_kernel<<<1, 32, 0, st>>>(ca);
-    OQ_LAUNCHED();
-    accept_kernel<<<blocks, 256, 0, st>>>(ctl, n, p->unew.p, p->k[6].p, p->u.p, p->k[0].p);
-    OQ_LAUNCHED();
-    return 0;
+    OQ_TRY(launch_error_and_control(p, ks, nullptr, 6));
+    return launch_accept(p, with_history);
 }
 
 }  // namespace oq
@@ -227,7 +344,9 @@ extern "C" int oq_solve(OqProblem* p, double t0, const OqSolveOptions* o, int64_
                         OqSolveStats* stats)
 {
     OQ_CHECK(p && o, "NULL argument");
-    OQ_CHECK(o->algorithm == 0, "only Tsit5 (algorithm 0) is implemented");
+    OQ_CHECK(o->algorithm == OQ_ALG_TSIT5 || o->algorithm == OQ_ALG_VCABM5,
+             "unknown algorithm (0 = Tsit5, 1 = VCABM5)");
+    const bool multistep = o->algorithm == OQ_ALG_VCABM5;
     OQ_CHECK(o->tstop > t0, "tstop must be greater than t0");
     OQ_CHECK(o->fixed_dt || (o->reltol > 0 && o->abstol > 0), "tolerances must be positive");
     OQ_TRY(enter());
@@ -239,6 +358,11 @@ extern "C" int oq_solve(OqProblem* p, double t0, const OqSolveOptions* o, int64_
     if (h.dt > h.dtmax) h.dt = h.dtmax;
     if (t0 + h.dt > o->tstop) h.dt = o->tstop - t0;
     h.qold = 1e-4; h.reltol = o->reltol; h.abstol = o->abstol; h.fixed = o->fixed_dt;
+    if (multistep) {
+        for (int i = 0; i < 4; ++i)
+            if (!p->hist[i].p) { OQ_TRY(p->hist[i].alloc(p->nstate + 2)); OQ_TRY(p->hist[i].zero()); }
+        if (!p->abm_coef.p) { OQ_TRY(p->abm_coef.alloc(kCoefLen)); OQ_TRY(p->abm_coef.zero()); }
+    }
     OQ_CUDA(cudaMemcpyAsync(p->ctl.p, &h, sizeof(h), cudaMemcpyHostToDevice, p->stream));
     // k1 = f(u0)
     OQ_TRY(rhs_device(p, p->u.p, p->k[0].p));
@@ -261,18 +385,30 @@ extern "C" int oq_solve(OqProblem* p, double t0, const OqSolveOptions* o, int64_
     int stop = snapshot(t0, 0);
     if (stop < 0) return 1;
 
-    // capture one step into a CUDA graph (all step-dependent scalars live in device memory)
-    cudaGraph_t graph = nullptr;
-    cudaGraphExec_t exec = nullptr;
-    OQ_CUDA(cudaStreamBeginCapture(p->stream, cudaStreamCaptureModeThreadLocal));
-    const int64_t launches_before = g_launches.load();
-    int rc = enqueue_step(p);
-    const int64_t per_step = g_launches.load() - launches_before;
-    cudaError_t ce = cudaStreamEndCapture(p->stream, &graph);
-    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
-    OQ_CUDA(ce);
-    OQ_CUDA(cudaGraphInstantiate(&exec, graph, 0));
-    g_launches.fetch_sub(per_step);   // capture enqueued nothing yet
+    // capture one step into a CUDA graph (all step-dependent scalars live in device memory); the multistep
+    // method has two: the Runge-Kutta step that builds its history, and the Adams step
+    struct StepGraph {
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        int64_t launches = 0;
+        ~StepGraph() { if (exec) cudaGraphExecDestroy(exec); if (graph) cudaGraphDestroy(graph); }
+    } rk, abm;
+    auto capture = [&](StepGraph& g, bool adams) -> int {
+        OQ_CUDA(cudaStreamBeginCapture(p->stream, cudaStreamCaptureModeThreadLocal));
+        const int64_t before = g_launches.load();
+        const int r = adams ? enqueue_abm_step(p) : enqueue_step(p, multistep);
+        g.launches = g_launches.load() - before;
+        g_launches.fetch_sub(g.launches);   // capture enqueued nothing yet
+        const cudaError_t e = cudaStreamEndCapture(p->stream, &g.graph);
+        if (r) return r;
+        OQ_CUDA(e);
+        OQ_CUDA(cudaGraphInstantiate(&g.exec, g.graph, 0));
+        return 0;
+    };
+    int rc = capture(rk, false);
+    if (rc) return rc;
+    if (multistep) { rc = capture(abm, true); if (rc) return rc; }
+    cudaError_t ce = cudaSuccess;
 
     const int64_t maxiters = o->maxiters > 0 ? o->maxiters : 1000000;
     int64_t iters = 0;
@@ -285,10 +421,14 @@ extern "C" int oq_solve(OqProblem* p, double t0, const OqSolveOptions* o, int64_
         int64_t batch = fn ? stride - (h.naccept % stride) : kMaxBatch;
         if (batch > kMaxBatch) batch = kMaxBatch;
         if (batch > maxiters - iters) batch = maxiters - iters;
+        // the Adams pair needs four accepted steps of history; until then Tsit5 steps, one at a time
+        const bool adams = multistep && h.nhist >= 4;
+        if (multistep && !adams) batch = 1;
         if (batch < 1) batch = 1;
+        const StepGraph& g = adams ? abm : rk;
         for (int64_t b = 0; b < batch && ce == cudaSuccess; ++b) {
-            ce = cudaGraphLaunch(exec, p->stream);
-            g_launches.fetch_add(per_step);
+            ce = cudaGraphLaunch(g.exec, p->stream);
+            g_launches.fetch_add(g.launches);
         }
         if (ce != cudaSuccess) { rc = fail("cudaGraphLaunch: %s", cudaGetErrorString(ce)); break; }
         const int64_t acc_before = h.naccept;
@@ -303,8 +443,6 @@ extern "C" int oq_solve(OqProblem* p, double t0, const OqSolveOptions* o, int64_
     }
     unsigned long long eflag = 0;
     cudaMemcpy(&eflag, p->epochs + kEpError, sizeof(eflag), cudaMemcpyDeviceToHost);
-    cudaGraphExecDestroy(exec);
-    cudaGraphDestroy(graph);
     if (!rc && eflag) rc = fail("timed out waiting for a peer rank during the solve");
     if (stats) {
         stats->t = h.t; stats->dt_last = h.dt_last; stats->dt_next = h.dt;

@@ -244,7 +244,22 @@ def assemble(*args, se=DieterichStateLaw(), gf11_form: str = "dense", fault_rows
 
 # ------------------------------------------------------------------------------------------------ solve
 class Tsit5:
+    """Tsitouras 5(4) Runge-Kutta pair (the algorithm of the reference's tests, test/tests.jl:11)."""
     code = 0
+
+
+class VCABM5:
+    """Variable-coefficient Adams-Bashforth-Moulton PECE of order 5, started with four Tsit5 steps (the
+    algorithm of the reference's example, examples/otf-with-mantle.jl:160-162): 2 RHS evaluations per step."""
+    code = 1
+
+
+def _alg_code(alg) -> int:
+    if alg is Tsit5 or isinstance(alg, Tsit5):
+        return Tsit5.code
+    if alg is VCABM5 or isinstance(alg, VCABM5):
+        return VCABM5.code
+    raise TypeError(f"unsupported algorithm {alg!r}: Tsit5() and VCABM5() are implemented")
 
 
 @dataclass
@@ -259,18 +274,18 @@ class ODESolution:
 def solve(prob: ODEProblem, alg=Tsit5(), *, reltol=1e-3, abstol=1e-6, dt=0.0, dtmax=0.0, maxiters=int(1e5),
           stride: int = 1, save_everystep: bool = True, callback: Optional[Callable] = None,
           adaptive: bool = True, local_u0: Optional[Sequence[np.ndarray]] = None) -> ODESolution:
-    """Device-resident counterpart of OrdinaryDiffEq's `solve(prob, Tsit5(); reltol, abstol, dt, dtmax,
-    maxiters)` (defaults reltol=1e-3, abstol=1e-6 as in OrdinaryDiffEq).  `callback(u, t, step)` plays the
+    """Device-resident counterpart of OrdinaryDiffEq's `solve(prob, alg; reltol, abstol, dt, dtmax,
+    maxiters)` for alg = Tsit5() or VCABM5() (defaults reltol=1e-3, abstol=1e-6 as in OrdinaryDiffEq).  `callback(u, t, step)` plays the
     role of wsolve's FunctionCallingCallback (src/io.jl:128-130): it fires at t0 and after every
     `stride`-th accepted step.  `local_u0`: this rank's slices of the state for multi-GPU runs."""
-    assert isinstance(alg, Tsit5) or alg is Tsit5, "only Tsit5 is implemented"
+    code = _alg_code(alg)
     p = prob.p
     parts0 = list(local_u0) if local_u0 is not None else list(prob.u0.x)
     p.set_state(parts0)
     shapes = [np.shape(a) for a in parts0]
     sol = ODESolution()
     opts = _lib.OqSolveOptions(float(reltol), float(abstol), float(dt), float(dtmax), float(prob.tspan[1]),
-                               int(maxiters), 0, 0 if adaptive else 1)
+                               int(maxiters), code, 0 if adaptive else 1)
     stats = _lib.OqSolveStats()
 
     def _snap(user, t, step, pu, pdu):

@@ -17,7 +17,7 @@ from typing import Callable, List, Sequence
 
 import numpy as np
 
-from .equation import ODEProblem, Tsit5, solve
+from .equation import ODEProblem, _alg_code, solve
 
 log = logging.getLogger("oetqf_b200")
 
@@ -79,7 +79,7 @@ def wsolve(prob: ODEProblem, alg, file: str, nstep: int, getu: Callable, ustrs: 
     """wsolve(prob, alg, file, nstep, getu, ustrs, tstr; stride, append, force, kwargs...)  (io.jl:118-133).
     `getu(u, t, du)` returns the tuple of arrays to save (du = derivative at t, the role of
     `integrator(t, Val{1})` in the reference's handlers)."""
-    assert isinstance(alg, Tsit5) or alg is Tsit5
+    _alg_code(alg)                       # raises for algorithms the device integrator does not provide
     if os.path.exists(file) and not force and not append:
         log.info("Overwrite existing file %s must set `force = true`.", file)
         log.info("Aborting computation.")

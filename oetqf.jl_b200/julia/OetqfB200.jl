@@ -219,4 +219,55 @@ function assemble(gf₁₁::AbstractArray, gf₁₂::AbstractMatrix, gf₂₁::A
     ODEProblem{true}(ode, u0, tspan, DeviceProblem(h[], Any[g11[], d12, d21, d22]))
 end
 
+# ---------------------------------------------------------------- resident mode: the whole integration on the GPU
+struct OqSolveOptions
+    reltol::Float64; abstol::Float64; dt0::Float64; dtmax::Float64; tstop::Float64
+    maxiters::Int64; algorithm::Int32; fixed_dt::Int32
+end
+
+struct OqSolveStats
+    t::Float64; dt_last::Float64; dt_next::Float64
+    naccept::Int64; nreject::Int64; nrhs::Int64
+    retcode::Int32
+end
+
+const ALGORITHMS = Dict(:Tsit5 => Int32(0), :VCABM5 => Int32(1))
+
+# snapshot trampoline: `user` points at a Julia closure (u_parts, du_parts arrive as host pointers valid for the call)
+function _snapshot(user::Ptr{Cvoid}, t::Cdouble, step::Int64, pu::Ptr{Ptr{Cdouble}}, pdu::Ptr{Ptr{Cdouble}})::Cint
+    f = unsafe_pointer_to_objref(user)::Function
+    try
+        return f(t, step, pu, pdu) ? Cint(1) : Cint(0)
+    catch
+        return Cint(1)          # never unwind through the C frame
+    end
+end
+
+"""
+    solve_resident(prob, alg = :VCABM5; reltol, abstol, dt, dtmax, maxiters, stride, callback)
+
+Counterpart of `solve(prob, VCABM5(); ...)` (examples/otf-with-mantle.jl:160-162) with stage combinations, error
+norm and step-size control on the device; `callback(u::ArrayPartition, t, du::ArrayPartition)` fires at t0 and after
+every `stride`-th accepted step (the role of wsolve's FunctionCallingCallback, src/io.jl:51-58).
+"""
+function solve_resident(prob::ODEProblem, alg::Symbol = :VCABM5; reltol = 1e-3, abstol = 1e-6, dt = 0.0, dtmax = 0.0,
+    maxiters = 100_000, stride = 1, callback = nothing)
+    p = prob.p::DeviceProblem
+    up = Ptr{Float64}[pointer(x) for x in prob.u0.x]
+    GC.@preserve prob up check(ccall((:oq_state_set, LIB), Cint, (Ptr{Cvoid}, Ptr{Ptr{Cdouble}}), p.h, up))
+    shapes = map(size, prob.u0.x)
+    wrap(pp) = ArrayPartition((copy(unsafe_wrap(Array, unsafe_load(pp, i), shapes[i])) for i in eachindex(shapes))...)
+    cb = (t, step, pu, pdu) -> callback === nothing ? false : (callback(wrap(pu), t, wrap(pdu)) === true)
+    opts = OqSolveOptions(reltol, abstol, dt, dtmax, prob.tspan[2], maxiters, ALGORITHMS[alg], 0)
+    stats = Ref(OqSolveStats(0, 0, 0, 0, 0, 0, 0))
+    cfn = @cfunction(_snapshot, Cint, (Ptr{Cvoid}, Cdouble, Int64, Ptr{Ptr{Cdouble}}, Ptr{Ptr{Cdouble}}))
+    GC.@preserve cb check(ccall((:oq_solve, LIB), Cint,
+        (Ptr{Cvoid}, Cdouble, Ref{OqSolveOptions}, Int64, Ptr{Cvoid}, Any, Ref{OqSolveStats}),
+        p.h, prob.tspan[1], opts, stride, callback === nothing ? C_NULL : cfn, cb, stats))
+    u = deepcopy(prob.u0)
+    up2 = Ptr{Float64}[pointer(x) for x in u.x]
+    GC.@preserve u up2 check(ccall((:oq_state_get, LIB), Cint, (Ptr{Cvoid}, Ptr{Ptr{Cdouble}}), p.h, up2))
+    (u = u, stats = stats[])
+end
+
 end # module

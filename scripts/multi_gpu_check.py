@@ -83,30 +83,31 @@ def main():
             print(f"[rank {rank}] RHS partition {k}: rel err {err:.3e}", flush=True)
 
     # ---------------- integrator: sharded vs full ----------------
-    sol = oq.solve(prob, oq.Tsit5(), reltol=1e-7, abstol=1e-9, dt=1e-6, dtmax=0.2 * W.YEAR, local_u0=loc,
-                   save_everystep=False, maxiters=4000)
-    solf = oq.solve(full, oq.Tsit5(), reltol=1e-7, abstol=1e-9, dt=1e-6, dtmax=0.2 * W.YEAR,
-                    save_everystep=False, maxiters=4000)
-    if sol.retcode != "Success" or solf.retcode != "Success":
-        ok = False
-        print(f"[rank {rank}] retcodes {sol.retcode} {solf.retcode}", flush=True)
-    if sol.stats["naccept"] != solf.stats["naccept"] or sol.stats["nreject"] != solf.stats["nreject"]:
-        ok = False
-        print(f"[rank {rank}] step counts differ: {sol.stats} vs {solf.stats}", flush=True)
-    uf = solf.u[-1].x
-    wantu = [uf[0].reshape(-1, order="F")[f0:f1], uf[1].reshape(-1, order="F")[f0:f1],
-             uf[2][e0:e1, :].reshape(-1, order="F"), uf[3][e0:e1, :].reshape(-1, order="F"),
-             uf[4].reshape(-1, order="F")[f0:f1]]
-    for k, (gt, w) in enumerate(zip(sol.u[-1].x, wantu)):
-        gt = np.asarray(gt).reshape(-1, order="F")
-        # components that stay ~0 by symmetry (e.g. eps_xz) carry only round-off: floor at 1e-3 of the field
-        den = np.maximum(np.abs(w), 1e-3 * np.max(np.abs(w)) + 1e-300)
-        err = float(np.max(np.abs(gt - w) / den)) if w.size else 0.0
-        if err > 1e-6:
+    for alg in (oq.Tsit5(), oq.VCABM5()):
+        sol = oq.solve(prob, alg, reltol=1e-7, abstol=1e-9, dt=1e-6, dtmax=0.2 * W.YEAR, local_u0=loc,
+                       save_everystep=False, maxiters=4000)
+        solf = oq.solve(full, alg, reltol=1e-7, abstol=1e-9, dt=1e-6, dtmax=0.2 * W.YEAR,
+                        save_everystep=False, maxiters=4000)
+        if sol.retcode != "Success" or solf.retcode != "Success":
             ok = False
-            print(f"[rank {rank}] solve partition {k}: rel err {err:.3e}", flush=True)
-    print(f"[rank {rank}] rows={rows} elems={elems} steps={sol.stats['naccept']}+{sol.stats['nreject']} "
-          f"t={sol.stats['t']:.4e} ok={ok}", flush=True)
+            print(f"[rank {rank}] retcodes {sol.retcode} {solf.retcode}", flush=True)
+        if sol.stats["naccept"] != solf.stats["naccept"] or sol.stats["nreject"] != solf.stats["nreject"]:
+            ok = False
+            print(f"[rank {rank}] step counts differ: {sol.stats} vs {solf.stats}", flush=True)
+        uf = solf.u[-1].x
+        wantu = [uf[0].reshape(-1, order="F")[f0:f1], uf[1].reshape(-1, order="F")[f0:f1],
+                 uf[2][e0:e1, :].reshape(-1, order="F"), uf[3][e0:e1, :].reshape(-1, order="F"),
+                 uf[4].reshape(-1, order="F")[f0:f1]]
+        for k, (gt, w) in enumerate(zip(sol.u[-1].x, wantu)):
+            gt = np.asarray(gt).reshape(-1, order="F")
+            # components that stay ~0 by symmetry (e.g. eps_xz) carry only round-off: floor at 1e-3 of the field
+            den = np.maximum(np.abs(w), 1e-3 * np.max(np.abs(w)) + 1e-300)
+            err = float(np.max(np.abs(gt - w) / den)) if w.size else 0.0
+            if err > 1e-6:
+                ok = False
+                print(f"[rank {rank}] solve partition {k}: rel err {err:.3e}", flush=True)
+        print(f"[rank {rank}] {type(alg).__name__} rows={rows} elems={elems} steps={sol.stats['naccept']}+{sol.stats['nreject']} "
+              f"t={sol.stats['t']:.4e} ok={ok}", flush=True)
     t = torch.tensor([0 if ok else 1], device="cuda")
     dist.all_reduce(t)
     dist.barrier()

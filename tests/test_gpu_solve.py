@@ -89,6 +89,110 @@ def test_fault_cycle_window_matches_oracle(gpu):
     assert worst_v < 1e-6 and worst_th < 1e-6, (worst_v, worst_th)
 
 
+def test_vcabm5_decay_problem_matches_oracle(gpu):
+    """the multistep integrator (examples/otf-with-mantle.jl:160-162 asks for VCABM5) on the linear problem of
+    test/tests.jl:2-7: device Lagrange form vs the oracle's divided-difference form of the same Adams pair"""
+    oq = gpu
+    nx, nxi = 4, 3
+    rng = np.random.default_rng(3)
+    a, b, L, sig = (rng.uniform(0.5, 1.5, (nx, nxi)) for _ in range(4))
+    v, th, dl = (rng.uniform(0.5, 1.5, (nx, nxi)) for _ in range(3))
+    st = np.zeros((nx, nxi, nxi), order="F")
+    pf_p = oq.RateStateQuasiDynamicProperty(a, b, L, sig, 0.7, 0.3, 0.6, 0.9)
+    pf_o = ref.FaultProp(a, b, L, sig, 0.7, 0.3, 0.6, 0.9)
+    u0 = oq.ArrayPartition(v, th, dl)
+    shapes = [x.shape for x in u0.x]
+
+    def f(u):
+        vv, tt, _ = _unpack(u, shapes)
+        return _pack(ref.rhs_fault(pf_o, st, vv, tt, form="toeplitz"))
+
+    ts, us, stats = integrator.vcabm5(f, _pack(u0.x), 0.0, 2.0, reltol=1e-8, abstol=1e-10, dt0=1e-3)
+    for form in ("dense", "fft"):
+        prob = oq.assemble(st, pf_p, u0, (0.0, 2.0), gf11_form=form)
+        sol = oq.solve(prob, oq.VCABM5(), reltol=1e-8, abstol=1e-10, dt=1e-3)
+        assert sol.retcode == "Success"
+        assert sol.stats["naccept"] == stats["naccept"] and sol.stats["nreject"] == stats["nreject"]
+        assert sol.stats["nf"] == stats["nrhs"]             # 6 per starting step, 2 per Adams step, 1 initial
+        np.testing.assert_allclose(sol.t, ts, rtol=2e-5)    # the estimate is a 6-term cancelling sum: round-off moves dt
+        for k in (len(ts) // 2, len(ts) - 1):
+            np.testing.assert_allclose(_pack(sol.u[k].x), us[k], rtol=1e-6)
+        assert sol.t[-1] == 2.0
+
+
+def test_vcabm5_fault_cycle_window_matches_oracle_and_tsit5(gpu):
+    """configs[0]-like fault: VCABM5 v and θ series within 1e-6 of the CPU oracle at every accepted step, and the
+    end state agrees with the Tsit5 run of the same window to the integration tolerance"""
+    oq = gpu
+    spec = W.C1_FAULT
+    mf_o, mf_p = meshes(oq, spec)
+    a, b, L, sig = W.fault_properties(mf_o.x, mf_o.z, mf_o.nx, mf_o.nxi)
+    v, th, dl = W.initial_state(mf_o.nx, mf_o.nxi, L)
+    st = ref.gf_fault_fault(mf_o, W.LAM, W.MU, buffer_ratio=1.0)
+    pf_o = ref.FaultProp(a, b, L, sig, W.ETA, W.VPL, W.F0, W.V0)
+    pf_p = oq.RateStateQuasiDynamicProperty(a, b, L, sig, W.ETA, W.VPL, W.F0, W.V0)
+    u0 = oq.ArrayPartition(v, th, dl)
+    shapes = [x.shape for x in u0.x]
+    tstop = 0.02 * W.YEAR
+
+    def f(u):
+        vv, tt, _ = _unpack(u, shapes)
+        return _pack(ref.rhs_fault(pf_o, st, vv, tt, form="toeplitz"))
+
+    kw = dict(reltol=1e-8, abstol=1e-10, dtmax=0.2 * W.YEAR)
+    ts, us, stats = integrator.vcabm5(f, _pack(u0.x), 0.0, tstop, dt0=1e-6, **kw)
+    gf = oq.stress_greens_function(mf_p, W.LAM, W.MU, buffer_ratio=1.0, fourier=False)
+    prob = oq.assemble(gf, pf_p, u0, (0.0, tstop), gf11_form="fft")
+    sol = oq.solve(prob, oq.VCABM5(), dt=1e-6, **kw)
+    assert sol.retcode == "Success" and len(sol.t) == len(ts), (len(sol.t), len(ts))
+    np.testing.assert_allclose(sol.t, ts, rtol=2e-5)
+    n = v.size
+    worst = 0.0
+    for k in range(len(ts)):
+        uk = _pack(sol.u[k].x)
+        worst = max(worst, np.max(np.abs(uk[:2 * n] - us[k][:2 * n]) / np.abs(us[k][:2 * n])))
+    assert worst < 1e-6, worst
+    rk = oq.solve(prob, oq.Tsit5(), dt=1e-6, **kw)
+    assert sol.stats["nf"] < rk.stats["nf"]                 # the point of the multistep method
+    np.testing.assert_allclose(_pack(sol.u[-1].x)[:2 * n], _pack(rk.u[-1].x)[:2 * n], rtol=1e-5)
+
+
+def test_vcabm5_viscoelastic_example_matches_oracle(gpu):
+    """configs[1] (the reference's example problem, fault + 36 hex8 cells) stepped with VCABM5 as the example
+    does: 5-partition state vs the CPU oracle RHS under the oracle's Adams stepping"""
+    oq = gpu
+    mf_o, mf_p, ma_o, ma_p = meshes(oq, W.C2_FAULT, W.C2_BOX)
+    a, b, L, sig = W.fault_properties(mf_o.x, mf_o.z, mf_o.nx, mf_o.nxi)
+    g, n, d0 = W.mantle_properties(ma_o.cz)
+    v, th, eps, sg, dl = W.initial_state(mf_o.nx, mf_o.nxi, L, ma_o.cz, g, n)
+    st = ref.gf_fault_fault(mf_o, W.LAM, W.MU, buffer_ratio=1.0)
+    g12 = ref.gf_fault_mantle(mf_o, ma_o, W.LAM, W.MU, buffer_ratio=1.0)
+    g21 = ref.gf_mantle_fault(ma_o, mf_o, W.LAM, W.MU)
+    g22 = ref.gf_mantle_mantle(ma_o, W.LAM, W.MU)
+    pf_o = ref.FaultProp(a, b, L, sig, W.ETA, W.VPL, W.F0, W.V0)
+    pa_o = ref.MantleProp(g[None, :], n[None, :], d0)
+    pf_p = oq.RateStateQuasiDynamicProperty(a, b, L, sig, W.ETA, W.VPL, W.F0, W.V0)
+    pa_p = oq.PowerLawViscosityProperty(g, n, d0)
+    u0 = oq.ArrayPartition(v, th, eps, sg, dl)
+    shapes = [x.shape for x in u0.x]
+    tstop = 0.05 * W.YEAR
+
+    def f(u):
+        vv, tt, _, ss, _ = _unpack(u, shapes)
+        return _pack(ref.rhs_viscoelastic(pf_o, pa_o, st, g12, g21, g22, vv, tt, ss, form="toeplitz"))
+
+    kw = dict(reltol=1e-6, abstol=1e-8, dtmax=0.2 * W.YEAR)
+    ts, us, stats = integrator.vcabm5(f, _pack(u0.x), 0.0, tstop, dt0=1e-8, **kw)
+    prob = oq.assemble(st, g12, g21, g22, pf_p, pa_p, u0, (0.0, tstop))
+    sol = oq.solve(prob, oq.VCABM5(), dt=1e-8, **kw)
+    assert sol.retcode == "Success" and len(sol.t) == len(ts), (len(sol.t), len(ts))
+    np.testing.assert_allclose(sol.t, ts, rtol=1e-4)
+    uk, uo = _pack(sol.u[-1].x), us[-1]
+    n = v.size
+    np.testing.assert_allclose(uk[:2 * n], uo[:2 * n], rtol=1e-6)
+    np.testing.assert_allclose(uk, uo, rtol=1e-5, atol=1e-12 * np.max(np.abs(uo)))
+
+
 def test_stride_and_callback(gpu):
     """wsolve's saving cadence (src/io.jl:51-58, test/tests.jl:34-41): every stride-th accepted step + t0"""
     oq = gpu
