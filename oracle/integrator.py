@@ -101,6 +101,85 @@ def _pi_controller(eest, qold, dt, beta1=7 / 50, beta2=2 / 25, gamma=0.9, qmin=0
     return q11, q
 
 
+def _tsit5_step(f, u, k1, dt):
+    """one Tsit5 step from (u, k1 = f(u)): returns (unew, err, f(unew)); 6 evaluations"""
+    k = [k1] + [None] * 6
+    for s in range(1, 7):
+        acc = np.zeros_like(u)
+        for j in range(s):
+            acc = acc + A[s][j] * k[j]
+        y = u + dt * acc
+        k[s] = f(y)
+    err = np.zeros_like(u)
+    for j in range(7):
+        err = err + BTILDE[j] * k[j]
+    return y, err * dt, k[6]
+
+
+def _adams_step(f, u, hist_f, hist_dt, dt):
+    """one PECE step of the order-5 variable-coefficient Adams pair on the grid dts = (dt, h_{n-1}, h_{n-2}, ...).
+    hist_f = [f(t_n), f(t_{n-1}), ...] (>= 5 samples), hist_dt = [h_{n-1}, h_{n-2}, ...] (>= 4 accepted steps).
+    Returns (unew, err, f(unew)); 2 evaluations."""
+    dts = [dt] + list(hist_dt[:4])
+
+    # phi_j(m): modified divided differences, rebuilt from the raw samples through
+    # phi_{j+1}(m) = phi_j(m) - phi*_j(m-1), phi*_j(m-1) = beta_j(m-1) phi_j(m-1),
+    # beta_j(m-1) = prod_{i<j-1} (t_m - t_{m-1-i}) / (t_{m-1} - t_{m-2-i})
+    def phis(level, depth):
+        out = [hist_f[level]]
+        if depth > 1:
+            prev = phis(level + 1, depth - 1)
+            grid = hist_dt[level:]
+            beta, xi, xi0 = 1.0, grid[0], 0.0
+            for j in range(1, depth):
+                if j > 1:
+                    xi0 += grid[j - 1]
+                    beta = beta * xi / xi0
+                    xi += grid[j - 1]
+                out.append(out[j - 1] - beta * prev[j - 1])
+        return out
+
+    phi_n = phis(0, 5)
+    beta = [1.0]
+    xi, xi0 = dts[0], 0.0
+    for i in range(1, 5):
+        xi0 += dts[i]
+        beta.append(beta[i - 1] * xi / xi0)
+        xi += dts[i]
+    phistar = [beta[i] * phi_n[i] for i in range(5)]
+    # g_j(n): c_{1,q} = 1/q, c_{2,q} = 1/(q(q+1)), c_{j,q} = c_{j-1,q} - c_{j-1,q+1} dt / (t_{n+1} - t_{n+2-j})
+    kk = 6
+    c = np.zeros((kk + 1, kk + 2))
+    g = np.zeros(kk + 1)
+    xi = dts[0]
+    for i in range(1, kk + 1):
+        if i > 2:
+            xi += dts[i - 2]
+        for q in range(1, kk - (i - 1) + 1):
+            if i == 1:
+                c[i, q] = 1.0 / q
+            elif i == 2:
+                c[i, q] = 1.0 / (q * (q + 1))
+            else:
+                c[i, q] = c[i - 1, q] - dt / xi * c[i - 1, q + 1]
+        g[i] = c[i, 1] * dt
+    p = u.copy()
+    for j in range(1, 5):
+        p = p + g[j] * phistar[j - 1]
+    fp = f(p)
+    phi_np1 = [fp]
+    for j in range(1, 6):
+        phi_np1.append(phi_np1[j - 1] - phistar[j - 1])
+    unew = p + g[5] * phi_np1[4]
+    err = (g[6] - g[5]) * phi_np1[5]
+    return unew, err, f(unew)
+
+
+def _eest(err, u, unew, reltol, abstol):
+    sk = abstol + reltol * np.maximum(np.abs(u), np.abs(unew))
+    return float(np.sqrt(np.sum((err / sk) ** 2) / u.size))
+
+
 def vcabm5(f, u0: np.ndarray, t0: float, tstop: float, reltol=1e-3, abstol=1e-6, dt0=0.0, dtmax=0.0,
            maxiters=100000):
     """Variable-coefficient Adams-Bashforth-Moulton PECE of order 5 -- the class of method the reference's
@@ -126,9 +205,8 @@ def vcabm5(f, u0: np.ndarray, t0: float, tstop: float, reltol=1e-3, abstol=1e-6,
     if t + dt > tstop:
         dt = tstop - t
     qold = 1e-4
-    fn = f(u)
-    hist_f = [fn]            # f(t_n), f(t_{n-1}), ... newest first
-    hist_dt: list[float] = []  # accepted step sizes, newest first
+    hist_f = [f(u)]            # f(t_n), f(t_{n-1}), ... newest first
+    hist_dt: list = []         # accepted step sizes, newest first
     ts, us = [t], [u.copy()]
     naccept = nreject = nrhs = 0
     done = False
@@ -136,80 +214,12 @@ def vcabm5(f, u0: np.ndarray, t0: float, tstop: float, reltol=1e-3, abstol=1e-6,
     while not done and it < maxiters:
         it += 1
         if len(hist_dt) < 4:
-            # ---- starting procedure: one adaptive Tsit5 step
-            k = [hist_f[0]] + [None] * 6
-            for s in range(1, 7):
-                acc = np.zeros_like(u)
-                for j in range(s):
-                    acc = acc + A[s][j] * k[j]
-                y = u + dt * acc
-                k[s] = f(y)
-            unew = y
-            err = np.zeros_like(u)
-            for j in range(7):
-                err = err + BTILDE[j] * k[j]
-            err = err * dt
-            fnew = k[6]
+            unew, err, fnew = _tsit5_step(f, u, hist_f[0], dt)      # starting procedure
             nrhs += 6
         else:
-            # ---- Adams PECE on the grid dts = (dt, h_{n-1}, h_{n-2}, ...)
-            dts = [dt] + hist_dt[:4]
-            # beta_j(n), phi_j(n), phi*_j(n), j = 1..5, from the raw derivative history (divided differences
-            # are rebuilt from the samples each step; the recurrence phi_{j+1}(m) = phi_j(m) - phi*_j(m-1))
-            def phis(level, depth):
-                """phi_1..phi_depth at time level n-level, from hist_f[level:]."""
-                out = [hist_f[level]]
-                if depth > 1:
-                    prev = phis(level + 1, depth - 1)
-                    grid = hist_dt[level:]              # h_{m-1}, h_{m-2}, ... for m = n-level
-                    beta = 1.0
-                    xi = grid[0]                        # t_m - t_{m-1}
-                    xi0 = 0.0
-                    for j in range(1, depth):
-                        # phi*_j(m-1) = beta_j(m-1) phi_j(m-1), beta_j(m-1) = prod (t_m - t_{m-1-i}) / (t_{m-1} - t_{m-2-i})
-                        if j > 1:
-                            xi0 += grid[j - 1]
-                            beta = beta * xi / xi0
-                            xi += grid[j - 1]
-                        out.append(out[j - 1] - beta * prev[j - 1])
-                return out
-            phi_n = phis(0, 5)
-            beta = [1.0]
-            xi, xi0 = dts[0], 0.0
-            for i in range(1, 5):
-                xi0 += dts[i]
-                beta.append(beta[i - 1] * xi / xi0)
-                xi += dts[i]
-            phistar = [beta[i] * phi_n[i] for i in range(5)]
-            # g_j(n): c_{1,q} = 1/q, c_{2,q} = 1/(q(q+1)), c_{j,q} = c_{j-1,q} - c_{j-1,q+1} dt / (t_{n+1} - t_{n+2-j})
-            kk = 6
-            c = np.zeros((kk + 1, kk + 2))
-            g = np.zeros(kk + 1)
-            xi = dts[0]
-            for i in range(1, kk + 1):
-                if i > 2:
-                    xi += dts[i - 2]
-                for q in range(1, kk - (i - 1) + 1):
-                    if i == 1:
-                        c[i, q] = 1.0 / q
-                    elif i == 2:
-                        c[i, q] = 1.0 / (q * (q + 1))
-                    else:
-                        c[i, q] = c[i - 1, q] - dt / xi * c[i - 1, q + 1]
-                g[i] = c[i, 1] * dt
-            p = u.copy()
-            for j in range(1, 5):
-                p = p + g[j] * phistar[j - 1]
-            fp = f(p)
-            phi_np1 = [fp]
-            for j in range(1, 6):
-                phi_np1.append(phi_np1[j - 1] - phistar[j - 1])
-            unew = p + g[5] * phi_np1[4]
-            err = (g[6] - g[5]) * phi_np1[5]
-            fnew = f(unew)
+            unew, err, fnew = _adams_step(f, u, hist_f, hist_dt, dt)
             nrhs += 2
-        sk = abstol + reltol * np.maximum(np.abs(u), np.abs(unew))
-        eest = float(np.sqrt(np.sum((err / sk) ** 2) / u.size))
+        eest = _eest(err, u, unew, reltol, abstol)
         q11, q = _pi_controller(eest, qold, dt)
         if eest <= 1.0:
             naccept += 1
@@ -231,3 +241,34 @@ def vcabm5(f, u0: np.ndarray, t0: float, tstop: float, reltol=1e-3, abstol=1e-6,
             nreject += 1
             dt = dt / min(1 / 0.2, q11 / 0.9)
     return np.array(ts), us, dict(naccept=naccept, nreject=nreject, nrhs=nrhs + 1)
+
+
+def vcabm5_on_grid(f, u0: np.ndarray, ts, reltol=1e-3, abstol=1e-6):
+    """The same stepping as `vcabm5`, but along a GIVEN grid of accepted times (e.g. the one a device run chose):
+    returns (us, eests), the state after every step and the scaled error estimate the controller would have seen.
+
+    Why it exists: where the solution is almost steady the error estimate is pure round-off (1e-10 ... 1e-7), and
+    the controller turns O(1) relative noise in it into per-cent differences of the next step, so two correct
+    implementations need not pick the same grid.  Following the device's grid compares the formulas step by step
+    (states), and the device's controller wherever the estimate is above the noise (tests/test_gpu_solve.py)."""
+    u = np.array(u0, dtype=np.float64)
+    hist_f, hist_dt = [f(u)], []
+    us, eests = [u.copy()], []
+    for n in range(1, len(ts)):
+        dt = float(ts[n] - ts[n - 1])
+        if len(hist_dt) < 4:
+            unew, err, fnew = _tsit5_step(f, u, hist_f[0], dt)
+        else:
+            unew, err, fnew = _adams_step(f, u, hist_f, hist_dt, dt)
+        eests.append(_eest(err, u, unew, reltol, abstol))
+        u = unew
+        hist_f = [fnew] + hist_f[:5]
+        hist_dt = [dt] + hist_dt[:4]
+        us.append(u.copy())
+    return us, np.array(eests)
+
+
+def pi_next_dt(eest, qold, dt):
+    """step the PI controller proposes after an accepted step (before dtmax / tstop clipping)"""
+    _, q = _pi_controller(eest, qold, dt)
+    return dt / q
