@@ -8,8 +8,9 @@ resident state: forcing kernel + fused dense matvec with the rate-and-state epil
 (2.15 GB) is far larger than the 126 MB L2, so every step streams it from HBM (no L2 flush needed).
 
   value        RHS evaluations / s, state and matrix resident in HBM (device-timed, max over ranks)
-  e2e          the same through the reference-facing call prob.f(du, u, p, t) with HOST buffers (pinned):
-               H2D of u and D2H of du inside the timed region
+  e2e          the same through the reference-facing call prob.f(du, u, p, t) with HOST buffers (page-locked):
+               every step moves u host->device and du device->host inside the timed region (the kernels read /
+               write the mapped host arrays over PCIe themselves; pageable arrays would be staged by copies)
   roofline     the fused matvec kernel: algorithmic bytes / its CUDA-event time vs the measured HBM copy peak
   cpu_baseline the oracle port of the reference's own CPU algorithm (FFT form of equation.jl:44-61, OpenMP +
                pocketfft) on this box's host cores, bounded sample
@@ -362,7 +363,7 @@ def run_ours(args):
     t0 = time.perf_counter()
     ev0.record()
     for _ in range(ksteps):
-        p.rhs(du_np, u_np, 0.0)          # H2D(u) -> kernels -> D2H(du), synchronous at return
+        p.rhs(du_np, u_np, 0.0)          # u read from / du written to host memory by the kernels; synchronous
     ev1.record()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0     # host clock: the call is synchronous and includes both copies

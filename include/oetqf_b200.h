@@ -64,6 +64,11 @@ int64_t oq_kernel_launch_count(void);
 int oq_measure_fp64_peak(double *flops_per_s);
 /* Measured HBM copy bandwidth (read+write bytes / s) over a buffer of `bytes` bytes. */
 int oq_measure_hbm_copy(size_t bytes, double *bytes_per_s);
+/* Page-lock and map a host array (cudaHostRegister) so that oq_rhs reads / writes it from the kernels themselves
+ * instead of staging copies (the arrays the integrator hands to `ode`, src/BEM/equation.jl:156-205).  The array
+ * must stay allocated until oq_host_unregister; memory from cudaHostAlloc / a pinned torch tensor needs neither. */
+int oq_host_register(void *ptr, size_t bytes);
+int oq_host_unregister(void *ptr);
 
 /* ------------------------------------------------------------------ Green's functions, host output
  * Drop-in for the four `stress_greens_function` methods.  Output arrays are column-major exactly as

@@ -5,7 +5,8 @@ meaning); every number is produced by the sm_100a kernels in csrc/ through the C
 include/oetqf_b200.h.  There is no CPU fallback.
 """
 from . import _lib, dist
-from ._lib import OqError, init, kernel_launch_count, measure_fp64_peak, measure_hbm_copy
+from ._lib import (OqError, host_register, host_unregister, init, kernel_launch_count, measure_fp64_peak,
+                   measure_hbm_copy)
 from .equation import ArrayPartition, DeviceProblem, ODEProblem, ODESolution, Tsit5, VCABM5, assemble, ode, solve
 from . import io
 from .io import wsolve

@@ -68,7 +68,7 @@ SNAPSHOT_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_double, C.c_int64,
 # every symbol include/oetqf_b200.h declares (tests check that the library exports all of them)
 EXPORTS = [
     "oq_abi_version", "oq_last_error", "oq_init", "oq_device_count", "oq_kernel_launch_count",
-    "oq_measure_fp64_peak", "oq_measure_hbm_copy",
+    "oq_measure_fp64_peak", "oq_measure_hbm_copy", "oq_host_register", "oq_host_unregister",
     "oq_gf_fault_fault", "oq_gf_fault_mantle", "oq_gf_mantle_fault", "oq_gf_mantle_mantle",
     "oq_dc3d_gradient", "oq_stress_vol_hex8",
     "oq_matrix_fault_fault", "oq_matrix_from_toeplitz", "oq_matrix_fault_mantle", "oq_matrix_mantle_fault", "oq_matrix_mantle_mantle",
@@ -129,3 +129,12 @@ def measure_hbm_copy(nbytes: int = 1 << 30) -> float:
     v = C.c_double()
     check(load().oq_measure_hbm_copy(C.c_size_t(nbytes), C.byref(v)))
     return v.value
+
+
+def host_register(a: np.ndarray):
+    """Page-lock and map a host array so that `ode` / oq_rhs reads and writes it without staging copies."""
+    check(load().oq_host_register(C.c_void_p(a.ctypes.data), C.c_size_t(a.nbytes)))
+
+
+def host_unregister(a: np.ndarray):
+    check(load().oq_host_unregister(C.c_void_p(a.ctypes.data)))

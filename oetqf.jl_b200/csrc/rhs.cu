@@ -530,11 +530,29 @@ StateView view_of(const OqProblem* p, double* b)
     return s;
 }
 
+// views over five separately allocated partitions (the host's ArrayPartition, mapped into the device's address space)
+static StateView view_of_parts(const OqProblem* p, double* const* b)
+{
+    StateView s{};
+    s.v = b[0];
+    s.theta = b[1];
+    if (p->kind == kFaultOnly) s.delta = b[2];
+    else if (p->kind == kDilatancy) { s.delta = b[2]; s.pr = b[3]; }
+    else { s.eps = b[2]; s.sig = b[3]; s.delta = b[4]; }
+    return s;
+}
+
+static int rhs_views(OqProblem* p, const StateView& in, const StateView& out, const double* uin, const StageSpec* stage);
+
 int rhs_device(OqProblem* p, const double* uin, double* du, const StageSpec* stage)
 {
+    return rhs_views(p, view_of(p, const_cast<double*>(uin)), view_of(p, du), uin, stage);
+}
+
+// `uin`: base of the state-shaped buffer the fused stage combination fills (needed only with a stage spec)
+static int rhs_views(OqProblem* p, const StateView& in, const StateView& out, const double* uin, const StageSpec* stage)
+{
     cudaStream_t st = p->stream;
-    const StateView in = view_of(p, const_cast<double*>(uin));
-    const StateView out = view_of(p, du);
     // 1. forcing vectors; every rank's slice is stored straight into all windows (fused all-gather)
     ForcingArgs fa{};
     fa.v = in.v; fa.sig = in.sig; fa.deps_out = out.eps;
@@ -888,11 +906,43 @@ static int download_parts(const OqProblem* p, const double* src, double* const* 
     return 0;
 }
 
+// Device addresses of host partitions that are page-locked and mapped (cudaHostAlloc / cudaHostRegister, e.g. a
+// pinned torch tensor or a registered Julia array); false if any partition is ordinary pageable memory.
+static bool mapped_parts(const OqProblem* p, const double* const* parts, double** dev)
+{
+    for (int i = 0; i < 5; ++i) dev[i] = nullptr;
+    for (int i = 0; i < p->nparts; ++i) {
+        if (!p->part_len[i]) continue;
+        if (!parts[i]) return false;
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, parts[i]) != cudaSuccess) { cudaGetLastError(); return false; }
+        if (at.type != cudaMemoryTypeHost || !at.devicePointer) return false;
+        dev[i] = static_cast<double*>(at.devicePointer);
+    }
+    return true;
+}
+
+static bool zero_copy_enabled()
+{
+    static const bool on = [] { const char* e = getenv("OQ_RHS_ZEROCOPY"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
 int oq_rhs(OqProblem* p, double t, const double* const* u_parts, double* const* du_parts)
 {
     (void)t;   // the system is autonomous (equation.jl:156-205 never reads t)
     OQ_CHECK(p && u_parts && du_parts, "NULL argument");
     OQ_TRY(enter());
+    // Page-locked host arrays are read and written by the kernels themselves over PCIe (no staging copies, no
+    // copy-engine launches: the evaluation is two kernel launches and one synchronisation); pageable arrays are
+    // staged through device buffers.
+    double *du_dev[5], *u_dev[5];
+    if (zero_copy_enabled() && mapped_parts(p, u_parts, u_dev) &&
+        mapped_parts(p, const_cast<const double* const*>(du_parts), du_dev)) {
+        OQ_TRY(rhs_views(p, view_of_parts(p, u_dev), view_of_parts(p, du_dev), nullptr, nullptr));
+        OQ_CUDA(cudaStreamSynchronize(p->stream));
+        return 0;
+    }
     OQ_TRY(upload_parts(p, u_parts, p->utmp.p));
     OQ_TRY(rhs_device(p, p->utmp.p, p->unew.p));
     return download_parts(p, p->unew.p, du_parts);

@@ -162,4 +162,20 @@ int oq_measure_hbm_copy(size_t bytes, double* bytes_per_s)
     return 0;
 }
 
+int oq_host_register(void* ptr, size_t bytes)
+{
+    OQ_CHECK(ptr && bytes > 0, "bad argument");
+    OQ_TRY(enter());
+    OQ_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterMapped | cudaHostRegisterPortable));
+    return 0;
+}
+
+int oq_host_unregister(void* ptr)
+{
+    OQ_CHECK(ptr, "bad argument");
+    OQ_TRY(enter());
+    OQ_CUDA(cudaHostUnregister(ptr));
+    return 0;
+}
+
 }  // extern "C"

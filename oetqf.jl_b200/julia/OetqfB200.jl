@@ -180,6 +180,11 @@ end
 toeplitz(gf::Array{Float64,3}) = gf
 toeplitz(gf::Array{ComplexF64,3}) = (nx = size(gf, 1); Oetqf.FFTW.irfft(gf, 2nx - 1, 1)[1:nx, :, :])
 
+# Page-lock an array the integrator will hand to `ode` (u0, and the cache arrays of the integrator): oq_rhs then
+# reads / writes it from the kernels directly instead of staging copies.  Unregister before the array is freed.
+host_register(a::Array{Float64}) = check(ccall((:oq_host_register, LIB), Cint, (Ptr{Cvoid}, Csize_t), a, sizeof(a)))
+host_unregister(a::Array{Float64}) = check(ccall((:oq_host_unregister, LIB), Cint, (Ptr{Cvoid},), a))
+
 # (du, u, p, t) -- exactly what OrdinaryDiffEq calls; u.x / du.x are the ArrayPartition components
 function ode(du::ArrayPartition, u::ArrayPartition, p::DeviceProblem, t)
     up = Ptr{Float64}[pointer(x) for x in u.x]
