@@ -266,3 +266,18 @@ def test_rhs_page_locked_buffers_take_the_zero_copy_path(gpu, form):
     prob.p.rhs(pd, pu, 0.0)
     for g_, w in zip(pd, du.x):
         assert np.array_equal(g_, w)
+
+
+@pytest.mark.parametrize("env", [{"OQ_MATVEC": "ldg"}, {"OQ_TOEPLITZ": "direct"}, {"OQ_RHS_ZEROCOPY": "0"}])
+def test_validation_twins_stay_correct(gpu, env):
+    """the alternative kernels kept behind environment switches (first LDG matvec, direct Toeplitz contraction,
+    staged copies for page-locked buffers) must pass the same RHS parity tests; the switches are read once per
+    process, hence the subprocess"""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_rhs.py"), "-m", "gpu", "-q",
+                          "-x", "-k", "test_rhs_fault_only or test_rhs_viscoelastic_machinery or zero_copy"],
+                         env={**os.environ, **env}, capture_output=True, text=True, timeout=600, cwd=root)
+    assert res.returncode == 0, res.stdout[-2000:]
