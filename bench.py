@@ -403,7 +403,8 @@ def run_ours(args):
     mv_avg_ms = mv_ms / max(1, mv_n)
     achieved = rhs_bytes / (mv_avg_ms * 1e-3) / 1e9
     traffic = None
-    prof = os.path.join(ROOT, "profiles", "r01_matvec_traffic.json")
+    # the ncu capture is of the single-GPU launch (all 16384 rows); no capture exists at the shard sizes of N > 1
+    prof = os.path.join(ROOT, "profiles", "r01_matvec_traffic.json") if world == 1 else ""
     if os.path.exists(prof):
         with open(prof) as fh:
             traffic = json.load(fh).get("dram_bytes_per_launch")
