@@ -253,8 +253,11 @@ struct MatvecJob {
     int nrb;              // row blocks of kStR rows
     int nch[2];           // chunks per operand
     int chunks_per_rb;
-    int slots;            // partial-sum slots per row (max contributing CTAs of a row block)
+    int slots;            // partial-sum slots per row (max contributing CTAs / pieces of a row block)
     long long chunk_begin;
+    // dynamic distribution, see matvec_dyn.cuh
+    int pieces_per_rb;
+    long long unit_begin;
 };
 
 struct MatvecArgs {
@@ -263,6 +266,10 @@ struct MatvecArgs {
     PeerWait pw;
     long long total_chunks;
     const int* done;      // optional device flag: skip the evaluation (integration complete)
+    // dynamic distribution: units of `piece_len` chunks drawn from a ticket counter
+    int piece_len;
+    long long total_units;
+    unsigned long long* ticket;
 };
 
 __global__ void __launch_bounds__(kMvThreads)
@@ -392,6 +399,7 @@ matvec_fused_kernel(const __grid_constant__ MatvecArgs args)
 
 }  // namespace oq
 #include "matvec_stream.cuh"
+#include "matvec_dyn.cuh"
 #include "toeplitz_fft.cuh"
 namespace oq {
 
@@ -441,18 +449,37 @@ static int plan_stream(MatvecArgs& a)
         if (s > j.chunks_per_rb) s = j.chunks_per_rb > 0 ? j.chunks_per_rb : 1;
         j.slots = (int)s;
     }
+    // dynamic distribution: about 96 units per CTA, but pieces of at least 4 chunks (the epilogue warp spends
+    // a fence and an atomic round trip per piece) unless the row block is shorter
+    long long want = total / ((long long)grid * 96);
+    int piece = 4;
+    while (piece * 2 <= want && piece < 64) piece *= 2;
+    if (const char* e = getenv("OQ_MATVEC_PIECE")) { const int v = atoi(e); if (v > 0) piece = v; }
+    a.piece_len = piece;
+    long long units = 0;
+    for (int jb = 0; jb < 2; ++jb) {
+        MatvecJob& j = a.job[jb];
+        j.pieces_per_rb = j.chunks_per_rb > 0 ? (j.chunks_per_rb + piece - 1) / piece : 0;
+        j.unit_begin = units;
+        units += (long long)j.nrb * j.pieces_per_rb;
+        if (j.pieces_per_rb > j.slots) j.slots = j.pieces_per_rb;
+    }
+    a.total_units = units;
     return grid;
 }
 
-static bool use_ldg_matvec()
+// 0: static spans (matvec_stream.cuh), 1: dynamic units (matvec_dyn.cuh), 2: first LDG kernel
+static int matvec_variant()
 {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("OQ_MATVEC");
-        v = (e && strcmp(e, "ldg") == 0) ? 1 : 0;
+        v = (e && strcmp(e, "ldg") == 0) ? 2 : (e && strcmp(e, "dyn") == 0) ? 1 : 0;
     }
-    return v == 1;
+    return v;
 }
+
+static bool use_ldg_matvec() { return matvec_variant() == 2; }
 
 // choose the column split so that the grid has enough CTAs to balance 148 SMs
 static void plan_operand(MatOperand& op, int nrowblocks, int other_min_seg)
@@ -491,8 +518,11 @@ int launch_matvec(MatvecArgs& a, cudaStream_t stream)
         if (!stream_attr_set) {
             OQ_CUDA(cudaFuncSetAttribute(matvec_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)kStSmemBytes));
+            OQ_CUDA(cudaFuncSetAttribute(matvec_dyn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)kStSmemBytes));
             stream_attr_set = true;
         }
+        const bool dyn = matvec_variant() == 1 && a.ticket != nullptr;
         // programmatic dependent launch: start while the forcing kernel still runs; the kernel prefetches its
         // first ring of matrix chunks and only then waits for the predecessor (pdl_wait)
         cudaLaunchConfig_t cfg = {};
@@ -502,7 +532,8 @@ int launch_matvec(MatvecArgs& a, cudaStream_t stream)
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        OQ_CUDA(cudaLaunchKernelEx(&cfg, matvec_stream_kernel, a));
+        if (dyn) OQ_CUDA(cudaLaunchKernelEx(&cfg, matvec_dyn_kernel, a));
+        else OQ_CUDA(cudaLaunchKernelEx(&cfg, matvec_stream_kernel, a));
         OQ_LAUNCHED();
         return 0;
     }
@@ -623,6 +654,7 @@ static int rhs_views(OqProblem* p, const StateView& in, const StateView& out, co
     const int nrbf = plan_job(a.job[0], p->nfl);
     a.job[1].op[0] = p->opm[0]; a.job[1].op[1] = p->opm[1];
     a.job[1].partial = p->partial_m.p; a.job[1].counters = p->counters.p + nrbf;
+    a.ticket = p->ticket.p;
     a.job[1].yout = out.sig; a.job[1].epilogue = kEpiStore;
     plan_job(a.job[1], p->kind == kViscoelastic ? 6 * p->nel : 0);
     if (a.job[0].nitems == 0 && p->nfl > 0 && !epilogue_done) {
@@ -648,9 +680,10 @@ static int rhs_views(OqProblem* p, const StateView& in, const StateView& out, co
 
 // plain y = A x / y += A x on a shard (the matvecmul! slot)
 int gemv_device(const OqMatrix* A, const double* x_dev_padded, const double* y_in, double* y_out,
-                double* partial, unsigned* counters, cudaStream_t st)
+                double* partial, unsigned* counters, unsigned long long* ticket, cudaStream_t st)
 {
     MatvecArgs a{};
+    a.ticket = ticket;
     a.job[0].op[0].G = A->d.p; a.job[0].op[0].ld = A->ld; a.job[0].op[0].x = x_dev_padded;
     a.job[0].op[0].cols = A->cols;
     a.job[0].partial = partial; a.job[0].counters = counters; a.job[0].y0 = y_in; a.job[0].yout = y_out;
@@ -798,6 +831,7 @@ static int finish_problem(OqProblem* p, const OqFaultProperty* pf, const OqDilat
     OQ_TRY(p->partial_f.alloc((size_t)nfl * (p->nseg_f > 0 ? p->nseg_f : 1) + 1));
     OQ_TRY(p->partial_m.alloc((size_t)6 * nel * (p->nseg_m > 0 ? p->nseg_m : 1) + 1));
     OQ_TRY(p->counters.alloc((size_t)nrbf + nrbm + 1)); OQ_TRY(p->counters.zero());
+    OQ_TRY(p->ticket.alloc(2)); OQ_TRY(p->ticket.zero());
     OQ_TRY(p->errpart.alloc(1024)); OQ_TRY(p->errpart.zero());
     OQ_TRY(p->ctl.alloc(32)); OQ_TRY(p->ctl.zero());
     OQ_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
@@ -1058,6 +1092,8 @@ int oq_gemv(const OqMatrix* A, const double* x, double* y, int accumulate)
     if (A->local_rows == 0) return 0;
     DevBuf<double> dx, dy, partial;
     DevBuf<unsigned> counters;
+    DevBuf<unsigned long long> ticket;
+    OQ_TRY(ticket.alloc(2)); OQ_TRY(ticket.zero());
     OQ_TRY(dx.alloc(A->ld + kMvMaxSeg)); OQ_TRY(dx.zero());
     OQ_CUDA(cudaMemcpy(dx.p, x, A->cols * sizeof(double), cudaMemcpyHostToDevice));
     OQ_TRY(dy.alloc(A->local_rows));
@@ -1066,7 +1102,7 @@ int oq_gemv(const OqMatrix* A, const double* x, double* y, int accumulate)
     gemv_scratch_sizes(A, &np, &nc);
     OQ_TRY(partial.alloc(np + 1));
     OQ_TRY(counters.alloc(nc + 1)); OQ_TRY(counters.zero());
-    OQ_TRY(gemv_device(A, dx.p, accumulate ? dy.p : nullptr, dy.p, partial.p, counters.p, 0));
+    OQ_TRY(gemv_device(A, dx.p, accumulate ? dy.p : nullptr, dy.p, partial.p, counters.p, ticket.p, 0));
     OQ_CUDA(cudaMemcpy(y, dy.p, A->local_rows * sizeof(double), cudaMemcpyDeviceToHost));
     return 0;
 }
