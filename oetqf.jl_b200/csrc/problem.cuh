@@ -76,7 +76,7 @@ struct OqProblem {
     // matvec scratch
     oq::DevBuf<double> partial_f, partial_m;        // [rows * nsegTotal]
     oq::DevBuf<unsigned> counters;                  // [row blocks fault + row blocks mantle]
-    oq::DevBuf<unsigned long long> ticket;          // work-unit ticket counter of the dynamic matvec
+    oq::DevBuf<unsigned long long> ticket;          // matvec pass counter + finished-CTA counter (traversal direction)
     oq::DevBuf<double> dtau0;                       // Toeplitz-form traction rate [nfl]
     // FFT form (toeplitz_fft.cuh): transform length, local receiver-row range, spectrum and work arrays
     int fftN = 0, fj0 = 0, fnj = 0;

@@ -255,9 +255,6 @@ struct MatvecJob {
     int chunks_per_rb;
     int slots;            // partial-sum slots per row (max contributing CTAs / pieces of a row block)
     long long chunk_begin;
-    // dynamic distribution, see matvec_dyn.cuh
-    int pieces_per_rb;
-    long long unit_begin;
 };
 
 struct MatvecArgs {
@@ -266,10 +263,12 @@ struct MatvecArgs {
     PeerWait pw;
     long long total_chunks;
     const int* done;      // optional device flag: skip the evaluation (integration complete)
-    // dynamic distribution: units of `piece_len` chunks drawn from a ticket counter
-    int piece_len;
-    long long total_units;
-    unsigned long long* ticket;
+    // traversal direction: pass[0] counts completed launches (its parity picks forward / reverse row-block order so
+    // that an evaluation starts on what the previous one left in L2), pass[1] counts CTAs that finished this launch
+    unsigned long long* pass;
+    // L2 residency: chunks [0, keep_chunks) of every CTA span are loaded evict-last, the rest evict-first
+    // (negative: no eviction hints)
+    int keep_chunks;
 };
 
 __global__ void __launch_bounds__(kMvThreads)
@@ -399,7 +398,6 @@ matvec_fused_kernel(const __grid_constant__ MatvecArgs args)
 
 }  // namespace oq
 #include "matvec_stream.cuh"
-#include "matvec_dyn.cuh"
 #include "toeplitz_fft.cuh"
 namespace oq {
 
@@ -449,34 +447,44 @@ static int plan_stream(MatvecArgs& a)
         if (s > j.chunks_per_rb) s = j.chunks_per_rb > 0 ? j.chunks_per_rb : 1;
         j.slots = (int)s;
     }
-    // dynamic distribution: about 96 units per CTA, but pieces of at least 4 chunks (the epilogue warp spends
-    // a fence and an atomic round trip per piece) unless the row block is shorter
-    long long want = total / ((long long)grid * 96);
-    int piece = 4;
-    while (piece * 2 <= want && piece < 64) piece *= 2;
-    if (const char* e = getenv("OQ_MATVEC_PIECE")) { const int v = atoi(e); if (v > 0) piece = v; }
-    a.piece_len = piece;
-    long long units = 0;
-    for (int jb = 0; jb < 2; ++jb) {
-        MatvecJob& j = a.job[jb];
-        j.pieces_per_rb = j.chunks_per_rb > 0 ? (j.chunks_per_rb + piece - 1) / piece : 0;
-        j.unit_begin = units;
-        units += (long long)j.nrb * j.pieces_per_rb;
-        if (j.pieces_per_rb > j.slots) j.slots = j.pieces_per_rb;
-    }
-    a.total_units = units;
     return grid;
 }
 
-// 0: static spans (matvec_stream.cuh), 1: dynamic units (matvec_dyn.cuh), 2: first LDG kernel
+// 0: streaming kernel (matvec_stream.cuh), 2: first LDG kernel
 static int matvec_variant()
 {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("OQ_MATVEC");
-        v = (e && strcmp(e, "ldg") == 0) ? 2 : (e && strcmp(e, "dyn") == 0) ? 1 : 0;
+        v = (e && strcmp(e, "ldg") == 0) ? 2 : 0;
     }
     return v;
+}
+
+// chunks per CTA span to keep L2-resident between evaluations: OQ_MATVEC_KEEP_MB megabytes over the grid
+// (default: three quarters of the L2; 0 disables the eviction hints)
+static int keep_chunks_per_cta(int grid)
+{
+    static double mb = -1.0;
+    if (mb < 0.0) {
+        const char* e = getenv("OQ_MATVEC_KEEP_MB");
+        if (e) mb = atof(e);
+        else {
+            cudaDeviceProp prop;
+            mb = cudaGetDeviceProperties(&prop, current_device() >= 0 ? current_device() : 0) == cudaSuccess
+                     ? 0.75 * prop.l2CacheSize / 1048576.0 : 90.0;
+        }
+        if (mb < 0.0) mb = 0.0;
+    }
+    if (mb == 0.0) return -1;
+    const double chunk_mb = (double)kStR * kStCH * sizeof(double) / 1048576.0;
+    return (int)(mb / (grid * chunk_mb));
+}
+
+static bool pingpong_enabled()
+{
+    static const bool on = [] { const char* e = getenv("OQ_MATVEC_PINGPONG"); return !(e && e[0] == '0'); }();
+    return on;
 }
 
 static bool use_ldg_matvec() { return matvec_variant() == 2; }
@@ -518,11 +526,10 @@ int launch_matvec(MatvecArgs& a, cudaStream_t stream)
         if (!stream_attr_set) {
             OQ_CUDA(cudaFuncSetAttribute(matvec_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)kStSmemBytes));
-            OQ_CUDA(cudaFuncSetAttribute(matvec_dyn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)kStSmemBytes));
             stream_attr_set = true;
         }
-        const bool dyn = matvec_variant() == 1 && a.ticket != nullptr;
+        if (!pingpong_enabled()) a.pass = nullptr;
+        a.keep_chunks = keep_chunks_per_cta(grid);
         // programmatic dependent launch: start while the forcing kernel still runs; the kernel prefetches its
         // first ring of matrix chunks and only then waits for the predecessor (pdl_wait)
         cudaLaunchConfig_t cfg = {};
@@ -532,8 +539,7 @@ int launch_matvec(MatvecArgs& a, cudaStream_t stream)
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        if (dyn) OQ_CUDA(cudaLaunchKernelEx(&cfg, matvec_dyn_kernel, a));
-        else OQ_CUDA(cudaLaunchKernelEx(&cfg, matvec_stream_kernel, a));
+        OQ_CUDA(cudaLaunchKernelEx(&cfg, matvec_stream_kernel, a));
         OQ_LAUNCHED();
         return 0;
     }
@@ -654,7 +660,7 @@ static int rhs_views(OqProblem* p, const StateView& in, const StateView& out, co
     const int nrbf = plan_job(a.job[0], p->nfl);
     a.job[1].op[0] = p->opm[0]; a.job[1].op[1] = p->opm[1];
     a.job[1].partial = p->partial_m.p; a.job[1].counters = p->counters.p + nrbf;
-    a.ticket = p->ticket.p;
+    a.pass = p->ticket.p;
     a.job[1].yout = out.sig; a.job[1].epilogue = kEpiStore;
     plan_job(a.job[1], p->kind == kViscoelastic ? 6 * p->nel : 0);
     if (a.job[0].nitems == 0 && p->nfl > 0 && !epilogue_done) {
@@ -683,7 +689,7 @@ int gemv_device(const OqMatrix* A, const double* x_dev_padded, const double* y_i
                 double* partial, unsigned* counters, unsigned long long* ticket, cudaStream_t st)
 {
     MatvecArgs a{};
-    a.ticket = ticket;
+    a.pass = ticket;
     a.job[0].op[0].G = A->d.p; a.job[0].op[0].ld = A->ld; a.job[0].op[0].x = x_dev_padded;
     a.job[0].op[0].cols = A->cols;
     a.job[0].partial = partial; a.job[0].counters = counters; a.job[0].y0 = y_in; a.job[0].yout = y_out;

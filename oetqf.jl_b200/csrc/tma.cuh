@@ -63,6 +63,22 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
         : "memory");
 }
 
+// L2 eviction-priority policies for bulk copies (the encodings `createpolicy.fractional.L2::evict_*.b64 p, 1.0`
+// produces; the same constants as CUTLASS' TMA::CacheHintSm100)
+constexpr unsigned long long kL2EvictNormal = 0x1000000000000000ull;
+constexpr unsigned long long kL2EvictFirst = 0x12F0000000000000ull;
+constexpr unsigned long long kL2EvictLast = 0x14F0000000000000ull;
+
+__device__ __forceinline__ void tma_load_1d_hint(void* smem_dst, const void* gmem_src, unsigned bytes, uint64_t* bar,
+                                                 unsigned long long policy)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_addr(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_addr(bar)), "l"(policy)
+        : "memory");
+}
+
 // Programmatic dependent launch: a kernel launched with programmatic stream serialisation may start while its
 // predecessor still runs; it must execute pdl_wait() before touching anything the predecessor produces.
 __device__ __forceinline__ void pdl_wait()

@@ -268,10 +268,12 @@ def test_rhs_page_locked_buffers_take_the_zero_copy_path(gpu, form):
         assert np.array_equal(g_, w)
 
 
-@pytest.mark.parametrize("env", [{"OQ_MATVEC": "ldg"}, {"OQ_TOEPLITZ": "direct"}, {"OQ_RHS_ZEROCOPY": "0"}])
+@pytest.mark.parametrize("env", [{"OQ_MATVEC": "ldg"}, {"OQ_TOEPLITZ": "direct"}, {"OQ_RHS_ZEROCOPY": "0"},
+                                 {"OQ_MATVEC_KEEP_MB": "0", "OQ_MATVEC_PINGPONG": "0"}])
 def test_validation_twins_stay_correct(gpu, env):
     """the alternative kernels kept behind environment switches (first LDG matvec, direct Toeplitz contraction,
-    staged copies for page-locked buffers) must pass the same RHS parity tests; the switches are read once per
+    staged copies for page-locked buffers, matvec without L2 hints / alternating traversal) must pass the same RHS
+    parity tests; the switches are read once per
     process, hence the subprocess"""
     import os
     import subprocess
