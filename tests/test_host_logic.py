@@ -104,3 +104,27 @@ def test_workload_shapes():
     v, th, eps, sig, dl = W.initial_state(mf.nx, mf.nxi, L, ma.cz, g, n)
     rel = g * (np.sqrt(2) * np.abs(sig[:, 1])) ** n * sig[:, 1]
     np.testing.assert_allclose(rel, d0[1], rtol=1e-10)       # examples/otf-with-mantle.jl:147-148
+
+
+def test_algorithm_selection(oq):
+    """solve/wsolve accept the two algorithms the device integrator provides (Tsit5: test/tests.jl:11; VCABM5:
+    examples/otf-with-mantle.jl:160), as instances or classes, and refuse anything else before touching the GPU"""
+    import pytest
+    from oetqf_b200.equation import _alg_code
+    assert _alg_code(oq.Tsit5()) == 0 and _alg_code(oq.Tsit5) == 0
+    assert _alg_code(oq.VCABM5()) == 1 and _alg_code(oq.VCABM5) == 1
+    with pytest.raises(TypeError):
+        _alg_code("RK4")
+    with pytest.raises(TypeError):
+        oq.wsolve(None, object(), "/nonexistent", 1, None, [], "t")
+
+
+def test_solve_option_struct_matches_header():
+    """OqSolveOptions / OqSolveStats field order and sizes as declared in include/oetqf_b200.h"""
+    import ctypes as C
+    from oetqf_b200 import _lib
+    assert [f[0] for f in _lib.OqSolveOptions._fields_] == ["reltol", "abstol", "dt0", "dtmax", "tstop", "maxiters",
+                                                           "algorithm", "fixed_dt"]
+    assert C.sizeof(_lib.OqSolveOptions) == 5 * 8 + 8 + 4 + 4
+    assert [f[0] for f in _lib.OqSolveStats._fields_] == ["t", "dt_last", "dt_next", "naccept", "nreject", "nrhs",
+                                                         "retcode"]
