@@ -124,3 +124,38 @@ def test_golden_fixtures_match_oracle():
         idx = np.array(case["index"])
         got = st[idx[:, 0], idx[:, 1], idx[:, 2]]
         np.testing.assert_allclose(got, case["values"], rtol=1e-13)
+
+
+@pytest.mark.parametrize("dip", [0.0, 17.0, 41.0, 70.0, 90.0])
+def test_dc3d_equals_volterra_quadrature_of_the_mindlin_tensor(dip):
+    """independent of Okada's tables: the displacement field of the rectangular dislocation from its definition
+    (oracle/okada_numeric.py: Volterra's formula, complex-step source derivative of the half-space Green's tensor,
+    64x64 Gauss-Legendre) == oracle/okada.c, for all three slip types, interior and surface receivers; gradients
+    by central differences of the quadrature field"""
+    from oracle.okada_numeric import dc3d_displacement
+    rng = np.random.default_rng(100 + int(dip))
+    alpha = 0.6
+    sd, cd = np.sin(np.radians(dip)), np.cos(np.radians(dip))
+    worst_u = worst_g = 0.0
+    n = 0
+    while n < 10:
+        x, y = rng.uniform(-6, 6, 2)
+        z = -rng.uniform(0.0, 8.0) if n else 0.0                    # the first receiver sits on the free surface
+        geom = (5.0, dip, -1.5, 2.5, -3.0, -0.5)
+        # distance from the fault plane (through (0,0,-5), normal (0,-sd,cd)): keep the integrand smooth
+        if abs(-(y * sd) + (z + 5.0) * cd) < 0.7:
+            continue
+        n += 1
+        d = rng.uniform(-1.0, 1.0, 3)
+        want = ref.dc3d(alpha, x, y, z, *geom, *d)
+        got = dc3d_displacement(alpha, x, y, z, *geom, *d)
+        worst_u = max(worst_u, np.max(np.abs(got - want[:3])) / np.max(np.abs(want[:3])))
+        if z < -0.5 and n % 3 == 0:
+            h = 2e-4
+            for ax in range(3):
+                e = np.zeros(3); e[ax] = h
+                fd = (dc3d_displacement(alpha, x + e[0], y + e[1], z + e[2], *geom, *d)
+                      - dc3d_displacement(alpha, x - e[0], y - e[1], z - e[2], *geom, *d)) / (2 * h)
+                worst_g = max(worst_g, np.max(np.abs(fd - want[3 + 3 * ax: 6 + 3 * ax])) / np.max(np.abs(want[3:])))
+    assert worst_u < 1e-10, worst_u
+    assert worst_g < 1e-6, worst_g
