@@ -191,7 +191,9 @@ int oq_problem_destroy(OqProblem *p);
 int oq_problem_layout(const OqProblem *p, int *nparts, int *lengths /* [5] */);
 
 /* "compat mode": the (du, u, p, t) call of OrdinaryDiffEq, host pointers in, host pointers out.
- * u_parts / du_parts: arrays of nparts host pointers in the partition order above. */
+ * u_parts / du_parts: arrays of nparts host pointers in the partition order above.  Page-locked, mapped
+ * partitions (cudaHostAlloc, oq_host_register) are read and written by the kernels directly over PCIe;
+ * pageable ones are staged through device buffers.  Synchronous: du is complete on return. */
 int oq_rhs(OqProblem *p, double t, const double *const *u_parts, double *const *du_parts);
 
 /* "resident mode": state lives on the device; load / read it and evaluate the RHS in place. */
