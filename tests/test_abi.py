@@ -37,16 +37,21 @@ def test_no_cpu_fallback(oq):
 
 
 def test_product_never_imports_the_oracle():
-    """The oracle is test infrastructure: nothing under the product package may import, include, link or load it."""
-    pkg = os.path.join(ROOT, "oetqf.jl_b200")
+    """The oracle is test infrastructure: nothing under the product package, the examples, the helper scripts, the
+    workload definitions or the import shim may import, include, link or load it (only tests/, smoke() and the CPU
+    legs of bench.py do)."""
     bad = re.compile(r"(^\s*(from|import)\s+oracle\b)|(#include\s+[\"<][^\">]*oracle)|liboetqf_oracle|oracle\.ref|oracle/ref", re.M)
-    for base, _, files in os.walk(pkg):
-        if os.path.basename(base) == "derive":
-            continue          # the generator WRITES the checker's copy of the closed form; it never reads the oracle
-        for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".h", ".jl", "Makefile")):
-                with open(os.path.join(base, f), errors="replace") as fh:
-                    assert not bad.search(fh.read()), f"{f} reaches into oracle/"
+    roots = [os.path.join(ROOT, d) for d in ("oetqf.jl_b200", "examples", "scripts", "include")]
+    singles = [os.path.join(ROOT, f) for f in ("workloads.py", "oetqf_b200.py")]
+    for top in roots:
+        for base, _, files in os.walk(top):
+            if os.path.basename(base) == "derive":
+                continue      # the generator WRITES the checker's copy of the closed form; it never reads the oracle
+            singles += [os.path.join(base, f) for f in files
+                        if f.endswith((".py", ".cu", ".cuh", ".h", ".jl", ".sh", "Makefile"))]
+    for path in singles:
+        with open(path, errors="replace") as fh:
+            assert not bad.search(fh.read()), f"{path} reaches into oracle/"
 
 
 def test_argument_validation_precedes_device_use(oq):
