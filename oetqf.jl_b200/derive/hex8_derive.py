@@ -327,8 +327,23 @@ def cse_block(assigns, prefix):
     strain components compiles the rest away"""
     repl, red = sp.cse([ex for _, ex, _ in assigns], symbols=sp.numbered_symbols(prefix), optimizations="basic")
     lines = [f"        const double {s_} = {_printer.doprint(ex)};" for s_, ex in repl]
-    for (tgt, _, mask), ex in zip(assigns, red):
-        lines.append(f"        if (HEX8_NEED({mask})) {tgt} += sgn * ({_printer.doprint(ex)});")
+    # The running sums live in shared memory behind volatile accesses.  Accumulating one function at a time
+    # (load, add, store, load, ...) exposes the full shared-memory latency once per function; batches of
+    # HEX8_BATCH functions issue their loads back to back and store after the arithmetic.
+    batch = int(os.environ.get("HEX8_BATCH", "6"))
+    todo = list(zip(assigns, red))
+    for b0 in range(0, len(todo), batch):
+        part = todo[b0:b0 + batch]
+        if batch == 1:
+            (tgt, _, mask), ex = part[0]
+            lines.append(f"        if (HEX8_NEED({mask})) {tgt} += sgn * ({_printer.doprint(ex)});")
+            continue
+        lines.append("        {")
+        for n, ((tgt, _, mask), ex) in enumerate(part):
+            lines.append(f"        double hA{n} = 0.0; if (HEX8_NEED({mask})) hA{n} = {tgt};")
+        for n, ((tgt, _, mask), ex) in enumerate(part):
+            lines.append(f"        if (HEX8_NEED({mask})) {tgt} = hA{n} + sgn * ({_printer.doprint(ex)});")
+        lines.append("        }")
     nops = count_ops([ex for _, ex in repl] + list(red))
     return lines, nops
 
