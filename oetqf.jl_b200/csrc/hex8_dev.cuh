@@ -66,12 +66,16 @@ __device__ __forceinline__ void hex8_corner_inputs(double r1, double r2, double 
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         const int a = (k + 1) % 3, b = (k + 2) % 3;
-        // R + R_k without cancellation when R_k < 0
-        c.w[k] = rs[k] >= 0.0 ? n + rs[k] : c.q[k] / (n - rs[k]);
+        // w = R + R_k without cancellation when R_k < 0: with d = R + |R_k|, w = d or q/d and 1/w = 1/d or d/q --
+        // one reciprocal serves both branches
+        const double d = n + fabs(rs[k]);
+        const double rd = 1.0 / d;
+        c.iq[k] = 1.0 / c.q[k];
+        const bool pos = rs[k] >= 0.0;
+        c.w[k] = pos ? d : c.q[k] * rd;
+        c.iw[k] = pos ? rd : d * c.iq[k];
         c.L[k] = log(c.w[k]);
         c.A[k] = atan(rs[a] * rs[b] / (rs[k] * n));
-        c.iw[k] = 1.0 / c.w[k];
-        c.iq[k] = 1.0 / c.q[k];
     }
 }
 
