@@ -136,6 +136,11 @@ int oq_matrix_from_host(const double *a_colmajor, int m, int n, int row_kind, in
 /* Download the shard as a column-major (local_rows x n) host array; local row order is
  * fault: f - row_begin ; mantle: (e - e_begin) + k*(e_end - e_begin). */
 int oq_matrix_to_host(const OqMatrix *a, double *out_colmajor);
+/* Download LOCAL rows [local_begin, local_end) of the shard as a ROW-major ((local_end-local_begin) x n) host
+ * array (one strided device->host copy, no transposition): lets a caller inspect a window of a shard that is
+ * itself too large to duplicate (parity checks of 100 GB-class matrices; row i of the output is what the
+ * reference holds in st[row, :], GF.jl:123-296). */
+int oq_matrix_rows_to_host(const OqMatrix *a, int local_begin, int local_end, double *out_rowmajor);
 int oq_matrix_shape(const OqMatrix *a, int *local_rows, int *cols, int *global_rows);
 /* device time (CUDA events) of the assembly kernel that filled this shard, in ms (0 for uploads) */
 int oq_matrix_kernel_ms(const OqMatrix *a, double *ms);

@@ -767,6 +767,19 @@ int oq_matrix_to_host(const OqMatrix* a, double* outp)
     return matrix_to_host_colmajor(a, outp);
 }
 
+int oq_matrix_rows_to_host(const OqMatrix* a, int local_begin, int local_end, double* outp)
+{
+    OQ_CHECK(a && outp, "NULL argument");
+    OQ_CHECK(0 <= local_begin && local_begin <= local_end && local_end <= a->local_rows,
+             "local row range [%d,%d) outside [0,%d)", local_begin, local_end, a->local_rows);
+    OQ_TRY(enter());
+    if (local_end == local_begin) return 0;
+    OQ_CUDA(cudaMemcpy2D(outp, (size_t)a->cols * sizeof(double), a->d.p + (size_t)local_begin * a->ld,
+                         a->ld * sizeof(double), (size_t)a->cols * sizeof(double), (size_t)(local_end - local_begin),
+                         cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 int oq_matrix_shape(const OqMatrix* a, int* local_rows, int* cols, int* global_rows)
 {
     OQ_CHECK(a, "NULL matrix");

@@ -153,6 +153,12 @@ class DeviceMatrix:
         _lib.check(_lib.load().oq_matrix_to_host(self.handle, _lib.dptr(out)))
         return out
 
+    def rows_to_host(self, begin: int, end: int) -> np.ndarray:
+        """Local rows [begin, end) of the shard as a C-ordered (rows x cols) array (oq_matrix_rows_to_host)."""
+        out = np.zeros((end - begin, self.cols))
+        _lib.check(_lib.load().oq_matrix_rows_to_host(self.handle, int(begin), int(end), _lib.dptr(out)))
+        return out
+
     def gemv(self, x, y=None) -> np.ndarray:
         """The matvecmul! slot (src/pref.jl:15-21): y = A x, or y += A x when y is given."""
         x = _lib.f64(np.asarray(x).reshape(-1, order="F"))

@@ -354,6 +354,48 @@ def rhs_fault(pf: FaultProp, gf, v, theta, form="fft"):
     return update_fault(pf, dtau, v, theta)
 
 
+class FaultRhsFFT:
+    """The fault-only ode() of src/BEM/equation.jl:156-166 as the reference runs it, with the reference's
+    allocation discipline (gen_alloc, equation.jl:18-32: every scratch array is created once) and its
+    threading: planned, multi-threaded FFTs (FFTW in the reference; pocketfft with `workers` here), the
+    per-receiver contraction and update_fault! in C/OpenMP.  Used as the timed CPU arm of bench.py."""
+
+    def __init__(self, pf: FaultProp, gf_dft, workers=None):
+        import scipy.fft as sfft
+        self._fft = sfft
+        self.pf = pf
+        nx, nxi, _ = gf_dft.shape
+        self.nx, self.nxi = nx, nxi
+        self.workers = int(workers or num_threads())
+        self.gf = np.asfortranarray(gf_dft, dtype=np.complex128)
+        self.relv = np.zeros((2 * nx - 1, nxi), order="F")                      # zero-padded, :22
+        self.td = np.zeros((nx, nxi), dtype=np.complex128, order="F")
+        self.prop = [np.asfortranarray(a, dtype=np.float64) for a in (pf.a, pf.b, pf.L, pf.sigma)]
+        self.dv, self.dth, self.ddl = (np.zeros((nx, nxi), order="F") for _ in range(3))
+        self.dtau = np.zeros((nx, nxi), order="F")
+
+    def __call__(self, v, theta):
+        nx, nxi, pf = self.nx, self.nxi, self.pf
+        np.subtract(v, pf.vpl, out=self.relv[:nx])                                # :35-42
+        rd = self._fft.rfft(self.relv, axis=0, workers=self.workers)              # :46
+        rd = rd if rd.flags["F_CONTIGUOUS"] else np.asfortranarray(rd)
+        lib().oq_ref_fft_contract(nx, nxi, self.gf.ctypes.data_as(_dp), rd.ctypes.data_as(_dp),
+                                  self.td.ctypes.data_as(_dp))                    # :48-54
+        full = self._fft.irfft(self.td, n=2 * nx - 1, axis=0, workers=self.workers)   # :56
+        self.dtau[...] = full[:nx]                                                # :57-59
+        d = C.c_double
+        lib().oq_ref_update_fault(nx * nxi, *[_p(a) for a in self.prop], d(pf.eta), d(pf.f0), d(pf.v0),
+                                  _p(self.dtau), _p(v), _p(theta), _p(self.dv), _p(self.dth), _p(self.ddl))
+        return self.dv, self.dth, self.ddl
+
+
+def blas_gemv(A, x):
+    """y = A x through OpenBLAS dgemv -- the reference's default matvecmul! backend (src/pref.jl:15-16);
+    A column-major as Julia holds it."""
+    from scipy.linalg import blas
+    return blas.dgemv(1.0, A, x)
+
+
 def rhs_fault_dilatancy(pf, dl, gf, v, theta, pr, form="fft"):
     """ode() dilatancy variant, src/BEM/equation.jl:168-183."""
     relv = v - pf.vpl
