@@ -163,6 +163,7 @@ def fault_parity(oq, fs, p, g11, rows, du_local, threads=None, block=1024):
     mf = oq.gen_mesh("RectOkada", fs.x, fs.xi, fs.dx, fs.dxi, fs.dip)
     st_gpu = oq.stress_greens_function(mf, W.LAM, W.MU, buffer_ratio=1.0, fourier=False)
     kern_err = float(np.max(np.abs(st_gpu - st) / np.abs(st)))
+    kern_identical = bool(np.array_equal(st_gpu, st))
     rows_err = 0.0
     for b0 in range(0, r1 - r0, block):
         b1 = min(r1 - r0, b0 + block)
@@ -177,7 +178,8 @@ def fault_parity(oq, fs, p, g11, rows, du_local, threads=None, block=1024):
         den = np.maximum(np.abs(w), 1e-6 * np.max(np.abs(w)) + 1e-300)           # scale of the WHOLE field
         rhs_err = max(rhs_err, float(np.max(np.abs(np.asarray(g) - w[r0:r1]) / den[r0:r1]))) if r1 > r0 else rhs_err
     return {"kernel_max_rel_err": kern_err, "matrix_rows_max_rel_err": rows_err, "rhs_max_rel_err": rhs_err,
-            "rows": r1 - r0, "matrix_entries": (r1 - r0) * fs.nx * fs.nxi, "kernel_entries": int(st.size)}
+            "rows": r1 - r0, "matrix_entries": (r1 - r0) * fs.nx * fs.nxi, "kernel_entries": int(st.size),
+            "kernel_bit_identical": kern_identical}
 
 
 def build_fault_problem(oq, fs, rows, rng_seed=42):
@@ -539,7 +541,7 @@ def run_ours(args):
         parity = {"max_rel_err": max(e[0], e[1], e[2]), "tol": PARITY_TOL, "rows": int(cnt[0].item()),
                   "ranks": world, "kernel_max_rel_err": e[0], "kernel_entries": mine["kernel_entries"],
                   "matrix_rows_max_rel_err": e[1], "matrix_entries": int(cnt[1].item()), "rhs_max_rel_err": e[2],
-                  "e2e_vs_resident_max_rel_diff": e[3],
+                  "e2e_vs_resident_max_rel_diff": e[3], "kernel_bit_identical_rank0": mine["kernel_bit_identical"],
                   "oracle": "oracle/ CPU restatement: gf_fault_fault (GF.jl:31-58), dense expansion "
                             "(test/BEM/tests.jl:46-49), Toeplitz-form RHS (equation.jl:156-166); every row of every rank",
                   "pass": bool(max(e) <= PARITY_TOL)}

@@ -38,9 +38,8 @@ def _ftype_code(ftype) -> int:
 
 
 def gauss_legendre_hex(n: int):
-    """Tensor-product Gauss-Legendre rule on [-1,1]^3, weights normalised to 1 (GF.jl:318-323).
-    n = 1 is Gmsh's "Gauss1"; n = 2, 3 are the product rules Gmsh >= 4.9 returns for "Gauss2"/"Gauss3"
-    up to point ordering (examples/otf-with-mantle.jl:64-66)."""
+    """Tensor-product Gauss-Legendre rule with n points per axis on [-1,1]^3, weights normalised to 1
+    (GF.jl:318-323); point order: first coordinate fastest."""
     p, w = np.polynomial.legendre.leggauss(n)
     k, j, i = np.meshgrid(np.arange(n), np.arange(n), np.arange(n), indexing="ij")
     coords = np.stack([p[i.ravel()], p[j.ravel()], p[k.ravel()]], axis=1).reshape(-1)
@@ -48,12 +47,25 @@ def gauss_legendre_hex(n: int):
     return coords, weights / weights.sum()
 
 
+def gmsh_hex_points_per_axis(order: int) -> int:
+    """Points per axis of the hexahedron rule Gmsh >= 4.9 returns for getIntegrationPoints(5, "Gauss<order>")
+    (the call behind GF.jl:318-323): <order> is the polynomial ORDER integrated exactly, not the point count --
+    "Gauss1": 1 point; "Gauss2" and "Gauss3": the 2x2x2 product rule (examples/otf-with-mantle.jl:64-66);
+    from order 4 on (order + 3) // 2 points per axis ("Gauss4": 27 points).  Gmsh itself is not available here: the
+    mapping restates Gmsh's documented behaviour; pass an explicit (coords, weights) tuple to be independent of it."""
+    if order < 2:
+        return 1
+    if order < 4:
+        return 2
+    return (order + 3) // 2
+
+
 def get_quadrature(qtype):
     """GF.jl:318-328: a "GaussN" name or a (localCoords[3nq], weights[nq]) tuple."""
     if isinstance(qtype, str):
         if not (qtype.startswith("Gauss") and qtype[5:].isdigit()):
             raise ValueError(f"unsupported quadrature {qtype!r}")
-        return gauss_legendre_hex(int(qtype[5:]))
+        return gauss_legendre_hex(gmsh_hex_points_per_axis(int(qtype[5:])))
     coords, weights = qtype
     coords = np.asarray(coords, dtype=np.float64).reshape(-1)
     weights = np.asarray(weights, dtype=np.float64).reshape(-1)

@@ -1,6 +1,11 @@
 """GPU parity: Green's-function assembly through the C ABI vs the CPU oracle on the same inputs.
-Tolerance (BASELINE.json north_star): 1e-10 relative per entry; for cancellation-dominated entries the
-scale-aware form |Δ| <= 1e-10 * max|row| of SURVEY.md §7 is used and says so."""
+
+Okada paths (dc3d gradient rows, fault->fault, fault->mantle): the default kernels keep the published operation
+order of DC3D without FMA contraction (csrc/okada_strict.cuh), so they must be BIT-IDENTICAL to the oracle --
+asserted with ==.  The closed form is conditioned to ~1e-2 of an entry 1000 cell sizes away, so nothing weaker than
+identical rounding meets BASELINE.json's 1e-10 per entry at full size.  With OQ_OKADA=fast (restructured,
+FMA-contracted kernels; run as a twin by test_fast_okada_twin) the same tests use 1e-10 relative to the scale of
+the receiver's / source's row."""
 import json
 import os
 
@@ -13,6 +18,7 @@ from oracle import ref
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-10
+EXACT = os.environ.get("OQ_OKADA") != "fast"
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 
@@ -27,6 +33,8 @@ def test_dc3d_gradient_pointwise(gpu, dip, ftype):
     got = oq.dc3d_gradient(x, y, z, 0.6, 4.0, dip, -1.5, 2.5, -3.0, -0.5, ftype=ftype)
     d = (1.0, 0.0, 0.0) if ftype == 0 else (0.0, 1.0, 0.0)
     want = np.array([ref.dc3d(0.6, x[i], y[i], z[i], 4.0, dip, -1.5, 2.5, -3.0, -0.5, *d)[3:] for i in range(n)])
+    if EXACT:
+        assert np.array_equal(got, want)            # same operations in the same order: same bits
     assert scaled_err(got, want, axis=1) < TOL      # relative to the largest gradient entry of that receiver
 
 
@@ -42,6 +50,8 @@ def test_dc3d_singular_edges_and_kxi_ket(gpu):
         d = (1.0, 0.0, 0.0) if ftype == 0 else (0.0, 1.0, 0.0)
         want = np.array([ref.dc3d(0.6, *p, 4.0, 90.0, -1, 1, -1, 1, *d)[3:] for p in pts])
         assert np.all(got[:3] == 0.0) and np.all(want[:3] == 0.0)
+        if EXACT:
+            assert np.array_equal(got, want)
         assert scaled_err(got, want) < TOL
 
 
@@ -60,6 +70,8 @@ def test_fault_fault_kernel(gpu, spec, ftype, nrept, br):
     ft = oq.StrikeSlip() if ftype == 0 else oq.DipSlip()
     got = oq.stress_greens_function(mf_p, W.LAM, W.MU, ftype=ft, fourier=False, nrept=nrept, buffer_ratio=br)
     assert got.shape == want.shape
+    if EXACT:
+        assert np.array_equal(got, want)                            # bit-identical Toeplitz kernel
     assert rel_err(got, want) < TOL                                 # plain per-entry relative error
 
 
@@ -92,6 +104,8 @@ def test_dense_expansion_and_shards(gpu):
     mf_o, mf_p = meshes(oq, W.FaultSpec(100.0, 100.0, 10.0, 10.0, 41.0))
     want = ref.dense_from_toeplitz(ref.gf_fault_fault(mf_o, W.LAM, W.MU))
     full = oq.device_fault_fault(mf_p, W.LAM, W.MU).to_host()
+    if EXACT:
+        assert np.array_equal(full, want)
     assert rel_err(full, want) < TOL
     nf = mf_p.nx * mf_p.nxi
     parts = [oq.device_fault_fault(mf_p, W.LAM, W.MU, rows=(a, b)).to_host()
@@ -109,6 +123,8 @@ def test_fault_mantle(gpu, quad, ftype):
     ft = oq.StrikeSlip() if ftype == 0 else oq.DipSlip()
     got = oq.stress_greens_function(mf_p, ma_p, W.LAM, W.MU, ftype=ft, qtype=quad, nrept=2, buffer_ratio=1.0)
     assert got.shape == (6 * 36, 32)
+    if EXACT:
+        assert np.array_equal(got, want)                            # image sum, quadrature sum and stress epilogue in the reference's order
     # per column (one source): relative to the largest stress that source produces anywhere
     assert scaled_err(got, want, axis=0) < TOL
     # user-supplied quadrature tuple (GF.jl:325-328)
@@ -166,7 +182,8 @@ def test_matrix_roundtrip_and_gemv(gpu):
 
 @pytest.mark.parametrize("ftype", [0, 1])
 def test_fault_mantle_dipping_gauss3(gpu, ftype):
-    """test/BEM/tests.jl:85-95 geometry with a 60-degree fault, Gauss3 product rule, no periodic images"""
+    """test/BEM/tests.jl:85-95 geometry with a 60-degree fault, 3x3x3 product rule as an explicit tuple
+    (GF.jl:325-328), no periodic images"""
     oq = gpu
     fs = W.FaultSpec(100.0, 100.0, 10.0, 20.0, 60.0)
     bs = W.BoxSpec(-100.0, -50.0, -120.0, 200.0, 100.0, -30.0, 2, 3, 4)
@@ -174,6 +191,22 @@ def test_fault_mantle_dipping_gauss3(gpu, ftype):
     q = ref.gauss_quadrature(3)
     want = ref.gf_fault_mantle(mf_o, ma_o, 1.0, 1.0, ftype=ftype, quad=q, nrept=0, buffer_ratio=0.0)
     ft = oq.StrikeSlip() if ftype == 0 else oq.DipSlip()
-    got = oq.stress_greens_function(mf_p, ma_p, 1.0, 1.0, ftype=ft, qtype="Gauss3", nrept=0, buffer_ratio=0.0)
+    got = oq.stress_greens_function(mf_p, ma_p, 1.0, 1.0, ftype=ft, qtype=q, nrept=0, buffer_ratio=0.0)
     assert got.shape == (144, 50)
+    if EXACT:
+        assert np.array_equal(got, want)
     assert scaled_err(got, want, axis=0) < TOL
+
+
+def test_fast_okada_twin(gpu):
+    """the restructured FMA-contracted Okada kernels (OQ_OKADA=fast) pass the same tests at 1e-10 of the row scale;
+    the switch is read once per process, hence the subprocess"""
+    import subprocess
+    import sys
+    if not EXACT:
+        pytest.skip("already the twin")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-q", "-x",
+                          "-k", "dc3d or fault_fault or fault_mantle or dense_expansion"],
+                         env={**os.environ, "OQ_OKADA": "fast"}, capture_output=True, text=True, timeout=900, cwd=root)
+    assert res.returncode == 0, res.stdout[-2000:]

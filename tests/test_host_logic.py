@@ -58,8 +58,12 @@ def test_quadrature(oq):
     assert w.size == 8 and abs(w.sum() - 1) < 1e-15 and np.allclose(np.abs(c), 1 / np.sqrt(3))
     with pytest.raises(AssertionError, match="Wrong format of quadrature!"):     # GF.jl:326
         oq.get_quadrature((np.zeros(5), np.ones(2)))
+    # "Gauss<N>": N is the polynomial order in Gmsh (getIntegrationPoints(5, ...), GF.jl:318-323), not the point count
+    for name, npts in (("Gauss0", 1), ("Gauss1", 1), ("Gauss2", 8), ("Gauss3", 8), ("Gauss4", 27), ("Gauss5", 64)):
+        c, w = oq.get_quadrature(name)
+        assert w.size == npts and c.size == 3 * npts and abs(w.sum() - 1) < 1e-15, name
     co, wo = ref.gauss_quadrature(3)
-    c, w = oq.get_quadrature("Gauss3")
+    c, w = oq.get_quadrature("Gauss4")                                          # the 3x3x3 product rule
     np.testing.assert_array_equal(c, co)
     np.testing.assert_array_equal(w, wo)
 
