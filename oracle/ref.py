@@ -40,6 +40,43 @@ def lib():
     return _LIB
 
 
+_LIB_LD = None
+_ldp = C.POINTER(C.c_longdouble)
+
+
+def lib_ld():
+    """The arbiter build: okada.c / hex8.c in 80-bit extended precision (oracle/Makefile, liboetqf_oracle_ld.so)."""
+    global _LIB_LD
+    if _LIB_LD is None:
+        so = os.path.join(_HERE, "liboetqf_oracle_ld.so")
+        srcs = [os.path.join(_HERE, f) for f in ("okada.c", "hex8.c", "hex8_gen.inc", "Makefile")]
+        if not os.path.exists(so) or any(os.path.getmtime(s_) > os.path.getmtime(so) for s_ in srcs):
+            subprocess.check_call(["make", "-C", _HERE, "-B", "liboetqf_oracle_ld.so"], stdout=subprocess.DEVNULL)
+        _LIB_LD = C.CDLL(so)
+    return _LIB_LD
+
+
+def dc3d_ld(alpha, x, y, z, depth, dip, al1, al2, aw1, aw2, d1, d2, d3):
+    """dc3d evaluated in extended precision (np.longdouble[12])"""
+    assert np.finfo(np.longdouble).nmant >= 63, "needs an 80-bit long double"
+    u = np.zeros(12, dtype=np.longdouble)
+    d = C.c_longdouble
+    lib_ld().oq_refl_dc3d(d(alpha), d(x), d(y), d(z), d(depth), d(dip), d(al1), d(al2), d(aw1), d(aw2),
+                          d(d1), d(d2), d(d3), u.ctypes.data_as(_ldp))
+    return u
+
+
+def stress_vol_hex8_ld(x, y, z, qx, qy, qz, dx, dy, dz, eps, mu, nu):
+    """stress_vol_hex8 evaluated in extended precision (np.longdouble[6])"""
+    assert np.finfo(np.longdouble).nmant >= 63, "needs an 80-bit long double"
+    sig = np.zeros(6, dtype=np.longdouble)
+    e = np.ascontiguousarray(np.asarray(eps, dtype=np.longdouble))
+    d = C.c_longdouble
+    lib_ld().oq_refl_stress_vol_hex8(d(x), d(y), d(z), d(qx), d(qy), d(qz), d(dx), d(dy), d(dz),
+                                     e.ctypes.data_as(_ldp), d(mu), d(nu), sig.ctypes.data_as(_ldp))
+    return sig
+
+
 def _p(a):
     assert a.dtype == np.float64 and a.flags["F_CONTIGUOUS"] or a.flags["C_CONTIGUOUS"]
     return a.ctypes.data_as(_dp)

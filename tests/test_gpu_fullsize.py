@@ -5,6 +5,7 @@
 * configs[3] scale (20 000 fault cells + 19 320 hex8 cells, the largest coupled case that fits one B200): >= 1e4
   randomly sampled entries of each of the four Green's matrices, pulled out of ROW SHARDS built at the full column
   count, against pointwise evaluations of the oracle's dc3d / stress_vol_hex8 with the loops of GF.jl:123-290.
+  Okada entries must be bit-identical; hex8 entries are judged against the extended-precision arbiter (_arbitrated).
 """
 import numpy as np
 import pytest
@@ -58,8 +59,27 @@ def _hex8_unit(mao, i, x, y, z, p, mu, nu):
     return ref.stress_vol_hex8(x, y, z, mao.qx[i], mao.qy[i], mao.qz[i], mao.dx[i], mao.dy[i], mao.dz[i], eps, mu, nu)
 
 
-def _scaled(got, want, scale):
-    return float(np.max(np.abs(np.asarray(got) - np.asarray(want)) / scale))
+def _hex8_unit_ld(mao, i, x, y, z, p, mu, nu):
+    eps = np.zeros(6)
+    eps[p] = 1.0
+    return ref.stress_vol_hex8_ld(x, y, z, mao.qx[i], mao.qy[i], mao.qz[i], mao.dx[i], mao.dy[i], mao.dz[i], eps, mu, nu)
+
+
+def _arbitrated(got, want, exact):
+    """The hex8 closed form loses up to ~8 digits to cancellation far from the source (the fp64 oracle itself is
+    off by ~1e-8 of a row's scale at these distances; measured below), so two fp64 evaluations cannot agree to
+    1e-10 per entry.  Parity is therefore judged against the SAME closed form evaluated in 80-bit extended
+    precision (oracle/Makefile: liboetqf_oracle_ld.so): the product may deviate from it by 1e-10 of the entry plus
+    four times the largest rounding error the fp64 oracle itself commits on the sample.  Returns
+    (worst ratio err/bound, oracle's own worst error, product's worst error), errors relative to the sample's max."""
+    got = np.asarray(got, dtype=np.longdouble)
+    want = np.asarray(want, dtype=np.longdouble)
+    exact = np.asarray(exact, dtype=np.longdouble)
+    e_ref = np.abs(want - exact)
+    e_gpu = np.abs(got - exact)
+    bound = TOL * np.abs(exact) + 4 * np.max(e_ref)
+    scale = np.max(np.abs(exact))
+    return float(np.max(e_gpu / bound)), float(np.max(e_ref) / scale), float(np.max(e_gpu) / scale)
 
 
 def test_coupled_scale_sampled_entries(gpu):
@@ -86,27 +106,24 @@ def test_coupled_scale_sampled_entries(gpu):
         got = M.rows_to_host(0, M.local_rows)                              # local row k*rows_per + el
         assert got.shape == (6 * rows_per, nf)
         cols = rng.integers(0, nf, 80)
-        scale = max(np.max(np.abs(got)), 1e-300)
         for el in range(rows_per):
             e = int(e0) + el
             for j in cols:
                 want = _okada_stress_at(mfo, int(j % mfo.nx), int(j // mfo.nx), mao.cx[e], mao.cy[e], mao.cz[e],
                                         lam, mu, 2, lrept)
                 g = got[np.arange(6) * rows_per + el, j]
-                den = np.maximum(np.abs(want), 1e-3 * scale)                # scale-aware floor (tests/helpers.py)
-                worst = max(worst, float(np.max(np.abs(g - want) / den)))
+                worst = max(worst, float(np.max(np.abs(g - want))))
                 checked += 6
         M.free()
-    assert checked >= 10000 and worst <= TOL, (checked, worst)
+    assert checked >= 10000 and worst == 0.0, (checked, worst)        # published operation order: same bits
 
     # gf21 mantle -> fault: shards of fault rows; 6 unit strains x sampled source elements
-    checked, worst = 0, 0.0
     sd, cd = ref.sincosd(mfo.dip)
+    got_l, want_l, exact_l = [], [], []
     for r0 in rng.integers(0, nf - rows_per, nshard):
         M = oq.device_mantle_fault(ma, mf, lam, mu, rows=(int(r0), int(r0) + rows_per))
         got = M.rows_to_host(0, rows_per)
         assert got.shape == (rows_per, 6 * ne)
-        scale = max(np.max(np.abs(got)), 1e-300)
         srcs = rng.integers(0, ne, 80)
         for fl in range(rows_per):
             f = int(r0) + fl
@@ -114,38 +131,42 @@ def test_coupled_scale_sampled_entries(gpu):
             for i in srcs:
                 for pc in range(6):
                     S = _hex8_unit(mao, int(i), x, y, z, pc, mu, nu)
-                    want = -S[1] * sd + S[2] * cd                           # GF.jl:89-92, strike-slip
-                    worst = max(worst, abs(got[fl, pc * ne + i] - want) / max(abs(want), 1e-3 * scale))
-                    checked += 1
+                    Sl = _hex8_unit_ld(mao, int(i), x, y, z, pc, mu, nu)
+                    got_l.append(got[fl, pc * ne + i])
+                    want_l.append(-S[1] * sd + S[2] * cd)                   # GF.jl:89-92, strike-slip
+                    exact_l.append(-Sl[1] * sd + Sl[2] * cd)
         M.free()
-    assert checked >= 10000 and worst <= TOL, (checked, worst)
+    ratio, e_ref, e_gpu = _arbitrated(got_l, want_l, exact_l)
+    print(f"gf21: {len(got_l)} entries, fp64 oracle error {e_ref:.2e}, product error {e_gpu:.2e} (of the sample max)")
+    assert len(got_l) >= 10000 and ratio <= 1.0, (len(got_l), ratio, e_ref, e_gpu)
 
     # gf22 mantle -> mantle: shards of receiver elements; 36 entries per sampled pair
-    checked, worst = 0, 0.0
+    got_l, want_l, exact_l = [], [], []
     for e0 in rng.integers(0, ne - rows_per, nshard):
         M = oq.device_mantle_mantle(ma, lam, mu, elems=(int(e0), int(e0) + rows_per))
         got = M.rows_to_host(0, M.local_rows)
         assert got.shape == (6 * rows_per, 6 * ne)
-        scale = max(np.max(np.abs(got)), 1e-300)
         srcs = rng.integers(0, ne, 14)
         for el in range(rows_per):
             j = int(e0) + el
             for i in srcs:
                 for pc in range(6):
                     S = _hex8_unit(mao, int(i), mao.cx[j], mao.cy[j], mao.cz[j], pc, mu, nu)
-                    g = got[np.arange(6) * rows_per + el, pc * ne + i]
-                    den = np.maximum(np.abs(S), 1e-3 * scale)
-                    worst = max(worst, float(np.max(np.abs(g - S) / den)))
-                    checked += 6
+                    Sl = _hex8_unit_ld(mao, int(i), mao.cx[j], mao.cy[j], mao.cz[j], pc, mu, nu)
+                    got_l += list(got[np.arange(6) * rows_per + el, pc * ne + i])
+                    want_l += list(S)
+                    exact_l += list(Sl)
         M.free()
-    assert checked >= 10000 and worst <= TOL, (checked, worst)
+    ratio, e_ref, e_gpu = _arbitrated(got_l, want_l, exact_l)
+    print(f"gf22: {len(got_l)} entries, fp64 oracle error {e_ref:.2e}, product error {e_gpu:.2e} (of the sample max)")
+    assert len(got_l) >= 10000 and ratio <= 1.0, (len(got_l), ratio, e_ref, e_gpu)
 
     # gf11 at 250 x 80 (non-power-of-two strike count): every Toeplitz entry, and dense rows out of a shard
     st = ref.gf_fault_fault(mfo, lam, mu, buffer_ratio=1.0)
     st_gpu = oq.stress_greens_function(mf, lam, mu, buffer_ratio=1.0, fourier=False)
-    assert float(np.max(np.abs(st_gpu - st) / np.abs(st))) <= TOL
+    assert np.array_equal(st_gpu, st)
     r0 = 12345
     M = oq.device_fault_fault(mf, lam, mu, buffer_ratio=1.0, rows=(r0, r0 + 8))
     want = bench.toeplitz_rows(st, r0, r0 + 8)
-    assert float(np.max(np.abs(M.rows_to_host(0, 8) - want) / np.abs(want))) <= TOL
+    assert np.array_equal(M.rows_to_host(0, 8), want)
     M.free()
