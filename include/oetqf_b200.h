@@ -230,7 +230,8 @@ typedef struct OqSolveOptions {
 typedef struct OqSolveStats {
     double t, dt_last, dt_next;
     int64_t naccept, nreject, nrhs;
-    int32_t retcode;        /* 0 success (t == tstop), 1 maxiters, 2 dt underflow / unstable */
+    int32_t retcode;        /* 0 success (t == tstop), 1 maxiters, 2 dt underflow / unstable, 3 a peer rank did not
+                             * deliver in time (multi-GPU; the call also returns non-zero), 4 terminated by the callback */
 } OqSolveStats;
 
 /* Snapshot callback: called on the host after every `stride`-th accepted step (and at t0), with the

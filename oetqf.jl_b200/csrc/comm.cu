@@ -36,7 +36,51 @@ int comm_alloc_window(OqProblem* p)
     p->red_slots = b + p->wl.off_red;
     p->flags = reinterpret_cast<unsigned long long*>(b + p->wl.off_flags);
     p->epochs = reinterpret_cast<unsigned long long*>(b + p->wl.off_epochs);
+    // peer-wait policy: bounded spin (default 30 s; OQ_PEER_TIMEOUT_S=0 waits for ever, e.g. under a debugger or
+    // with host callbacks that may stall one rank for long) and a host-visible error word
+    double tmo = 30.0;
+    if (const char* e = getenv("OQ_PEER_TIMEOUT_S")) tmo = atof(e);
+    if (tmo < 0) tmo = 0;
+    unsigned long long init[kEpCount] = {};
+    init[kEpTimeoutNs] = (unsigned long long)(tmo * 1e9);
+    if (!p->err_host) {
+        if (cudaHostAlloc(reinterpret_cast<void**>(&p->err_host), sizeof(unsigned long long), cudaHostAllocMapped) ==
+            cudaSuccess) {
+            *p->err_host = 0;
+            void* dev = nullptr;
+            if (cudaHostGetDevicePointer(&dev, p->err_host, 0) == cudaSuccess) init[kEpHostErr] = (unsigned long long)dev;
+        } else {
+            cudaGetLastError();
+            p->err_host = nullptr;
+        }
+    }
+    OQ_CUDA(cudaMemcpy(p->epochs, init, sizeof(init), cudaMemcpyHostToDevice));
     return 0;
+}
+
+int comm_check_error(OqProblem* p, const char* where)
+{
+    if (p->err_host && *reinterpret_cast<volatile unsigned long long*>(p->err_host))
+        return fail("%s: timed out waiting for a peer rank (results of this call are invalid; OQ_PEER_TIMEOUT_S sets the limit)", where);
+    return 0;
+}
+
+void comm_clear_error(OqProblem* p)
+{
+    if (p->err_host && *reinterpret_cast<volatile unsigned long long*>(p->err_host)) {
+        *p->err_host = 0;
+        cudaMemsetAsync(p->epochs + kEpError, 0, sizeof(unsigned long long), p->stream);
+    }
+}
+
+ColOwners comm_owners(const OqProblem* p)
+{
+    if (p->peers) return p->peers->own;
+    ColOwners o;
+    o.world = 1;
+    o.fb[0] = 0; o.fb[1] = p->nf;
+    o.eb[0] = 0; o.eb[1] = p->ne;
+    return o;
 }
 
 PeerTargets comm_targets(const OqProblem* p)
@@ -50,7 +94,9 @@ PeerTargets comm_targets(const OqProblem* p)
 
 void comm_release(OqProblem* p)
 {
-    if (!p->peers) return;
+    if (!p->peers) {
+        return;
+    }
     for (int r = 0; r < p->peers->t.world; ++r)
         if (p->peers->opened[r] && p->peers->ipc_base[r]) cudaIpcCloseMemHandle(p->peers->ipc_base[r]);
     delete p->peers;
@@ -115,6 +161,7 @@ int oq_comm_connect(OqProblem* p, const uint8_t* all)
     comm_release(p);
     PeerWindow* pw = new PeerWindow();
     pw->t.world = world; pw->t.rank = rank;
+    pw->own.world = world;
     int fcover = 0, ecover = 0;
     for (int r = 0; r < world; ++r) {
         HandleBlob b;
@@ -126,6 +173,8 @@ int oq_comm_connect(OqProblem* p, const uint8_t* all)
         else if (b.f0 != fcover || b.e0 != ecover)
             rc = fail("row shards are not contiguous in rank order at rank %d", r);
         if (rc) { p->peers = pw; comm_release(p); return rc; }
+        pw->own.fb[r] = b.f0; pw->own.fb[r + 1] = b.f1;
+        pw->own.eb[r] = b.e0; pw->own.eb[r + 1] = b.e1;
         fcover = b.f1; ecover = b.e1;
         if (r == rank) { pw->t.base[r] = p->window.p; continue; }
         void* ptr = nullptr;

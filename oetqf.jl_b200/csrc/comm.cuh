@@ -21,7 +21,9 @@ enum : int {
     kEpReduce = 1,      // number of error-norm publications so far
     kEpBlocksF = 2,     // block-done counter of the forcing kernel
     kEpBlocksR = 3,     // block-done counter of the error-norm kernel
-    kEpError = 4,       // sticky error flag (peer wait timed out)
+    kEpError = 4,       // sticky error flag (peer wait timed out); cleared by oq_solve / oq_rhs* on entry
+    kEpTimeoutNs = 5,   // how long a kernel waits for a peer before giving up (0: for ever); OQ_PEER_TIMEOUT_S
+    kEpHostErr = 6,     // device address of a page-locked host word that receives 1 on a timeout (0: none)
     kEpCount = 8
 };
 
@@ -37,8 +39,17 @@ struct PeerTargets {
     double* base[kMaxWorld] = {};          // window base of each rank in this process's address space
 };
 
+// who owns which columns of the two forcing vectors (row shards are contiguous in rank order): rank r owns fault
+// cells [fb[r], fb[r+1]) and mantle elements [eb[r], eb[r+1])
+struct ColOwners {
+    int world = 1;
+    int fb[kMaxWorld + 1] = {};
+    int eb[kMaxWorld + 1] = {};
+};
+
 struct PeerWindow {
     PeerTargets t;
+    ColOwners own;
     void* ipc_base[kMaxWorld] = {};        // what cudaIpcOpenMemHandle returned (allocation base)
     bool opened[kMaxWorld] = {};
 };
@@ -46,24 +57,51 @@ struct PeerWindow {
 int comm_alloc_window(OqProblem* p);
 void comm_release(OqProblem* p);
 PeerTargets comm_targets(const OqProblem* p);
+ColOwners comm_owners(const OqProblem* p);
+// 0 if no kernel of this problem gave up waiting for a peer since the last comm_clear_error
+int comm_check_error(OqProblem* p, const char* where);
+void comm_clear_error(OqProblem* p);
 
 #ifdef __CUDACC__
-// spin until every peer's flag reaches `epoch` (bounded: sets the sticky error flag after ~4 s)
+// A peer did not deliver in time: raise the sticky device flag (the step controller turns it into done / retcode 3,
+// so the device stops stepping) and the host-visible word (checked by the host after every synchronisation, so
+// oq_rhs / oq_rhs_resident / oq_solve return an error instead of numbers computed from stale data).
+__device__ __forceinline__ void raise_peer_timeout(unsigned long long* epochs)
+{
+    atomicExch(epochs + kEpError, 1ull);
+    unsigned long long* host = reinterpret_cast<unsigned long long*>(epochs[kEpHostErr]);
+    if (host) asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(host), "l"(1ull) : "memory");
+}
+
+// spin until *flag >= target.  sys: the flag is written by a peer GPU (acquire at system scope), else by another
+// CTA of this GPU.  Bounded by epochs[kEpTimeoutNs]; returns false after raising the error flags.
+__device__ __forceinline__ bool spin_until(const unsigned long long* flag, unsigned long long target, bool sys,
+                                           unsigned long long* epochs)
+{
+    unsigned long long t0 = 0;
+    const unsigned long long limit = epochs[kEpTimeoutNs];
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        unsigned long long v;
+        if (sys) asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+        else asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+        if (v >= target) return true;
+        if (limit) {
+            unsigned long long t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > limit) { raise_peer_timeout(epochs); return false; }
+        }
+    }
+}
+
+// spin until every peer's flag reaches `epoch` (err = epochs + kEpError, kept for the callers' convenience)
 __device__ __forceinline__ void wait_peers(const unsigned long long* flags, int world, int self,
                                            unsigned long long epoch, unsigned long long* err)
 {
-    unsigned long long t0 = 0;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    unsigned long long* epochs = err - kEpError;
     for (int r = 0; r < world; ++r) {
         if (r == self) continue;
-        for (;;) {
-            unsigned long long v;
-            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + r) : "memory");
-            if (v >= epoch) break;
-            unsigned long long t1;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-            if (t1 - t0 > 4000000000ull) { atomicExch(err, 1ull); return; }
-        }
+        if (!spin_until(flags + r, epoch, true, epochs)) return;
     }
 }
 

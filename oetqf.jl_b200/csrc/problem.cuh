@@ -15,6 +15,7 @@ struct MatOperand {
     const double* x = nullptr;  // copy 0 of the forcing vector
     size_t x_stride = 0;        // distance to copy 1 (0: single copy)
     int cols = 0;
+    int x_kind = 0;     // 0: x = v - vpl (columns are fault cells); 1: x = dϵ - dϵ0 (column p*ne + e is element e)
     int nseg = 0;       // number of column segments the row is split into
     int seg_len = 0;    // columns per segment (multiple of 512)
 };
@@ -73,6 +74,7 @@ struct OqProblem {
     double* red_slots = nullptr;                    // [2][kMaxWorld] partial sums of the step error norm
     unsigned long long* flags = nullptr;            // [2][kMaxWorld] arrival epochs: forcing, error norm
     unsigned long long* epochs = nullptr;           // local counters, see comm.cuh
+    unsigned long long* err_host = nullptr;         // page-locked, device-mapped word: 1 after a peer-wait timeout
     // matvec scratch
     oq::DevBuf<double> partial_f, partial_m;        // [rows * nsegTotal]
     oq::DevBuf<unsigned> counters;                  // [row blocks fault + row blocks mantle]
@@ -91,8 +93,10 @@ struct OqProblem {
     oq::DevBuf<double> ctl;                         // device-side controller record (StepCtl)
 
     cudaStream_t stream = nullptr;
-    cudaGraphExec_t rhs_graph = nullptr;            // one resident RHS evaluation (u -> k1), captured once
+    cudaGraphExec_t rhs_graph = nullptr;            // TWO resident RHS evaluations (u -> k1), captured once (the
+                                                    // traversal direction of the matvec alternates between them)
     int64_t rhs_graph_launches = 0;                 // kernels per replay
+    unsigned mv_seq = 0;                            // evaluations enqueued so far (parity = traversal direction)
 
     // optional per-launch timing of the matvec (bench.py's roofline line)
     bool prof_on = false;

@@ -398,6 +398,7 @@ matvec_fused_kernel(const __grid_constant__ MatvecArgs args)
 
 }  // namespace oq
 #include "matvec_stream.cuh"
+#include "matvec_panel.cuh"
 #include "toeplitz_fft.cuh"
 namespace oq {
 
@@ -423,15 +424,18 @@ static int sm_count()
     return n;
 }
 
-// streaming plan over both row sets; returns the grid size
-static int plan_stream(MatvecArgs& a)
+// streaming plan over both row sets; returns the grid size.  by_cols: chunk the columns that exist (rounded up to
+// 16; the panel kernel) instead of the padded leading dimension (the first streaming kernel)
+static int plan_stream(MatvecArgs& a, bool by_cols = false)
 {
     long long total = 0;
     for (int jb = 0; jb < 2; ++jb) {
         MatvecJob& j = a.job[jb];
         j.nrb = j.nrows > 0 ? (j.nrows + kStR - 1) / kStR : 0;
-        for (int o = 0; o < 2; ++o)
-            j.nch[o] = (j.op[o].G && j.op[o].cols > 0 && j.nrows > 0) ? (int)((j.op[o].ld + kStCH - 1) / kStCH) : 0;
+        for (int o = 0; o < 2; ++o) {
+            const size_t width = by_cols ? round_up((size_t)j.op[o].cols, 16) : j.op[o].ld;
+            j.nch[o] = (j.op[o].G && j.op[o].cols > 0 && j.nrows > 0) ? (int)((width + kStCH - 1) / kStCH) : 0;
+        }
         j.chunks_per_rb = j.nch[0] + j.nch[1];
         if (j.chunks_per_rb == 0) j.nrb = 0;
         j.chunk_begin = total;
@@ -450,13 +454,13 @@ static int plan_stream(MatvecArgs& a)
     return grid;
 }
 
-// 0: streaming kernel (matvec_stream.cuh), 2: first LDG kernel
+// 0: fused panel kernel (matvec_panel.cuh), 1: first streaming kernel (matvec_stream.cuh), 2: first LDG kernel
 static int matvec_variant()
 {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("OQ_MATVEC");
-        v = (e && strcmp(e, "ldg") == 0) ? 2 : 0;
+        v = (e && strcmp(e, "ldg") == 0) ? 2 : (e && strcmp(e, "stream") == 0) ? 1 : 0;
     }
     return v;
 }
@@ -517,8 +521,60 @@ int plan_job(MatvecJob& job, int nrows)
     return nrb;
 }
 
-int launch_matvec(MatvecArgs& a, cudaStream_t stream)
+// the fused kernel: `pro` non-null folds the forcing front end into the launch
+int launch_panel(MatvecArgs& a, const ForcingArgs* pro, const ColOwners& own, int ne, int f0, unsigned seq,
+                 cudaStream_t stream)
 {
+    PanelArgs A{};
+    int grid = plan_stream(a, true);
+    if (grid == 0) {
+        if (!pro) return 0;
+        grid = 1;      // a rank without rows still takes part in the exchange (publishes an empty slice)
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        OQ_CUDA(cudaFuncSetAttribute(matvec_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPnSmemBytes));
+        attr_set = true;
+    }
+    a.pass = nullptr;
+    a.keep_chunks = keep_chunks_per_cta(grid);
+    A.mv = a;
+    A.pro.enabled = pro ? 1 : 0;
+    if (pro) A.pro.fa = *pro;
+    A.own = own;
+    A.ne = ne > 0 ? ne : 1;
+    A.reverse = pingpong_enabled() ? (int)(seq & 1u) : 0;
+    for (int jb = 0; jb < 2; ++jb) {
+        const int n0 = a.job[jb].nch[0];
+        A.cstart[jb] = n0 > 0 ? (f0 / kPnCH < n0 ? f0 / kPnCH : n0 - 1) : 0;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kPnThreads);
+    cfg.dynamicSmemBytes = kPnSmemBytes; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    OQ_CUDA(cudaLaunchKernelEx(&cfg, matvec_panel_kernel, A));
+    OQ_LAUNCHED();
+    return 0;
+}
+
+struct PanelLaunch {
+    const ForcingArgs* pro = nullptr;   // fold the forcing front end into the launch
+    ColOwners own;
+    int ne = 1, f0 = 0;
+    unsigned seq = 0;
+};
+
+int launch_matvec(MatvecArgs& a, cudaStream_t stream, const PanelLaunch* pl = nullptr)
+{
+    if (matvec_variant() == 0) {
+        if (pl) return launch_panel(a, pl->pro, pl->own, pl->ne, pl->f0, pl->seq, stream);
+        ColOwners own;
+        own.world = 1; own.fb[1] = 0x7fffffff; own.eb[1] = 0x7fffffff;
+        return launch_panel(a, nullptr, own, 1, 0, 0u, stream);
+    }
     if (!use_ldg_matvec()) {
         const int grid = plan_stream(a);
         if (grid == 0) return 0;
@@ -611,7 +667,11 @@ static int rhs_views(OqProblem* p, const StateView& in, const StateView& out, co
     // single-rank, FFT form, no dense operand: the forward transform forms v - vpl itself (one launch fewer)
     const bool direct_fft = p->gf11_form == OQ_GF11_FFT && p->kind != kViscoelastic && p->world == 1 && !stage &&
                             !use_direct_toeplitz();
-    if (!direct_fft) {
+    // dense fault-fault operand + panel kernel: the forcing front end runs inside the matvec launch (one launch per
+    // evaluation); the FFT form needs the forcing vector before its transforms, the older kernels have no prologue
+    static const bool split_forcing = [] { const char* e = getenv("OQ_FORCING"); return e && strcmp(e, "split") == 0; }();
+    const bool fused = matvec_variant() == 0 && p->gf11_form == OQ_GF11_DENSE && !split_forcing && p->nfl + fa.nel > 0;
+    if (!direct_fft && !fused) {
     // small shards: ONE block (no cross-block handshake before the publication); large ones: 256-thread blocks
     if (nthr <= 4096) forcing_kernel<<<1, 1024, 0, st>>>(fa);
     else forcing_kernel<<<(nthr + 255) / 256, 256, 0, st>>>(fa);
@@ -676,7 +736,11 @@ static int rhs_views(OqProblem* p, const StateView& in, const StateView& out, co
     }();
     const bool prof = p->prof_on && !capturing && p->prof_used + 2 <= p->prof_ev.size();
     if (prof) OQ_CUDA(cudaEventRecord(p->prof_ev[p->prof_used], st));
-    OQ_TRY(launch_matvec(a, st));
+    PanelLaunch pl;
+    pl.pro = fused ? &fa : nullptr;
+    pl.own = comm_owners(p);
+    pl.ne = p->ne; pl.f0 = p->f0; pl.seq = p->mv_seq++;
+    OQ_TRY(launch_matvec(a, st, &pl));
     if (prof) {
         OQ_CUDA(cudaEventRecord(p->prof_ev[p->prof_used + 1], st));
         p->prof_used += 2;
@@ -704,7 +768,7 @@ int gemv_scratch_sizes(const OqMatrix* A, size_t* npartial, size_t* ncounters)
     MatvecJob& j = a.job[0];
     j.op[0].G = A->d.p; j.op[0].ld = A->ld; j.op[0].cols = A->cols;
     const int nrb = plan_job(j, A->local_rows);
-    plan_stream(a);
+    plan_stream(a, matvec_variant() == 0);
     const int per_row = j.nsegTotal > j.slots ? j.nsegTotal : j.slots;
     *npartial = (size_t)A->local_rows * (per_row > 0 ? per_row : 1);
     *ncounters = nrb;
@@ -720,6 +784,7 @@ OqProblem::~OqProblem()
     for (cudaEvent_t e : prof_ev) cudaEventDestroy(e);
     if (rhs_graph) cudaGraphExecDestroy(rhs_graph);
     comm_release(this);
+    if (err_host) cudaFreeHost(err_host);
     if (stream) cudaStreamDestroy(stream);
 }
 
@@ -820,9 +885,9 @@ static int finish_problem(OqProblem* p, const OqFaultProperty* pf, const OqDilat
         }
     }
     if (p->kind == kViscoelastic) {
-        p->opf[1].G = p->g21->d.p; p->opf[1].ld = p->g21->ld; p->opf[1].x = p->reldeps; p->opf[1].x_stride = p->wl.reldeps_len; p->opf[1].cols = p->g21->cols;
+        p->opf[1].G = p->g21->d.p; p->opf[1].ld = p->g21->ld; p->opf[1].x = p->reldeps; p->opf[1].x_stride = p->wl.reldeps_len; p->opf[1].cols = p->g21->cols; p->opf[1].x_kind = 1;
         p->opm[0].G = p->g12->d.p; p->opm[0].ld = p->g12->ld; p->opm[0].x = p->relv; p->opm[0].x_stride = p->wl.relv_len; p->opm[0].cols = p->g12->cols;
-        p->opm[1].G = p->g22->d.p; p->opm[1].ld = p->g22->ld; p->opm[1].x = p->reldeps; p->opm[1].x_stride = p->wl.reldeps_len; p->opm[1].cols = p->g22->cols;
+        p->opm[1].G = p->g22->d.p; p->opm[1].ld = p->g22->ld; p->opm[1].x = p->reldeps; p->opm[1].x_stride = p->wl.reldeps_len; p->opm[1].cols = p->g22->cols; p->opm[1].x_kind = 1;
     }
     // matvec scratch
     MatvecArgs plan{};
@@ -831,7 +896,7 @@ static int finish_problem(OqProblem* p, const OqFaultProperty* pf, const OqDilat
     jm.op[0] = p->opm[0]; jm.op[1] = p->opm[1];
     const int nrbf = plan_job(jf, nfl);
     const int nrbm = plan_job(jm, p->kind == kViscoelastic ? 6 * nel : 0);
-    plan_stream(plan);
+    plan_stream(plan, matvec_variant() == 0);
     p->nseg_f = jf.nsegTotal > jf.slots ? jf.nsegTotal : jf.slots;
     p->nseg_m = jm.nsegTotal > jm.slots ? jm.nsegTotal : jm.slots;
     OQ_TRY(p->partial_f.alloc((size_t)nfl * (p->nseg_f > 0 ? p->nseg_f : 1) + 1));
@@ -979,13 +1044,16 @@ int oq_rhs(OqProblem* p, double t, const double* const* u_parts, double* const* 
     double *du_dev[5], *u_dev[5];
     if (zero_copy_enabled() && mapped_parts(p, u_parts, u_dev) &&
         mapped_parts(p, const_cast<const double* const*>(du_parts), du_dev)) {
+        comm_clear_error(p);
         OQ_TRY(rhs_views(p, view_of_parts(p, u_dev), view_of_parts(p, du_dev), nullptr, nullptr));
         OQ_CUDA(cudaStreamSynchronize(p->stream));
-        return 0;
+        return comm_check_error(p, "oq_rhs");
     }
+    comm_clear_error(p);
     OQ_TRY(upload_parts(p, u_parts, p->utmp.p));
     OQ_TRY(rhs_device(p, p->utmp.p, p->unew.p));
-    return download_parts(p, p->unew.p, du_parts);
+    OQ_TRY(download_parts(p, p->unew.p, du_parts));
+    return comm_check_error(p, "oq_rhs");
 }
 
 int oq_state_set(OqProblem* p, const double* const* u_parts)
@@ -1019,11 +1087,14 @@ int oq_rhs_resident(OqProblem* p, int nevals, double* ms_total)
     // scalar -- buffer parity, epochs -- lives in device memory), which removes the launch gaps that dominate
     // small problems.
     const bool graph = !p->prof_on && nevals >= 4;
+    comm_clear_error(p);
     if (graph && !p->rhs_graph) {
         cudaGraph_t g = nullptr;
+        p->mv_seq &= ~1u;                             // the captured pair starts with a forward traversal
         OQ_CUDA(cudaStreamBeginCapture(p->stream, cudaStreamCaptureModeThreadLocal));
         const int64_t before = g_launches.load();
-        const int rc = rhs_device(p, p->u.p, p->k[0].p);
+        int rc = rhs_device(p, p->u.p, p->k[0].p);
+        if (!rc) rc = rhs_device(p, p->u.p, p->k[0].p);
         p->rhs_graph_launches = g_launches.load() - before;
         g_launches.fetch_sub(p->rhs_graph_launches);
         const cudaError_t ce = cudaStreamEndCapture(p->stream, &g);
@@ -1035,16 +1106,17 @@ int oq_rhs_resident(OqProblem* p, int nevals, double* ms_total)
     }
     EventTimer tm;
     OQ_TRY(tm.start(p->stream));
-    for (int i = 0; i < nevals; ++i) {
-        if (graph) {
+    int i = 0;
+    if (graph) {
+        if (p->mv_seq & 1u) { OQ_TRY(rhs_device(p, p->u.p, p->k[0].p)); ++i; }   // keep the direction alternating
+        for (; i + 2 <= nevals; i += 2) {
             OQ_CUDA(cudaGraphLaunch(p->rhs_graph, p->stream));
             g_launches.fetch_add(p->rhs_graph_launches);
-        } else {
-            OQ_TRY(rhs_device(p, p->u.p, p->k[0].p));
         }
     }
+    for (; i < nevals; ++i) OQ_TRY(rhs_device(p, p->u.p, p->k[0].p));
     OQ_TRY(tm.stop(ms_total, p->stream));
-    return 0;
+    return comm_check_error(p, "oq_rhs_resident");
 }
 
 int oq_profile_enable(OqProblem* p, int on)

@@ -153,6 +153,11 @@ __global__ void controller_kernel(CtlArgs a)
     if (c.done) { c.accepted = 0; return; }
     const unsigned long long ep = *(volatile unsigned long long*)(a.epochs + kEpReduce);
     if (a.world > 1) wait_peers(a.flags + kMaxWorld, a.world, a.rank, ep, a.epochs + kEpError);
+    if (*reinterpret_cast<volatile unsigned long long*>(a.epochs + kEpError)) {
+        // a kernel of this step gave up waiting for a peer: its numbers are stale -- stop stepping, tell the host
+        c.accepted = 0; c.done = 1; c.retcode = 3;
+        return;
+    }
     const size_t par = (size_t)((ep - 1ull) & 1ull);
     double tot = 0.0;
     for (int r = 0; r < a.world; ++r) tot += *(volatile const double*)(a.red_slots + par * kMaxWorld + r);
@@ -351,6 +356,7 @@ extern "C" int oq_solve(OqProblem* p, double t0, const OqSolveOptions* o, int64_
     OQ_CHECK(o->fixed_dt || (o->reltol > 0 && o->abstol > 0), "tolerances must be positive");
     OQ_TRY(enter());
     if (stride < 1) stride = 1;
+    comm_clear_error(p);
     StepCtl h{};
     h.t = t0; h.tstop = o->tstop;
     h.dtmax = o->dtmax > 0 ? o->dtmax : (o->tstop - t0);
@@ -436,18 +442,21 @@ extern "C" int oq_solve(OqProblem* p, double t0, const OqSolveOptions* o, int64_
         if (ce == cudaSuccess) ce = cudaStreamSynchronize(p->stream);
         if (ce != cudaSuccess) { rc = fail("step failed: %s", cudaGetErrorString(ce)); break; }
         iters += batch;
+        if (h.retcode == 3 || comm_check_error(p, "oq_solve")) {
+            rc = fail("oq_solve: timed out waiting for a peer rank at t = %g (state not advanced past it; "
+                      "OQ_PEER_TIMEOUT_S sets the limit)", h.t);
+            break;
+        }
         if (h.naccept > acc_before && (h.naccept % stride == 0 || h.done)) {
             stop = snapshot(h.t, h.naccept);
             if (stop < 0) { rc = 1; break; }
         }
     }
-    unsigned long long eflag = 0;
-    cudaMemcpy(&eflag, p->epochs + kEpError, sizeof(eflag), cudaMemcpyDeviceToHost);
-    if (!rc && eflag) rc = fail("timed out waiting for a peer rank during the solve");
+    if (!rc && comm_check_error(p, "oq_solve")) rc = 1;
     if (stats) {
         stats->t = h.t; stats->dt_last = h.dt_last; stats->dt_next = h.dt;
         stats->naccept = h.naccept; stats->nreject = h.nreject; stats->nrhs = h.nrhs + 1;
-        stats->retcode = h.retcode ? h.retcode : (h.done ? 0 : (iters >= maxiters ? 1 : 0));
+        stats->retcode = h.retcode ? h.retcode : (h.done ? 0 : (stop > 0 ? 4 : (iters >= maxiters ? 1 : 0)));
     }
     return rc;
 }

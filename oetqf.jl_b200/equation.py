@@ -314,7 +314,7 @@ def solve(prob: ODEProblem, alg=Tsit5(), *, reltol=1e-3, abstol=1e-6, dt=0.0, dt
         sol.t.append(stats.t)
         sol.u.append(ArrayPartition(*u))
     if sol.retcode == "Default":
-        sol.retcode = {0: "Success", 1: "MaxIters", 2: "Unstable"}.get(stats.retcode, "Failure")
+        sol.retcode = {0: "Success", 1: "MaxIters", 2: "Unstable", 3: "PeerTimeout", 4: "Terminated"}.get(stats.retcode, "Failure")
     sol.stats = dict(naccept=stats.naccept, nreject=stats.nreject, nf=stats.nrhs, t=stats.t,
                      dt_last=stats.dt_last, dt_next=stats.dt_next)
     return sol
