@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define OQ_ABI_VERSION 1
+#define OQ_ABI_VERSION 2
 
 /* FaultType, src/BEM/GF.jl:3-5 */
 enum { OQ_STRIKE_SLIP = 0, OQ_DIP_SLIP = 1 };
@@ -225,6 +225,10 @@ typedef struct OqSolveOptions {
     int64_t maxiters;
     int32_t algorithm;      /* OQ_ALG_TSIT5 (test/tests.jl:11) or OQ_ALG_VCABM5 (examples/otf-with-mantle.jl:160) */
     int32_t fixed_dt;       /* != 0: take fixed steps of dt0 (no error control) */
+    int32_t async_snapshots;/* != 0: snapshots go through a device-side ring drained by a second stream; fn runs while
+                             * the next batch of steps executes (wsolve's mode, src/io.jl:51-58,128-130).  A stop request
+                             * then takes effect within one batch (<= 16 steps) instead of at exactly that step. */
+    int32_t reserved;
 } OqSolveOptions;
 
 typedef struct OqSolveStats {

@@ -54,7 +54,7 @@ class OqDilatancyProperty(C.Structure):
 class OqSolveOptions(C.Structure):
     _fields_ = [("reltol", C.c_double), ("abstol", C.c_double), ("dt0", C.c_double), ("dtmax", C.c_double),
                 ("tstop", C.c_double), ("maxiters", C.c_int64), ("algorithm", C.c_int32),
-                ("fixed_dt", C.c_int32)]
+                ("fixed_dt", C.c_int32), ("async_snapshots", C.c_int32), ("reserved", C.c_int32)]
 
 
 class OqSolveStats(C.Structure):

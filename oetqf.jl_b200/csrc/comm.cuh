@@ -19,12 +19,12 @@ constexpr int kMaxWorld = 16;
 enum : int {
     kEpForcing = 0,     // number of forcing publications so far (parity selects the buffer copy)
     kEpReduce = 1,      // number of error-norm publications so far
-    kEpBlocksF = 2,     // block-done counter of the forcing kernel
-    kEpBlocksR = 3,     // block-done counter of the error-norm kernel
+    kEpBlocksF = 16,    // block-done counter of the forcing front end  (own 128-byte line: every CTA adds to it while
+    kEpBlocksR = 17,    // block-done counter of the error-norm kernel   the producers of the grid poll kEpForcing)
     kEpError = 4,       // sticky error flag (peer wait timed out); cleared by oq_solve / oq_rhs* on entry
     kEpTimeoutNs = 5,   // how long a kernel waits for a peer before giving up (0: for ever); OQ_PEER_TIMEOUT_S
     kEpHostErr = 6,     // device address of a page-locked host word that receives 1 on a timeout (0: none)
-    kEpCount = 8
+    kEpCount = 32
 };
 
 // Offsets (in doubles) inside a window; identical on every rank (they depend on global sizes only).
@@ -86,6 +86,7 @@ __device__ __forceinline__ bool spin_until(const unsigned long long* flag, unsig
         if (sys) asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
         else asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
         if (v >= target) return true;
+        __nanosleep(40);
         if (limit) {
             unsigned long long t1;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));

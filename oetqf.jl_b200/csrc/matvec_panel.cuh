@@ -4,8 +4,8 @@
 // Successor of matvec_stream.cuh (kept as a validation twin, OQ_MATVEC=stream), built for the small row shards of
 // the 8-GPU configuration, where the evaluation is 40-50 us long and every microsecond outside the streaming loop
 // shows:
-//   * PROLOGUE in the kernel (was forcing_kernel, a second launch): the otherwise idle epilogue warp of every CTA
-//     forms its slice of v - vpl and dϵ - dϵ0 (with the integrator's stage combination fused in), stores it into
+//   * PROLOGUE in the kernel (was forcing_kernel, a second launch): the consumer warps of every CTA, idle until the
+//     first forcing piece arrives, form their slice of v - vpl and dϵ - dϵ0 (with the integrator's stage combination fused in), stores it into
 //     every rank's window over NVLink and joins a grid-wide count; the last CTA publishes the epoch to the peers.
 //     The producer warp has its whole ring of matrix tiles in flight before any of this is awaited.
 //   * PANEL traversal: a CTA walks its span of chunks in panels of up to kPnP row blocks, column by column, starting
@@ -27,7 +27,7 @@ namespace oq {
 constexpr int kPnR = kStR;          // rows per row block
 constexpr int kPnCH = kStCH;        // columns per chunk
 constexpr int kPnStages = 6;        // ring stages of kPnR x kPnCH doubles (32 KB each)
-constexpr int kPnP = 6;             // row blocks per panel (24 running sums per consumer thread)
+constexpr int kPnPMax = 6;          // row blocks per panel (24 running sums per consumer thread); template parameter P <= kPnPMax
 constexpr int kPnConsumers = 256;
 constexpr int kPnCWarps = kPnConsumers / 32;
 constexpr int kPnThreads = kPnConsumers + 64;
@@ -50,6 +50,7 @@ struct PanelArgs {
 };
 
 // segments [k0, k0 + ns) of a span (row-block parts in processing order) that form one panel
+template <int kPnP>
 struct Panel {
     int job, ns, cpr;
     int rb[kPnP], lo[kPnP], hi[kPnP];
@@ -91,8 +92,8 @@ __device__ __forceinline__ void panel_column(const MatvecJob& j, int c, int& ose
     ncol = min(kPnCH, colsp - c0);
 }
 
-// one pass of the forcing front end over this CTA's slice of the local rows (executed by ONE warp)
-__device__ __forceinline__ void prologue_slice(const ForcingArgs& a, int lane, unsigned long long ep)
+// one pass of the forcing front end over this CTA's slice of the local rows (executed by `nthr` threads)
+__device__ __forceinline__ void prologue_slice(const ForcingArgs& a, int lane, int nthr, unsigned long long ep)
 {
     const size_t par = (size_t)(ep & 1ull);
     const int world = a.peers.world;
@@ -108,7 +109,7 @@ __device__ __forceinline__ void prologue_slice(const ForcingArgs& a, int lane, u
     };
     const int G = gridDim.x, b = blockIdx.x;
     const int t0 = (int)(((long long)a.nfl * b) / G), t1 = (int)(((long long)a.nfl * (b + 1)) / G);
-    for (int t = t0 + lane; t < t1; t += 32) {
+    for (int t = t0 + lane; t < t1; t += nthr) {
         // (the fault partitions of the stage state are written by the epilogue of the row, which needs them anyway)
         const double vt = staged ? combine(a.off_fault[0] + t) : a.v[t];
         const double rv = vt - a.vpl;                                        // equation.jl:38
@@ -116,7 +117,7 @@ __device__ __forceinline__ void prologue_slice(const ForcingArgs& a, int lane, u
         for (int r = 0; r < world; ++r) a.peers.base[r][off] = rv;           // local + NVLink peer stores
     }
     const int e0 = (int)(((long long)a.nel * b) / G), e1 = (int)(((long long)a.nel * (b + 1)) / G);
-    for (int t = e0 + lane; t < e1; t += 32) {
+    for (int t = e0 + lane; t < e1; t += nthr) {
         const size_t n = a.nel;
         double s[6];
         if (staged) {
@@ -169,9 +170,11 @@ __device__ __forceinline__ void fault_row_epilogue(const PanelArgs& A, int row, 
     update_fault_row(A.mv.fe, row, dtau);
 }
 
+template <int kPnP>
 __global__ void __launch_bounds__(kPnThreads, 1)
 matvec_panel_kernel(const __grid_constant__ PanelArgs A)
 {
+    using Panel = oq::Panel<kPnP>;
     extern __shared__ __align__(128) double smem[];
     __shared__ __align__(8) uint64_t full_bar[kPnStages];
     __shared__ __align__(8) uint64_t empty_bar[kPnStages];
@@ -180,7 +183,7 @@ matvec_panel_kernel(const __grid_constant__ PanelArgs A)
     __shared__ __align__(8) uint64_t red_full[2];
     __shared__ __align__(8) uint64_t red_empty[2];
     __shared__ __align__(8) uint64_t ep_bar;
-    __shared__ double red[2][kPnCWarps][kPnP][kPnR];
+    __shared__ double red[2][kPnCWarps][kPnPMax][kPnR];
     __shared__ unsigned long long ep_s;
     __shared__ int done_s;
 
@@ -344,30 +347,6 @@ matvec_panel_kernel(const __grid_constant__ PanelArgs A)
         done = __shfl_sync(0xffffffffu, done, 0);
         ep = __shfl_sync(0xffffffffu, ep, 0);
         if (done) return;                             // integration already complete: identically on every rank
-        if (A.pro.enabled) {
-            prologue_slice(A.pro.fa, lane, ep);
-            __syncwarp();
-            if (lane == 0) {
-                const int world = A.pro.fa.peers.world;
-                unsigned long long* epochs = A.pro.fa.epochs;
-                if (world > 1) __threadfence_system(); else __threadfence();
-                const unsigned long long prev = atomicAdd(&epochs[kEpBlocksF], 1ull);
-                if (prev == (unsigned long long)gridDim.x - 1ull) {
-                    epochs[kEpBlocksF] = 0ull;
-                    if (world > 1) {
-                        __threadfence_system();       // acquire the other CTAs' slices before telling the peers
-                        for (int r = 0; r < world; ++r) {
-                            if (r == A.pro.fa.peers.rank) continue;
-                            unsigned long long* f =
-                                reinterpret_cast<unsigned long long*>(A.pro.fa.peers.base[r] + A.pro.fa.wl.off_flags);
-                            publish_flag(f + A.pro.fa.peers.rank, ep + 1ull);
-                        }
-                    }
-                    __threadfence();
-                    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(epochs + kEpForcing), "l"(ep + 1ull) : "memory");
-                }
-            }
-        }
         if (!has_work) return;
         int buf = 0;
         unsigned rphase[2] = {0u, 0u};
@@ -435,9 +414,37 @@ matvec_panel_kernel(const __grid_constant__ PanelArgs A)
     }
 
     // ---------------------------------------------------------------------- consumer warps
-    if (!has_work) return;
     mbar_wait(&ep_bar, 0);
     if (done_s) return;
+    if (A.pro.enabled) {
+        pdl_wait();                                   // the prologue reads the predecessor's state and slopes
+        // the forcing front end: idle until the first forcing piece arrives anyway, the 256 consumer threads form this
+        // CTA's slice, then one of them joins the grid-wide count (the last CTA publishes the epoch)
+        const unsigned long long ep = ep_s;
+        prologue_slice(A.pro.fa, tid, kPnConsumers, ep);
+        asm volatile("bar.sync 1, %0;" ::"n"(kPnConsumers) : "memory");
+        if (tid == 0) {
+            const int world = A.pro.fa.peers.world;
+            unsigned long long* epochs = A.pro.fa.epochs;
+            if (world > 1) __threadfence_system(); else __threadfence();
+            const unsigned long long prev = atomicAdd(&epochs[kEpBlocksF], 1ull);
+            if (prev == (unsigned long long)gridDim.x - 1ull) {
+                epochs[kEpBlocksF] = 0ull;
+                if (world > 1) {
+                    __threadfence_system();           // acquire the other CTAs' slices before telling the peers
+                    for (int r = 0; r < world; ++r) {
+                        if (r == A.pro.fa.peers.rank) continue;
+                        unsigned long long* f =
+                            reinterpret_cast<unsigned long long*>(A.pro.fa.peers.base[r] + A.pro.fa.wl.off_flags);
+                        publish_flag(f + A.pro.fa.peers.rank, ep + 1ull);
+                    }
+                }
+                __threadfence();
+                asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(epochs + kEpForcing), "l"(ep + 1ull) : "memory");
+            }
+        }
+    }
+    if (!has_work) return;
     double acc[kPnP][kPnR];
 #pragma unroll
     for (int s = 0; s < kPnP; ++s)

@@ -91,6 +91,7 @@ struct OqProblem {
     oq::DevBuf<double> hist[4], abm_coef;           // multistep integrator: f(t_{n-1..n-4}), per-step weights
     oq::DevBuf<double> errpart;                     // per-block partial sums of the error norm
     oq::DevBuf<double> ctl;                         // device-side controller record (StepCtl)
+    oq::DevBuf<double> snap_ring;                   // device-side snapshot ring of oq_solve (async_snapshots)
 
     cudaStream_t stream = nullptr;
     cudaGraphExec_t rhs_graph = nullptr;            // TWO resident RHS evaluations (u -> k1), captured once (the

@@ -531,9 +531,14 @@ int launch_panel(MatvecArgs& a, const ForcingArgs* pro, const ColOwners& own, in
         if (!pro) return 0;
         grid = 1;      // a rank without rows still takes part in the exchange (publishes an empty slice)
     }
+    // row blocks per panel (OQ_PANEL_P = 1, 2, 4 or 6; default 6)
+    static const int panel_p = [] { const char* e = getenv("OQ_PANEL_P"); const int v = e ? atoi(e) : 6;
+                                    return v == 1 || v == 2 || v == 4 ? v : 6; }();
+    void (*kern)(const PanelArgs) = panel_p == 1 ? matvec_panel_kernel<1> : panel_p == 2 ? matvec_panel_kernel<2>
+                                    : panel_p == 4 ? matvec_panel_kernel<4> : matvec_panel_kernel<6>;
     static bool attr_set = false;
     if (!attr_set) {
-        OQ_CUDA(cudaFuncSetAttribute(matvec_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPnSmemBytes));
+        OQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPnSmemBytes));
         attr_set = true;
     }
     a.pass = nullptr;
@@ -555,7 +560,7 @@ int launch_panel(MatvecArgs& a, const ForcingArgs* pro, const ColOwners& own, in
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    OQ_CUDA(cudaLaunchKernelEx(&cfg, matvec_panel_kernel, A));
+    OQ_CUDA(cudaLaunchKernelEx(&cfg, kern, A));
     OQ_LAUNCHED();
     return 0;
 }

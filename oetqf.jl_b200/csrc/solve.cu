@@ -44,6 +44,9 @@ struct StepCtl {
     long long naccept, nreject, nrhs;
     int accepted, done, retcode, fixed;
     int nhist;                       // accepted steps recorded in the history so far (saturates at 4)
+    int snap_slot;                   // ring slot the accept kernel copies this step's state into (-1: none)
+    long long snap_stride;           // device-side snapshot ring: every snap_stride-th accepted step (0: off)
+    long long nsnap;                 // snapshots written to the ring so far
 };
 static_assert(sizeof(StepCtl) <= 32 * sizeof(double), "ctl buffer too small");
 
@@ -145,10 +148,27 @@ struct CtlArgs {
     int nrhs_inc;                        // RHS evaluations this step spent
 };
 
-// one thread: error norm -> accept/reject -> next dt (OrdinaryDiffEq's PI controller)
+constexpr int kSnapSlots = 32;       // ring capacity: two batches of kMaxBatch = 16 steps
+
+__device__ void controller_body(CtlArgs& a);
+
+// one thread: error norm -> accept/reject -> next dt (OrdinaryDiffEq's PI controller), then the snapshot decision
 __global__ void controller_kernel(CtlArgs a)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    controller_body(a);
+    StepCtl& c = *a.ctl;
+    // device-side snapshot ring (the role of wsolve's FunctionCallingCallback, src/io.jl:51-58,128-130): every
+    // snap_stride-th accepted step, and the completing one, is copied into the ring by the accept kernel
+    c.snap_slot = -1;
+    if (c.snap_stride > 0 && c.accepted && (c.naccept % c.snap_stride == 0 || c.done)) {
+        c.snap_slot = (int)(c.nsnap % kSnapSlots);
+        c.nsnap += 1;
+    }
+}
+
+__device__ void controller_body(CtlArgs& a)
+{
     StepCtl& c = *a.ctl;
     if (c.done) { c.accepted = 0; return; }
     const unsigned long long ep = *(volatile unsigned long long*)(a.epochs + kEpReduce);
@@ -200,26 +220,44 @@ __global__ void controller_kernel(CtlArgs a)
 }
 
 // on acceptance: u <- unew, k1 <- k7 (first-same-as-last)
+// snapshot slot layout: u[n] | du[n] | t | accepted-step number
+__device__ __forceinline__ void snap_store(const StepCtl* ctl, double* ring, size_t n, size_t i, double ui, double dui)
+{
+    const int slot = ctl->snap_slot;
+    if (!ring || slot < 0) return;
+    double* s = ring + (size_t)slot * (2 * n + 2);
+    s[i] = ui;
+    s[n + i] = dui;
+    if (i == 0) { s[2 * n] = ctl->t; s[2 * n + 1] = (double)ctl->naccept; }
+}
+
 __global__ void __launch_bounds__(256)
 accept_kernel(const StepCtl* __restrict__ ctl, size_t n, const double* __restrict__ unew,
-              const double* __restrict__ k7, double* __restrict__ u, double* __restrict__ k1)
+              const double* __restrict__ k7, double* __restrict__ u, double* __restrict__ k1, double* ring)
 {
     if (!ctl->accepted) return;      // (the controller clears `accepted` for steps enqueued past completion)
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) { u[i] = unew[i]; k1[i] = k7[i]; }
+    if (i < n) {
+        const double a = unew[i], b = k7[i];
+        u[i] = a; k1[i] = b;
+        snap_store(ctl, ring, n, i, a, b);
+    }
 }
 
 // on acceptance, multistep bookkeeping included: u <- unew and the derivative history shifts by one step
 __global__ void __launch_bounds__(256)
 accept_hist_kernel(const StepCtl* __restrict__ ctl, size_t n, const double* __restrict__ unew,
                    const double* __restrict__ fnew, double* __restrict__ u, double* __restrict__ f0,
-                   double* __restrict__ h0, double* __restrict__ h1, double* __restrict__ h2, double* __restrict__ h3)
+                   double* __restrict__ h0, double* __restrict__ h1, double* __restrict__ h2, double* __restrict__ h3,
+                   double* ring)
 {
     if (!ctl->accepted) return;
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    u[i] = unew[i];
-    h3[i] = h2[i]; h2[i] = h1[i]; h1[i] = h0[i]; h0[i] = f0[i]; f0[i] = fnew[i];
+    const double a = unew[i], b = fnew[i];
+    u[i] = a;
+    h3[i] = h2[i]; h2[i] = h1[i]; h1[i] = h0[i]; h0[i] = f0[i]; f0[i] = b;
+    snap_store(ctl, ring, n, i, a, b);
 }
 
 // Weights of the variable-coefficient Adams formulas for the step [t_n, t_n + dt] on the grid of the last
@@ -293,9 +331,10 @@ static int launch_accept(OqProblem* p, bool with_history)
     const StepCtl* ctl = reinterpret_cast<const StepCtl*>(p->ctl.p);
     if (with_history)
         accept_hist_kernel<<<blocks, 256, 0, p->stream>>>(ctl, n, p->unew.p, p->k[6].p, p->u.p, p->k[0].p,
-                                                          p->hist[0].p, p->hist[1].p, p->hist[2].p, p->hist[3].p);
+                                                          p->hist[0].p, p->hist[1].p, p->hist[2].p, p->hist[3].p,
+                                                          p->snap_ring.p);
     else
-        accept_kernel<<<blocks, 256, 0, p->stream>>>(ctl, n, p->unew.p, p->k[6].p, p->u.p, p->k[0].p);
+        accept_kernel<<<blocks, 256, 0, p->stream>>>(ctl, n, p->unew.p, p->k[6].p, p->u.p, p->k[0].p, p->snap_ring.p);
     OQ_LAUNCHED();
     return 0;
 }
@@ -364,6 +403,28 @@ extern "C" int oq_solve(OqProblem* p, double t0, const OqSolveOptions* o, int64_
     if (h.dt > h.dtmax) h.dt = h.dtmax;
     if (t0 + h.dt > o->tstop) h.dt = o->tstop - t0;
     h.qold = 1e-4; h.reltol = o->reltol; h.abstol = o->abstol; h.fixed = o->fixed_dt;
+    // Snapshot delivery.  Synchronous (default): the host copies the state and calls fn between batches, and fn's
+    // return value stops the run at exactly that step.  Asynchronous (async_snapshots != 0, what wsolve uses): the
+    // device copies every stride-th accepted state into a ring in HBM, a second stream drains the ring into
+    // page-locked memory and fn runs on the host while the next batch of steps is already executing -- the
+    // integration never waits for the callback or the disk; a stop request takes effect within one batch.
+    const bool async = fn && o->async_snapshots != 0;
+    h.snap_slot = -1; h.snap_stride = async ? stride : 0; h.nsnap = 0;
+    const size_t slot_len = 2 * p->nstate + 2;
+    struct HostRing {
+        double* host = nullptr;
+        cudaStream_t copy = nullptr;
+        cudaEvent_t ev = nullptr;
+        ~HostRing() { if (host) cudaFreeHost(host); if (copy) cudaStreamDestroy(copy); if (ev) cudaEventDestroy(ev); }
+    } hr;
+    if (async) {
+        if (p->snap_ring.n != (size_t)kSnapSlots * slot_len) OQ_TRY(p->snap_ring.alloc((size_t)kSnapSlots * slot_len));
+        OQ_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&hr.host), (size_t)kSnapSlots * slot_len * sizeof(double), cudaHostAllocDefault));
+        OQ_CUDA(cudaStreamCreateWithFlags(&hr.copy, cudaStreamNonBlocking));
+        OQ_CUDA(cudaEventCreateWithFlags(&hr.ev, cudaEventDisableTiming));
+    } else {
+        p->snap_ring.release();          // the accept kernels test the pointer
+    }
     if (multistep) {
         for (int i = 0; i < 4; ++i)
             if (!p->hist[i].p) { OQ_TRY(p->hist[i].alloc(p->nstate + 2)); OQ_TRY(p->hist[i].zero()); }
@@ -419,12 +480,26 @@ extern "C" int oq_solve(OqProblem* p, double t0, const OqSolveOptions* o, int64_
     const int64_t maxiters = o->maxiters > 0 ? o->maxiters : 1000000;
     int64_t iters = 0;
     const int64_t kMaxBatch = 16;    // steps enqueued after completion exit at their first instruction (ctl.done)
+    // asynchronous delivery: snapshots [pend_lo, pend_hi) are on their way to (or already in) the pinned ring
+    long long pend_lo = 0, pend_hi = 0;
+    auto deliver_pending = [&]() -> int {
+        if (pend_hi == pend_lo) return 0;
+        if (cudaStreamSynchronize(hr.copy) != cudaSuccess) return -1;
+        int st = 0;
+        for (long long q = pend_lo; q < pend_hi && st == 0; ++q) {
+            const double* slot = hr.host + (size_t)(q % kSnapSlots) * slot_len;
+            for (int i = 0; i < p->nparts; ++i) { pu[i] = slot + p->part_off[i]; pdu[i] = slot + p->nstate + p->part_off[i]; }
+            st = fn(user, slot[2 * p->nstate], (int64_t)slot[2 * p->nstate + 1], pu.data(), pdu.data());
+        }
+        pend_lo = pend_hi;
+        return st;
+    };
     while (!stop && !h.done && iters < maxiters) {
         // Launch as many steps as can pass before the next snapshot is due (all decisions are taken on the
         // device; steps enqueued after completion are no-ops for the state), then read the control record once.
         // (the batch size must be a pure function of the control record: every rank of a multi-GPU run has to
         // enqueue exactly the same sequence of kernels, or the peers' epoch flags would never match)
-        int64_t batch = fn ? stride - (h.naccept % stride) : kMaxBatch;
+        int64_t batch = (fn && !async) ? stride - (h.naccept % stride) : kMaxBatch;
         if (batch > kMaxBatch) batch = kMaxBatch;
         if (batch > maxiters - iters) batch = maxiters - iters;
         // the Adams pair needs four accepted steps of history; until then Tsit5 steps, one at a time
@@ -438,7 +513,15 @@ extern "C" int oq_solve(OqProblem* p, double t0, const OqSolveOptions* o, int64_
         }
         if (ce != cudaSuccess) { rc = fail("cudaGraphLaunch: %s", cudaGetErrorString(ce)); break; }
         const int64_t acc_before = h.naccept;
+        const long long snap_before = h.nsnap;
         ce = cudaMemcpyAsync(&h, p->ctl.p, sizeof(h), cudaMemcpyDeviceToHost, p->stream);
+        if (async && ce == cudaSuccess) {
+            ce = cudaEventRecord(hr.ev, p->stream);
+            // the callbacks of the previous batch run on the host while this batch executes on the device
+            const int st = deliver_pending();
+            if (st < 0) { rc = fail("snapshot copy failed"); break; }
+            if (st > 0) stop = st;
+        }
         if (ce == cudaSuccess) ce = cudaStreamSynchronize(p->stream);
         if (ce != cudaSuccess) { rc = fail("step failed: %s", cudaGetErrorString(ce)); break; }
         iters += batch;
@@ -447,10 +530,27 @@ extern "C" int oq_solve(OqProblem* p, double t0, const OqSolveOptions* o, int64_
                       "OQ_PEER_TIMEOUT_S sets the limit)", h.t);
             break;
         }
-        if (h.naccept > acc_before && (h.naccept % stride == 0 || h.done)) {
+        if (async) {
+            // start draining what this batch wrote (the copy stream waits for the batch, not the other way round)
+            if (h.nsnap > snap_before) {
+                ce = cudaStreamWaitEvent(hr.copy, hr.ev, 0);
+                for (long long q = snap_before; q < h.nsnap && ce == cudaSuccess; ++q) {
+                    const size_t off = (size_t)(q % kSnapSlots) * slot_len;
+                    ce = cudaMemcpyAsync(hr.host + off, p->snap_ring.p + off, slot_len * sizeof(double),
+                                         cudaMemcpyDeviceToHost, hr.copy);
+                }
+                if (ce != cudaSuccess) { rc = fail("snapshot copy failed: %s", cudaGetErrorString(ce)); break; }
+                pend_lo = snap_before; pend_hi = h.nsnap;
+            }
+        } else if (h.naccept > acc_before && (h.naccept % stride == 0 || h.done)) {
             stop = snapshot(h.t, h.naccept);
             if (stop < 0) { rc = 1; break; }
         }
+    }
+    if (async && !rc) {
+        const int st = deliver_pending();
+        if (st < 0) rc = fail("snapshot copy failed");
+        else if (st > 0 && !stop) stop = st;
     }
     if (!rc && comm_check_error(p, "oq_solve")) rc = 1;
     if (stats) {

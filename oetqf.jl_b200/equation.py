@@ -273,19 +273,25 @@ class ODESolution:
 
 def solve(prob: ODEProblem, alg=Tsit5(), *, reltol=1e-3, abstol=1e-6, dt=0.0, dtmax=0.0, maxiters=int(1e5),
           stride: int = 1, save_everystep: bool = True, callback: Optional[Callable] = None,
-          adaptive: bool = True, local_u0: Optional[Sequence[np.ndarray]] = None) -> ODESolution:
+          adaptive: bool = True, local_u0: Optional[Sequence[np.ndarray]] = None,
+          async_snapshots: Optional[bool] = None) -> ODESolution:
     """Device-resident counterpart of OrdinaryDiffEq's `solve(prob, alg; reltol, abstol, dt, dtmax,
     maxiters)` for alg = Tsit5() or VCABM5() (defaults reltol=1e-3, abstol=1e-6 as in OrdinaryDiffEq).  `callback(u, t, step)` plays the
     role of wsolve's FunctionCallingCallback (src/io.jl:128-130): it fires at t0 and after every
-    `stride`-th accepted step.  `local_u0`: this rank's slices of the state for multi-GPU runs."""
+    `stride`-th accepted step.  `local_u0`: this rank's slices of the state for multi-GPU runs.
+    `async_snapshots`: deliver snapshots through the device-side ring of oq_solve (the integration does not wait for
+    the callback; a stop request takes effect within one batch of steps).  Default: on when nothing can ask for a
+    stop (no user callback), off otherwise."""
     code = _alg_code(alg)
     p = prob.p
     parts0 = list(local_u0) if local_u0 is not None else list(prob.u0.x)
     p.set_state(parts0)
     shapes = [np.shape(a) for a in parts0]
     sol = ODESolution()
+    if async_snapshots is None:
+        async_snapshots = callback is None
     opts = _lib.OqSolveOptions(float(reltol), float(abstol), float(dt), float(dtmax), float(prob.tspan[1]),
-                               int(maxiters), code, 0 if adaptive else 1)
+                               int(maxiters), code, 0 if adaptive else 1, 1 if async_snapshots else 0, 0)
     stats = _lib.OqSolveStats()
 
     def _snap(user, t, step, pu, pdu):

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol(oq):
     lib = oq._lib.load()
     for name in _header_symbols():
         assert hasattr(lib, name), f"{name} declared in include/oetqf_b200.h but not exported"
-    assert lib.oq_abi_version() == 1
+    assert lib.oq_abi_version() == 2
 
 
 def test_no_cpu_fallback(oq):

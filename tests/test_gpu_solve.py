@@ -275,10 +275,18 @@ def test_wsolve_store_append_stride(gpu, tmp_path):
     stride = 11
     oq.wsolve(prob, oq.Tsit5(), f, 50, oq.io.VThetaDelta, names, "t", stride=stride, force=True, **kw)
     tt = oq.io.read(f, "t")
-    want = [sol.t[i] for i in range(0, len(sol.t), stride)]
-    if (len(sol.t) - 1) % stride != 0:
-        want.append(sol.t[-1])
-    assert np.array_equal(tt, np.array(want))
+    want = [sol.t[i] for i in range(0, len(sol.t), stride)]     # every stride-th callback only (io.jl:51-58): the
+    assert np.array_equal(tt, np.array(want))                   # end state is saved only if it is stride-aligned
+    # the store is append-only: one chunk file per flush and dataset, nothing rewritten (io.jl:22-82)
+    import json
+    import os
+    meta = json.load(open(os.path.join(f, "meta.json")))
+    assert meta["nt"] == len(want) and meta["chunks"] == list(range(0, len(want), 50))
+    oq.wsolve(prob, oq.Tsit5(), f, 7, oq.io.VThetaDelta, names, "t", force=True, **kw)
+    meta = json.load(open(os.path.join(f, "meta.json")))
+    assert meta["chunks"] == list(range(0, len(sol.t), 7))
+    assert sorted(x for x in os.listdir(f) if x.startswith("u1.")) == [f"u1.{c:09d}.npy" for c in meta["chunks"]]
+    assert np.array_equal(oq.io.read(f, "t"), np.array(sol.t))
 
 
 def test_max_real_eigval(gpu):

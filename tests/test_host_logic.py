@@ -128,7 +128,7 @@ def test_solve_option_struct_matches_header():
     import ctypes as C
     from oetqf_b200 import _lib
     assert [f[0] for f in _lib.OqSolveOptions._fields_] == ["reltol", "abstol", "dt0", "dtmax", "tstop", "maxiters",
-                                                           "algorithm", "fixed_dt"]
-    assert C.sizeof(_lib.OqSolveOptions) == 5 * 8 + 8 + 4 + 4
+                                                           "algorithm", "fixed_dt", "async_snapshots", "reserved"]
+    assert C.sizeof(_lib.OqSolveOptions) == 5 * 8 + 8 + 4 * 4
     assert [f[0] for f in _lib.OqSolveStats._fields_] == ["t", "dt_last", "dt_next", "naccept", "nreject", "nrhs",
                                                          "retcode"]
