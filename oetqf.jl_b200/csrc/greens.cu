@@ -5,6 +5,8 @@
 // image loop (GF.jl:47,154), the quadrature loop (GF.jl:146,270) and the stress/traction projections
 // (GF.jl:76-96,163-169) are fused into the kernels.  All device matrices are row-major so that the
 // RHS matvec (rhs.cu) streams each row with coalesced 128-bit loads.
+#include <algorithm>
+
 #include "common.cuh"
 #include "greens_okada.cuh"
 #include "hex8_dev.cuh"
@@ -109,6 +111,158 @@ gf_mantle_mantle_kernel(Hex8Geom a, double mu, double nu, const double* __restri
                                  *dst = (w == 0) ? S[k] * wt : *dst + S[k] * wt;
                              }
                          });
+    }
+}
+
+// ---- K3'/K4': the hex8 kernels on TILES of source cells that share vertices -----------------------------------
+// A tile is up to kTileC source cells and the up to kTileV distinct mesh vertices they touch (a 4x4x4 block of a
+// conforming mesh: 64 cells, 125 vertices instead of 512 corners).  One CTA takes one tile and a run of receivers;
+// per receiver (and quadrature point) thread v evaluates the basis + combination at vertex v ONCE (hex8_vertex_kernels,
+// the transcendental-heavy part), the 36 strain kernels of every vertex go to shared memory, then thread c forms
+// the signed 8-vertex sum of cell c and applies the stress / traction epilogue.  Same closed form, same entries
+// (GF.jl:206-225, :262-290), ~4x fewer basis evaluations.
+constexpr int kTileC = 64;
+constexpr int kTileV = 128;       // == kHex8Threads: one vertex per thread
+static_assert(kTileV == kHex8Threads, "one vertex per thread");
+
+struct Hex8TileView {
+    const double *vx, *vy, *vz;          // [ntiles][kTileV]
+    const int* cell;                     // [ntiles][kTileC] global source cell, -1: unused slot
+    const unsigned char* corner;         // [ntiles][kTileC][8] local vertex of corner c1 + 2 c2 + 4 c3
+    const int* counts;                   // [ntiles][2]: cells, vertices
+    const double* nudge;                 // [ntiles]
+    int ntiles;
+};
+
+struct TileSmem {
+    double vx[kTileV], vy[kTileV], vz[kTileV];
+    int cell[kTileC];
+    unsigned char corner[kTileC][8];
+    int ncell, nvert;
+    double nudge;
+};
+
+__device__ __forceinline__ void tile_load(const Hex8TileView& T, int tile, TileSmem& ts)
+{
+    const int tid = threadIdx.x;
+    if (tid < kTileV) {
+        ts.vx[tid] = T.vx[(size_t)tile * kTileV + tid];
+        ts.vy[tid] = T.vy[(size_t)tile * kTileV + tid];
+        ts.vz[tid] = T.vz[(size_t)tile * kTileV + tid];
+    }
+    if (tid < kTileC) {
+        ts.cell[tid] = T.cell[(size_t)tile * kTileC + tid];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) ts.corner[tid][k] = T.corner[((size_t)tile * kTileC + tid) * 8 + k];
+    }
+    if (tid == 0) { ts.ncell = T.counts[2 * tile]; ts.nvert = T.counts[2 * tile + 1]; ts.nudge = T.nudge[tile]; }
+    __syncthreads();
+}
+
+// signed sum over the eight vertices of a cell of the per-vertex strain kernels in shared memory
+template <int NEED>
+__device__ __forceinline__ void tile_cell_kernels(const double* qv, const unsigned char (&cn)[8], double (&Q)[36])
+{
+#pragma unroll
+    for (int m = 0; m < 36; ++m) {
+        if (!((NEED >> (m / 6)) & 1)) { Q[m] = 0.0; continue; }
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const double v = qv[m * kHex8Threads + cn[k]];
+            s += (((k & 1) + ((k >> 1) & 1) + (k >> 2)) & 1) ? v : -v;       // s1 s2 s3, s = -1 at the lower limit
+        }
+        Q[m] = s;
+    }
+}
+
+template <int SLIP>
+__global__ void __launch_bounds__(kHex8Threads, OQ_HEX8_MINB)
+gf_mantle_fault_tile_kernel(Hex8TileView T, Hex8Geom a, FaultGeom f, double mu, double nu, int slip, double s1, double c1,
+                            double s2, double c2, int r0, int nrows, int rows_per_cta, size_t ld, double* __restrict__ G)
+{
+    extern __shared__ double hex8_acc[];
+    __shared__ TileSmem ts;
+    tile_load(T, blockIdx.x, ts);
+    constexpr int kNeed = SLIP == kStrikeSlip ? 0x06 : 0x38;     // GF.jl:89-96: xy,xz or yy,yz,zz strain rows
+    const int tid = threadIdx.x;
+    const double lam = 2.0 * mu * nu / (1.0 - 2.0 * nu);
+    const double alpha = (lam + mu) / (lam + 2.0 * mu);
+    const size_t ne = a.n;
+    const int fl0 = blockIdx.y * rows_per_cta, fl1 = min(nrows, fl0 + rows_per_cta);
+    for (int fl = fl0; fl < fl1; ++fl) {
+        const int fc = r0 + fl;
+        const int q1 = fc % f.nx, q2 = fc / f.nx;
+        const double x = f.x[q1], y = f.y[q2], z = f.z[q2];
+        if (tid < ts.nvert) {
+            double Q[36];
+            hex8_vertex_kernels<kNeed>(x, y, z, ts.vx[tid], ts.vy[tid], ts.vz[tid], ts.nudge, alpha, hex8_acc + tid, Q);
+#pragma unroll
+            for (int m = 0; m < 36; ++m)
+                if ((kNeed >> (m / 6)) & 1) hex8_acc[m * kHex8Threads + tid] = Q[m];
+        }
+        __syncthreads();
+        if (tid < ts.ncell) {
+            const int e = ts.cell[tid];
+            double Q[36];
+            tile_cell_kernels<kNeed>(hex8_acc, ts.corner[tid], Q);
+            const double qx = a.qx[e], qy = a.qy[e], qz = a.qz[e], dx = a.dx[e], dy = a.dy[e], dz = a.dz[e];
+            const bool inside = x > qx - 0.5 * dx && x < qx + 0.5 * dx && y > qy && y < qy + dy && z > qz - dz && z < qz;
+            double* row = G + (size_t)fl * ld + e;
+            hex8_stress_from_kernels(Q, inside, mu, nu, [&](int pc, const double (&S)[6]) {
+                row[(size_t)pc * ne] = shear_traction_stress(slip, S, s1, c1, s2, c2);
+            });
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(kHex8Threads, OQ_HEX8_MINB)
+gf_mantle_mantle_tile_kernel(Hex8TileView T, Hex8Geom a, double mu, double nu, const double* __restrict__ qc,
+                             const double* __restrict__ qw, int nq, int e_begin, int nel, int rows_per_cta, size_t ld,
+                             double* __restrict__ G)
+{
+    extern __shared__ double hex8_acc[];
+    __shared__ TileSmem ts;
+    tile_load(T, blockIdx.x, ts);
+    const int tid = threadIdx.x;
+    const double lam = 2.0 * mu * nu / (1.0 - 2.0 * nu);
+    const double alpha = (lam + mu) / (lam + 2.0 * mu);
+    const size_t ne = a.n;
+    const int jl0 = blockIdx.y * rows_per_cta, jl1 = min(nel, jl0 + rows_per_cta);
+    for (int jl = jl0; jl < jl1; ++jl) {
+        const int j = e_begin + jl;
+        const double cx = a.cx[j], cy = a.cy[j], cz = a.cz[j];
+        const double hx = a.dx[j] / 2, hy = a.dy[j] / 2, hz = a.dz[j] / 2;
+        for (int w = 0; w < nq; ++w) {
+            const double rx = cx + qc[3 * w] * hx;
+            const double ry = cy + qc[3 * w + 1] * hy;
+            const double rz = cz + qc[3 * w + 2] * hz;
+            const double wt = qw[w];
+            if (tid < ts.nvert) {
+                double Q[36];
+                hex8_vertex_kernels<0x3f>(rx, ry, rz, ts.vx[tid], ts.vy[tid], ts.vz[tid], ts.nudge, alpha, hex8_acc + tid, Q);
+#pragma unroll
+                for (int m = 0; m < 36; ++m) hex8_acc[m * kHex8Threads + tid] = Q[m];
+            }
+            __syncthreads();
+            if (tid < ts.ncell) {
+                const int i = ts.cell[tid];
+                double Q[36];
+                tile_cell_kernels<0x3f>(hex8_acc, ts.corner[tid], Q);
+                const double qx = a.qx[i], qy = a.qy[i], qz = a.qz[i], ex = a.dx[i], ey = a.dy[i], ez = a.dz[i];
+                const bool inside = rx > qx - 0.5 * ex && rx < qx + 0.5 * ex && ry > qy && ry < qy + ey && rz > qz - ez && rz < qz;
+                // the thread owns its 36 entries: the first quadrature point stores, later ones accumulate in place
+                hex8_stress_from_kernels(Q, inside, mu, nu, [&](int pc, const double (&S)[6]) {
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) {
+                        double* dst = G + ((size_t)k * nel + jl) * ld + (size_t)pc * ne + i;
+                        *dst = (w == 0) ? S[k] * wt : *dst + S[k] * wt;
+                    }
+                });
+            }
+            __syncthreads();
+        }
     }
 }
 
@@ -242,6 +396,142 @@ struct DevQuad {
         return w.upload(q->weights, nq);
     }
 };
+
+// Cuts a hex8 source mesh into tiles of cells that share vertices (host side of K3'/K4').  Corner coordinates are
+// formed exactly as the pair kernels form them (x0 = qx - dx/2, x0 + dx; qy, qy + dy; qz - dz, qz); coordinates of
+// neighbouring cells that agree to 1e-12 of the mesh extent are one vertex plane (conforming meshes built from
+// centroids and sizes differ by an ulp or two); anything less regular simply shares fewer vertices.
+struct DevHex8Tiles {
+    DevBuf<double> vx, vy, vz, nudge;
+    DevBuf<int> cell, counts;
+    DevBuf<unsigned char> corner;
+    Hex8TileView v{};
+    double corners_per_vertex = 0.0;     // 8 * cells / vertices over all tiles (sharing factor, for the record)
+
+    static void planes(const std::vector<double>& vals, std::vector<double>& uniq, std::vector<int>& index)
+    {
+        const size_t n = vals.size();
+        std::vector<size_t> ord(n);
+        for (size_t i = 0; i < n; ++i) ord[i] = i;
+        std::sort(ord.begin(), ord.end(), [&](size_t a, size_t b) { return vals[a] < vals[b]; });
+        const double span = n ? vals[ord[n - 1]] - vals[ord[0]] : 0.0;
+        const double tol = 1e-12 * (span > 0 ? span : 1.0);
+        index.assign(n, 0);
+        uniq.clear();
+        for (size_t k = 0; k < n; ++k) {
+            const double v = vals[ord[k]];
+            if (uniq.empty() || v - uniq.back() > tol) uniq.push_back(v);
+            index[ord[k]] = (int)uniq.size() - 1;
+        }
+    }
+
+    int build(const OqHex8Mesh* ma)
+    {
+        const int n = ma->n;
+        std::vector<double> xs(2 * (size_t)n), ys(2 * (size_t)n), zs(2 * (size_t)n);
+        for (int i = 0; i < n; ++i) {
+            const double x0 = ma->qx[i] - 0.5 * ma->dx[i];
+            xs[2 * i] = x0; xs[2 * i + 1] = x0 + ma->dx[i];
+            ys[2 * i] = ma->qy[i]; ys[2 * i + 1] = ma->qy[i] + ma->dy[i];
+            zs[2 * i] = ma->qz[i] - ma->dz[i]; zs[2 * i + 1] = ma->qz[i];
+        }
+        std::vector<double> ux, uy, uz;
+        std::vector<int> ix, iy, iz;
+        planes(xs, ux, ix); planes(ys, uy, iy); planes(zs, uz, iz);
+        // group cells by 4x4x4 blocks of plane indices
+        struct Key { int kx, ky, kz, cell; };
+        std::vector<Key> keys(n);
+        for (int i = 0; i < n; ++i) keys[i] = {ix[2 * i] / 4, iy[2 * i] / 4, iz[2 * i] / 4, i};
+        std::sort(keys.begin(), keys.end(), [](const Key& a, const Key& b) {
+            if (a.kz != b.kz) return a.kz < b.kz;
+            if (a.ky != b.ky) return a.ky < b.ky;
+            if (a.kx != b.kx) return a.kx < b.kx;
+            return a.cell < b.cell;
+        });
+        std::vector<double> hvx, hvy, hvz, hnudge;
+        std::vector<int> hcell, hcounts;
+        std::vector<unsigned char> hcorner;
+        size_t total_vertices = 0;
+        auto flush = [&](const std::vector<int>& cells) {
+            // one tile; vertices in order of first use
+            std::vector<long long> vkey;
+            std::vector<int> vids;
+            const size_t t = hcounts.size() / 2;
+            hvx.resize((t + 1) * kTileV, 0.0); hvy.resize((t + 1) * kTileV, 0.0); hvz.resize((t + 1) * kTileV, 0.0);
+            hcell.resize((t + 1) * kTileC, -1); hcorner.resize((t + 1) * kTileC * 8, 0);
+            double nudge = 1e300;
+            int nv = 0;
+            for (size_t c = 0; c < cells.size(); ++c) {
+                const int i = cells[c];
+                hcell[t * kTileC + c] = i;
+                nudge = std::min(nudge, 1e-6 * std::min(ma->dx[i], std::min(ma->dy[i], ma->dz[i])));
+                for (int k = 0; k < 8; ++k) {
+                    const int jx = ix[2 * i + (k & 1)], jy = iy[2 * i + ((k >> 1) & 1)], jz = iz[2 * i + (k >> 2)];
+                    const long long key = ((long long)jz * (long long)uy.size() + jy) * (long long)ux.size() + jx;
+                    int found = -1;
+                    for (int q = 0; q < nv; ++q) if (vkey[q] == key) { found = q; break; }
+                    if (found < 0) {
+                        found = nv++;
+                        vkey.push_back(key);
+                        hvx[t * kTileV + found] = ux[jx]; hvy[t * kTileV + found] = uy[jy]; hvz[t * kTileV + found] = uz[jz];
+                    }
+                    hcorner[(t * kTileC + c) * 8 + k] = (unsigned char)found;
+                }
+            }
+            hcounts.push_back((int)cells.size()); hcounts.push_back(nv);
+            hnudge.push_back(nudge);
+            total_vertices += nv;
+        };
+        auto vkey_of = [&](int i, int k) {
+            return ((long long)iz[2 * i + (k >> 2)] * (long long)uy.size() + iy[2 * i + ((k >> 1) & 1)]) * (long long)ux.size() +
+                   ix[2 * i + (k & 1)];
+        };
+        // cells of one 4x4x4 block form a tile; a block of an irregular mesh may hold more cells / vertices than a
+        // tile takes: cut it greedily (vertex set kept incrementally)
+        std::vector<int> part;
+        std::vector<long long> pkeys;
+        for (int k = 0; k <= n; ++k) {
+            const bool brk = k == n || (k > 0 && (keys[k].kx != keys[k - 1].kx || keys[k].ky != keys[k - 1].ky ||
+                                                  keys[k].kz != keys[k - 1].kz));
+            if (brk && !part.empty()) { flush(part); part.clear(); pkeys.clear(); }
+            if (k == n) break;
+            const int c = keys[k].cell;
+            int fresh = 0;
+            long long add[8];
+            for (int q = 0; q < 8; ++q) {
+                const long long key = vkey_of(c, q);
+                if (std::find(pkeys.begin(), pkeys.end(), key) == pkeys.end() && std::find(add, add + fresh, key) == add + fresh)
+                    add[fresh++] = key;
+            }
+            if ((int)part.size() + 1 > kTileC || (int)pkeys.size() + fresh > kTileV) {
+                flush(part); part.clear(); pkeys.clear();
+                fresh = 0;
+                for (int q = 0; q < 8; ++q) {
+                    const long long key = vkey_of(c, q);
+                    if (std::find(add, add + fresh, key) == add + fresh) add[fresh++] = key;
+                }
+            }
+            part.push_back(c);
+            pkeys.insert(pkeys.end(), add, add + fresh);
+        }
+        const int ntiles = (int)(hcounts.size() / 2);
+        corners_per_vertex = total_vertices ? 8.0 * n / (double)total_vertices : 0.0;
+        OQ_TRY(vx.upload(hvx.data(), hvx.size())); OQ_TRY(vy.upload(hvy.data(), hvy.size())); OQ_TRY(vz.upload(hvz.data(), hvz.size()));
+        OQ_TRY(nudge.upload(hnudge.data(), hnudge.size()));
+        OQ_TRY(cell.upload(hcell.data(), hcell.size())); OQ_TRY(counts.upload(hcounts.data(), hcounts.size()));
+        OQ_TRY(corner.upload(hcorner.data(), hcorner.size()));
+        v.vx = vx.p; v.vy = vy.p; v.vz = vz.p; v.cell = cell.p; v.corner = corner.p; v.counts = counts.p; v.nudge = nudge.p;
+        v.ntiles = ntiles;
+        return 0;
+    }
+};
+
+// hex8 kernels: tiles with shared vertices by default; OQ_HEX8=pair selects the one-thread-per-pair kernels
+static bool hex8_tiles_enabled()
+{
+    static const bool on = [] { const char* e = getenv("OQ_HEX8"); return !(e && strcmp(e, "pair") == 0); }();
+    return on;
+}
 
 static int make_okada_params(const OqFaultMesh* mf, double lam, double mu, int ftype, int nrept,
                              double buffer_ratio, OkadaParams* p)
@@ -452,6 +742,9 @@ static int hex8_smem_optin()
         OQ_CUDA(cudaFuncSetAttribute(gf_mantle_fault_kernel<kDipSlip>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHex8SmemBytes));
         OQ_CUDA(cudaFuncSetAttribute(gf_mantle_mantle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHex8SmemBytes));
         OQ_CUDA(cudaFuncSetAttribute(hex8_stress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHex8SmemBytes));
+        OQ_CUDA(cudaFuncSetAttribute(gf_mantle_fault_tile_kernel<kStrikeSlip>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHex8SmemBytes));
+        OQ_CUDA(cudaFuncSetAttribute(gf_mantle_fault_tile_kernel<kDipSlip>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHex8SmemBytes));
+        OQ_CUDA(cudaFuncSetAttribute(gf_mantle_mantle_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHex8SmemBytes));
         done = true;
     }
     return 0;
@@ -479,9 +772,25 @@ static int build_mantle_fault(const OqHex8Mesh* ma, const OqFaultMesh* mf, doubl
     if (alloc_matrix(M, OQ_ROWS_FAULT, row_begin, row_end, nf, 6 * ma->n) || M->d.zero()) { delete M; return 1; }
     if (M->local_rows > 0) {
         const size_t total = (size_t)ma->n * M->local_rows;
+        DevHex8Tiles tiles;
+        const bool tiled = hex8_tiles_enabled();
+        if (tiled && tiles.build(ma)) { delete M; return 1; }
         EventTimer tm;
         int rc = tm.start();
-        if (!rc) {
+        if (!rc && tiled) {
+            // receivers per CTA: enough CTAs to fill the GPU several times over, tile data reused across the run
+            int rpc = 16;
+            while (rpc > 1 && (long long)tiles.v.ntiles * ((M->local_rows + rpc - 1) / rpc) < 148LL * 2 * 8) rpc >>= 1;
+            dim3 grid((unsigned)tiles.v.ntiles, (unsigned)((M->local_rows + rpc - 1) / rpc));
+            if (ftype == OQ_STRIKE_SLIP)
+                gf_mantle_fault_tile_kernel<kStrikeSlip><<<grid, kHex8Threads, kHex8SmemBytes>>>(
+                    tiles.v, dma.g, dmf.g, mu, nu, ftype, s1, c1, s2, c2, row_begin, M->local_rows, rpc, M->ld, M->d.p);
+            else
+                gf_mantle_fault_tile_kernel<kDipSlip><<<grid, kHex8Threads, kHex8SmemBytes>>>(
+                    tiles.v, dma.g, dmf.g, mu, nu, ftype, s1, c1, s2, c2, row_begin, M->local_rows, rpc, M->ld, M->d.p);
+            g_launches.fetch_add(1);
+            rc = tm.stop(&M->kernel_ms);
+        } else if (!rc) {
             const unsigned nb = (unsigned)((total + kHex8Threads - 1) / kHex8Threads);
             if (ftype == OQ_STRIKE_SLIP)
                 gf_mantle_fault_kernel<kStrikeSlip><<<nb, kHex8Threads, kHex8SmemBytes>>>(
@@ -534,9 +843,20 @@ static int build_mantle_mantle(const OqHex8Mesh* ma, const OqQuadrature* quad, d
     if (alloc_matrix(M, OQ_ROWS_MANTLE, e_begin, e_end, 6 * ma->n, 6 * ma->n) || M->d.zero()) { delete M; return 1; }
     if (nel > 0) {
         const size_t total = (size_t)ma->n * nel;
+        DevHex8Tiles tiles;
+        const bool tiled = hex8_tiles_enabled();
+        if (tiled && tiles.build(ma)) { delete M; return 1; }
         EventTimer tm;
         int rc = tm.start();
-        if (!rc) {
+        if (!rc && tiled) {
+            int rpc = 16;
+            while (rpc > 1 && (long long)tiles.v.ntiles * ((nel + rpc - 1) / rpc) < 148LL * 2 * 8) rpc >>= 1;
+            dim3 grid((unsigned)tiles.v.ntiles, (unsigned)((nel + rpc - 1) / rpc));
+            gf_mantle_mantle_tile_kernel<<<grid, kHex8Threads, kHex8SmemBytes>>>(tiles.v, dma.g, mu, nu, dq.c.p, dq.w.p, dq.nq,
+                                                                                 e_begin, nel, rpc, M->ld, M->d.p);
+            g_launches.fetch_add(1);
+            rc = tm.stop(&M->kernel_ms);
+        } else if (!rc) {
             gf_mantle_mantle_kernel<<<(unsigned)((total + kHex8Threads - 1) / kHex8Threads), kHex8Threads, kHex8SmemBytes>>>(dma.g, mu, nu, dq.c.p, dq.w.p, dq.nq,
                                                                               e_begin, nel, M->ld, M->d.p);
             g_launches.fetch_add(1);

@@ -150,6 +150,64 @@ __device__ __forceinline__ void hex8_strain_kernels(double x, double y, double z
 #undef ACCI
 }
 
+// ---- vertex form --------------------------------------------------------------------------------------------
+// The strain kernels are LINEAR in the corner sums, so the 36 x 91 combination can be applied to the basis values of
+// ONE corner: Qv[36] of a mesh VERTEX (sign +1).  A cell's kernels are then the signed sum of the Qv of its eight
+// vertices -- and conforming cells share every vertex up to eight ways, so a tile of cells needs one basis
+// evaluation per (receiver, vertex) instead of one per (receiver, cell, corner): ~4x fewer for a 4x4x4 tile
+// (125 vertices for 64 cells = 512 corners).  `acc` as in hex8_strain_kernels.
+template <int NEED>
+__device__ __forceinline__ void hex8_vertex_kernels(double x, double y, double z, double vx, double vy, double vz,
+                                                    double nudge, double al, double* acc, double (&Q)[36])
+{
+#pragma unroll 1
+    for (int b = 0; b < kHex8Acc; ++b) acc[b * kHex8Threads] = 0.0;
+    Hex8Corner c;
+    {
+        double r1 = x - vx, r2 = y - vy, r3 = z - vz;                 // real source
+        hex8_regularise(r1, r2, r3, nudge);
+        hex8_corner_inputs(r1, r2, r3, c);
+        hex8_basis_real<NEED>(r1, r2, r3, c, 1.0, acc);
+    }
+    {
+        double r1 = x - vx, r2 = y - vy, r3 = -z - vz;                // image source
+        hex8_regularise(r1, r2, r3, nudge);
+        hex8_corner_inputs(r1, r2, r3, c);
+        hex8_basis_image<NEED>(r1, r2, r3, c, atan(r1 / r2), atan(r2 / r1), 1.0, acc + HEX8_NB_REAL * kHex8Threads);
+    }
+    const double x3 = z, ial = 1.0 / al;
+#define ACCR(b) acc[(b) * kHex8Threads]
+#define ACCI(b) acc[(HEX8_NB_REAL + (b)) * kHex8Threads]
+    HEX8_COMBINE_BODY
+#undef ACCR
+#undef ACCI
+}
+
+// out(p, S) for the six unit eigenstrains from the strain kernels Q of one (receiver, cuboid) pair; `inside`: the
+// receiver lies strictly inside the cuboid (the eigenstrain itself is subtracted there)
+template <class Out>
+__device__ __forceinline__ void hex8_stress_from_kernels(const double (&Q)[36], bool inside, double mu, double nu, Out&& out)
+{
+    const double lam = 2.0 * mu * nu / (1.0 - 2.0 * nu);
+    const double pref = 1.0 / (8.0 * 3.14159265358979323846 * mu);
+#pragma unroll
+    for (int p = 0; p < 6; ++p) {
+        const bool diag = (p == 0 || p == 3 || p == 5);
+        double e[6];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+            double s = 2.0 * mu * Q[6 * a + p];
+            if (diag) s += lam * (Q[6 * a + 0] + Q[6 * a + 3] + Q[6 * a + 5]);
+            e[a] = pref * s;
+        }
+        if (inside) e[p] -= 1.0;
+        const double ekk = e[0] + e[3] + e[5];
+        const double S[6] = {lam * ekk + 2.0 * mu * e[0], 2.0 * mu * e[1], 2.0 * mu * e[2],
+                             lam * ekk + 2.0 * mu * e[3], 2.0 * mu * e[4], lam * ekk + 2.0 * mu * e[5]};
+        out(p, S);
+    }
+}
+
 // Calls out(p, S) with S[k] = stress component k (xx,xy,xz,yy,yz,zz) at (x,y,z) for unit eigenstrain component
 // p = 0..5 of the cuboid x∈[qx-dx/2,qx+dx/2], y∈[qy,qy+dy], z∈[qz-dz,qz]  (mesh.jl:181-183, GF.jl:218).
 // The six stresses of one p are handed over as soon as they exist, so callers never hold all 36.  With NEED a

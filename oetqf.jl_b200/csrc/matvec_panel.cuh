@@ -47,7 +47,21 @@ struct PanelArgs {
     int reverse;           // walk the row blocks of a span backwards (alternates between evaluations)
     int cstart[2];         // first column chunk of a panel per row set: the chunk holding this rank's own columns
     int ne;                // mantle elements (column p*ne + e of the strain-rate operand belongs to element e)
+    unsigned long long* timeline;   // debug (OQ_TIMELINE=file): [gridDim.x][32] globaltimer stamps, null: off
 };
+
+// debug timeline slots
+enum : int { kTlStart = 0, kTlProdPre = 1, kTlProdWait = 2, kTlProdEp = 3, kTlPeer0 = 4 /* +rank, 16 */, kTlFirstX = 20,
+             kTlProdEnd = 21, kTlProlBegin = 22, kTlProlStores = 23, kTlProlArrive = 24, kTlConsFirst = 25, kTlConsEnd = 26,
+             kTlEpiEnd = 27, kTlPublished = 28 };
+__device__ __forceinline__ void tl_stamp(const PanelArgs& A, int slot)
+{
+    if (A.timeline) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        A.timeline[(size_t)blockIdx.x * 32 + slot] = t;
+    }
+}
 
 // segments [k0, k0 + ns) of a span (row-block parts in processing order) that form one panel
 template <int kPnP>
@@ -210,6 +224,7 @@ matvec_panel_kernel(const __grid_constant__ PanelArgs A)
         fence_mbar_init();
     }
     __syncthreads();
+    if (tid == 0) tl_stamp(A, kTlStart);
     // the next evaluation's CTAs may be scheduled as soon as this grid's CTAs leave their SMs
     pdl_launch_dependents();
 
@@ -256,8 +271,11 @@ matvec_panel_kernel(const __grid_constant__ PanelArgs A)
             }
         }
         // 2. everything else reads what the predecessor kernel (and this grid's prologue) produced
+        tl_stamp(A, kTlProdPre);
         pdl_wait();
+        tl_stamp(A, kTlProdWait);
         mbar_wait(&ep_bar, 0);                        // the epilogue warp has read the epoch / the done flag
+        tl_stamp(A, kTlProdEp);
         if (done_s || !has_work) {
             for (int s = 0; s < npre; ++s) mbar_wait(&full_bar[s], 0);   // never leave with bulk copies in flight
             return;
@@ -275,6 +293,7 @@ matvec_panel_kernel(const __grid_constant__ PanelArgs A)
                 fence_proxy_async();                  // peer stores -> async-proxy (TMA) reads
             }
             confirmed |= 1u << r;
+            tl_stamp(A, kTlPeer0 + (r & 15));
         };
         auto need_columns = [&](int x_is_strain, int c0, int ncol) {
             if (confirmed == 0xffffffffu) return;
@@ -312,6 +331,7 @@ matvec_panel_kernel(const __grid_constant__ PanelArgs A)
                 mbar_arrive_expect_tx(&xfull[xs], xbytes);
                 tma_load_1d_hint(xbuf + (size_t)xs * kPnCH, op.x + par * op.x_stride + c0, xbytes, &xfull[xs],
                                  args.keep_chunks < 0 ? kL2EvictNormal : kL2EvictLast);
+                if (xcount == 0) tl_stamp(A, kTlFirstX);
                 ++xcount;
 #pragma unroll
                 for (int s = 0; s < kPnP; ++s) {
@@ -327,6 +347,7 @@ matvec_panel_kernel(const __grid_constant__ PanelArgs A)
             }
             k = kn;
         }
+        tl_stamp(A, kTlProdEnd);
         return;
     }
 
@@ -410,6 +431,7 @@ matvec_panel_kernel(const __grid_constant__ PanelArgs A)
             }
             k = kn;
         }
+        if (lane == 0) tl_stamp(A, kTlEpiEnd);
         return;
     }
 
@@ -421,13 +443,16 @@ matvec_panel_kernel(const __grid_constant__ PanelArgs A)
         // the forcing front end: idle until the first forcing piece arrives anyway, the 256 consumer threads form this
         // CTA's slice, then one of them joins the grid-wide count (the last CTA publishes the epoch)
         const unsigned long long ep = ep_s;
+        if (tid == 0) tl_stamp(A, kTlProlBegin);
         prologue_slice(A.pro.fa, tid, kPnConsumers, ep);
         asm volatile("bar.sync 1, %0;" ::"n"(kPnConsumers) : "memory");
         if (tid == 0) {
+            tl_stamp(A, kTlProlStores);
             const int world = A.pro.fa.peers.world;
             unsigned long long* epochs = A.pro.fa.epochs;
             if (world > 1) __threadfence_system(); else __threadfence();
             const unsigned long long prev = atomicAdd(&epochs[kEpBlocksF], 1ull);
+            tl_stamp(A, kTlProlArrive);
             if (prev == (unsigned long long)gridDim.x - 1ull) {
                 epochs[kEpBlocksF] = 0ull;
                 if (world > 1) {
@@ -441,6 +466,7 @@ matvec_panel_kernel(const __grid_constant__ PanelArgs A)
                 }
                 __threadfence();
                 asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(epochs + kEpForcing), "l"(ep + 1ull) : "memory");
+                tl_stamp(A, kTlPublished);
             }
         }
     }
@@ -465,6 +491,7 @@ matvec_panel_kernel(const __grid_constant__ PanelArgs A)
             panel_column(j, c, osel, c0, ncol);
             const int xs = xcount & 1;
             mbar_wait(&xfull[xs], (xcount >> 1) & 1u);
+            if (xcount == 0 && tid == 0) tl_stamp(A, kTlConsFirst);
             // this thread's two double2 of the forcing piece stay in registers for every row block of the panel
             const double2* x2 = reinterpret_cast<const double2*>(xbuf + (size_t)xs * kPnCH);
             const bool in0 = 2 * tid < ncol, in1 = 2 * (tid + kPnConsumers) < ncol;
@@ -527,6 +554,7 @@ matvec_panel_kernel(const __grid_constant__ PanelArgs A)
             for (int r = 0; r < kPnR; ++r) acc[s][r] = 0.0;
         k = kn;
     }
+    if (tid == 0) tl_stamp(A, kTlConsEnd);
 }
 
 }  // namespace oq

@@ -454,15 +454,19 @@ static int plan_stream(MatvecArgs& a, bool by_cols = false)
     return grid;
 }
 
-// 0: fused panel kernel (matvec_panel.cuh), 1: first streaming kernel (matvec_stream.cuh), 2: first LDG kernel
-static int matvec_variant()
+// 0: fused panel kernel (matvec_panel.cuh), 1: streaming kernel behind a forcing kernel (matvec_stream.cuh),
+// 2: first LDG kernel.  Default (OQ_MATVEC unset): the fused kernel on one GPU -- one launch per evaluation, fastest
+// end to end -- and the streaming pair on row shards: there the evaluation is 40-50 us long and the measured timeline
+// of the fused kernel (profiles/r02_panel_timeline_n8.md) shows its grid-wide publication (per-CTA system fence,
+// counter, second fence, flags: first multiply 14 us after the launch) costing more than the launch it saves.
+static int matvec_variant(int world = 1)
 {
-    static int v = -1;
-    if (v < 0) {
+    static int v = -2;
+    if (v == -2) {
         const char* e = getenv("OQ_MATVEC");
-        v = (e && strcmp(e, "ldg") == 0) ? 2 : (e && strcmp(e, "stream") == 0) ? 1 : 0;
+        v = !e ? -1 : strcmp(e, "ldg") == 0 ? 2 : strcmp(e, "stream") == 0 ? 1 : strcmp(e, "panel") == 0 ? 0 : -1;
     }
-    return v;
+    return v >= 0 ? v : (world > 1 ? 1 : 0);
 }
 
 // chunks per CTA span to keep L2-resident between evaluations: OQ_MATVEC_KEEP_MB megabytes over the grid
@@ -521,6 +525,20 @@ int plan_job(MatvecJob& job, int nrows)
     return nrb;
 }
 
+static unsigned long long* g_timeline = nullptr;
+
+static void dump_timeline(int rank)
+{
+    const char* f = getenv("OQ_TIMELINE");
+    if (!f || !g_timeline) return;
+    std::vector<unsigned long long> h(160 * 32);
+    cudaMemcpy(h.data(), g_timeline, h.size() * 8, cudaMemcpyDeviceToHost);
+    static int calls = 0;
+    char name[512];
+    snprintf(name, sizeof name, "%s.rank%d.call%d", f, rank, calls++);
+    if (FILE* fp = fopen(name, "wb")) { fwrite(h.data(), 8, h.size(), fp); fclose(fp); }
+}
+
 // the fused kernel: `pro` non-null folds the forcing front end into the launch
 int launch_panel(MatvecArgs& a, const ForcingArgs* pro, const ColOwners& own, int ne, int f0, unsigned seq,
                  cudaStream_t stream)
@@ -531,9 +549,10 @@ int launch_panel(MatvecArgs& a, const ForcingArgs* pro, const ColOwners& own, in
         if (!pro) return 0;
         grid = 1;      // a rank without rows still takes part in the exchange (publishes an empty slice)
     }
-    // row blocks per panel (OQ_PANEL_P = 1, 2, 4 or 6; default 6)
-    static const int panel_p = [] { const char* e = getenv("OQ_PANEL_P"); const int v = e ? atoi(e) : 6;
-                                    return v == 1 || v == 2 || v == 4 ? v : 6; }();
+    // row blocks per panel (OQ_PANEL_P = 1, 2, 4 or 6; default 2: measured fastest on one GPU, 3 193 vs 3 086-3 117
+    // evaluations/s of the 256x64 problem for 1, 4, 6)
+    static const int panel_p = [] { const char* e = getenv("OQ_PANEL_P"); const int v = e ? atoi(e) : 2;
+                                    return v == 1 || v == 4 || v == 6 ? v : 2; }();
     void (*kern)(const PanelArgs) = panel_p == 1 ? matvec_panel_kernel<1> : panel_p == 2 ? matvec_panel_kernel<2>
                                     : panel_p == 4 ? matvec_panel_kernel<4> : matvec_panel_kernel<6>;
     static bool attr_set = false;
@@ -549,6 +568,8 @@ int launch_panel(MatvecArgs& a, const ForcingArgs* pro, const ColOwners& own, in
     A.own = own;
     A.ne = ne > 0 ? ne : 1;
     A.reverse = pingpong_enabled() ? (int)(seq & 1u) : 0;
+    // debug timeline (OQ_TIMELINE=<file>): globaltimer stamps of the last launch, dumped by oq_rhs_resident
+    A.timeline = g_timeline;
     for (int jb = 0; jb < 2; ++jb) {
         const int n0 = a.job[jb].nch[0];
         A.cstart[jb] = n0 > 0 ? (f0 / kPnCH < n0 ? f0 / kPnCH : n0 - 1) : 0;
@@ -574,7 +595,7 @@ struct PanelLaunch {
 
 int launch_matvec(MatvecArgs& a, cudaStream_t stream, const PanelLaunch* pl = nullptr)
 {
-    if (matvec_variant() == 0) {
+    if (matvec_variant(pl ? pl->own.world : 1) == 0) {
         if (pl) return launch_panel(a, pl->pro, pl->own, pl->ne, pl->f0, pl->seq, stream);
         ColOwners own;
         own.world = 1; own.fb[1] = 0x7fffffff; own.eb[1] = 0x7fffffff;
@@ -675,7 +696,7 @@ static int rhs_views(OqProblem* p, const StateView& in, const StateView& out, co
     // dense fault-fault operand + panel kernel: the forcing front end runs inside the matvec launch (one launch per
     // evaluation); the FFT form needs the forcing vector before its transforms, the older kernels have no prologue
     static const bool split_forcing = [] { const char* e = getenv("OQ_FORCING"); return e && strcmp(e, "split") == 0; }();
-    const bool fused = matvec_variant() == 0 && p->gf11_form == OQ_GF11_DENSE && !split_forcing && p->nfl + fa.nel > 0;
+    const bool fused = matvec_variant(p->world) == 0 && p->gf11_form == OQ_GF11_DENSE && !split_forcing && p->nfl + fa.nel > 0;
     if (!direct_fft && !fused) {
     // small shards: ONE block (no cross-block handshake before the publication); large ones: 256-thread blocks
     if (nthr <= 4096) forcing_kernel<<<1, 1024, 0, st>>>(fa);
@@ -773,7 +794,10 @@ int gemv_scratch_sizes(const OqMatrix* A, size_t* npartial, size_t* ncounters)
     MatvecJob& j = a.job[0];
     j.op[0].G = A->d.p; j.op[0].ld = A->ld; j.op[0].cols = A->cols;
     const int nrb = plan_job(j, A->local_rows);
-    plan_stream(a, matvec_variant() == 0);
+    plan_stream(a, true);
+    const int slots_cols = j.slots;
+    plan_stream(a, false);
+    if (slots_cols > j.slots) j.slots = slots_cols;
     const int per_row = j.nsegTotal > j.slots ? j.nsegTotal : j.slots;
     *npartial = (size_t)A->local_rows * (per_row > 0 ? per_row : 1);
     *ncounters = nrb;
@@ -901,7 +925,12 @@ static int finish_problem(OqProblem* p, const OqFaultProperty* pf, const OqDilat
     jm.op[0] = p->opm[0]; jm.op[1] = p->opm[1];
     const int nrbf = plan_job(jf, nfl);
     const int nrbm = plan_job(jm, p->kind == kViscoelastic ? 6 * nel : 0);
-    plan_stream(plan, matvec_variant() == 0);
+    // (the kernel variant is chosen per launch -- the world size is not known yet: size the scratch for both plans)
+    plan_stream(plan, true);
+    const int sf = jf.slots, sm_ = jm.slots;
+    plan_stream(plan, false);
+    if (sf > jf.slots) jf.slots = sf;
+    if (sm_ > jm.slots) jm.slots = sm_;
     p->nseg_f = jf.nsegTotal > jf.slots ? jf.nsegTotal : jf.slots;
     p->nseg_m = jm.nsegTotal > jm.slots ? jm.nsegTotal : jm.slots;
     OQ_TRY(p->partial_f.alloc((size_t)nfl * (p->nseg_f > 0 ? p->nseg_f : 1) + 1));
@@ -911,6 +940,10 @@ static int finish_problem(OqProblem* p, const OqFaultProperty* pf, const OqDilat
     OQ_TRY(p->errpart.alloc(1024)); OQ_TRY(p->errpart.zero());
     OQ_TRY(p->ctl.alloc(32)); OQ_TRY(p->ctl.zero());
     OQ_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    if (getenv("OQ_TIMELINE") && !g_timeline) {          // debug timeline of the fused kernel (never inside a capture)
+        OQ_CUDA(cudaMalloc(&g_timeline, 160 * 32 * sizeof(unsigned long long)));
+        OQ_CUDA(cudaMemset(g_timeline, 0, 160 * 32 * sizeof(unsigned long long)));
+    }
     OQ_CUDA(cudaDeviceSynchronize());
     return 0;
 }
@@ -1109,6 +1142,10 @@ int oq_rhs_resident(OqProblem* p, int nevals, double* ms_total)
         cudaGraphDestroy(g);
         OQ_CUDA(ie);
     }
+    // Row-sharded runs: one untimed evaluation first.  Its exchange lines the ranks' streams up on the device, so the
+    // event pair below brackets nevals evaluations of device work and not the few tens of microseconds by which
+    // the host threads of the ranks reach this call apart.
+    if (p->world > 1 && nevals > 0) OQ_TRY(rhs_device(p, p->u.p, p->k[0].p));
     EventTimer tm;
     OQ_TRY(tm.start(p->stream));
     int i = 0;
@@ -1121,6 +1158,7 @@ int oq_rhs_resident(OqProblem* p, int nevals, double* ms_total)
     }
     for (; i < nevals; ++i) OQ_TRY(rhs_device(p, p->u.p, p->k[0].p));
     OQ_TRY(tm.stop(ms_total, p->stream));
+    dump_timeline(p->rank);
     return comm_check_error(p, "oq_rhs_resident");
 }
 

@@ -62,7 +62,75 @@ def hex8():
         json.dump(dict(cases=cases), fh, indent=1)
 
 
+def hex8_patterns():
+    """>= 200 further cases at the reference's CALL PATTERNS (GF.jl:215-221, :277-283), again from the quadrature
+    oracle: mantle->fault (receiver = fault-cell centroid, sources = cells of the example's hex8 box,
+    examples/otf-with-mantle.jl:18,25-29) and mantle->mantle (receiver = cell centroid or a Gauss2 point of it;
+    itself, stacked / side neighbours, distant cells), unit eigenstrains as the builders pass them, plus scaled copies
+    of the geometry out to r/a = 50 and receivers on the free surface."""
+    import workloads as W
+    from oracle import hex8_numeric as hn
+    rng = np.random.default_rng(4242)
+    fs, bs = W.C2_FAULT, W.C2_BOX
+    mf = ref.fault_mesh(fs.x, fs.xi, fs.dx, fs.dxi, fs.dip)
+    ma = ref.hex8_box(*bs.args())
+    lam, mu = W.LAM, W.MU
+    nu = lam / 2 / (lam + mu)
+    cases = []
+
+    def add(kind, p, i, pc):
+        eps = np.zeros(6)
+        eps[pc] = 1.0
+        g = (ma.qx[i], ma.qy[i], ma.qz[i], ma.dx[i], ma.dy[i], ma.dz[i])
+        # the cells are strongly anisotropic (20 km x 1.7 km x 4.6-11.6 km): a receiver next to a large face needs a
+        # fine rule (64 points leave 5e-3, 200 points 2e-12 for a neighbouring centroid)
+        lo = np.array([g[0] - g[3] / 2, g[1], g[2] - g[5]])
+        hi = np.array([g[0] + g[3] / 2, g[1] + g[4], g[2]])
+        dist = np.linalg.norm(np.maximum(0.0, np.maximum(lo - np.array(p), np.array(p) - hi)))
+        nq = 256 if dist < 1.5 * max(g[3:]) else 96
+        sg = hn.stress_vol_hex8(*p, *g, eps, mu, nu, nquad=nq)
+        cases.append(dict(kind=kind, point=[float(v) for v in p], geom=[float(v) for v in g], mu=mu, nu=nu,
+                          eps=eps.tolist(), sigma=[float(v) for v in sg], nquad=nq))
+
+    # mantle -> fault: 60 (fault cell, hex8 cell, unit strain) triples of the example
+    for _ in range(60):
+        f, i, pc = int(rng.integers(0, mf.nx * mf.nxi)), int(rng.integers(0, ma.n)), int(rng.integers(0, 6))
+        add("mantle_fault", (mf.x[f % mf.nx], mf.y[f // mf.nx], mf.z[f // mf.nx]), i, pc)
+    # mantle -> mantle at centroids: self, neighbours in x / y / z, random pairs
+    nx, ny = bs.nx, bs.ny
+    for j in rng.integers(0, ma.n, 12):
+        j = int(j)
+        nb = [j, (j + 1) % ma.n, (j + nx) % ma.n, (j + nx * ny) % ma.n, int(rng.integers(0, ma.n))]
+        for i in nb:
+            add("mantle_mantle", (ma.cx[j], ma.cy[j], ma.cz[j]), i, int(rng.integers(0, 6)))
+    # Gauss2 points of the receiver cell (GF.jl:270-276)
+    gp = 1 / np.sqrt(3.0)
+    for _ in range(40):
+        j, i = int(rng.integers(0, ma.n)), int(rng.integers(0, ma.n))
+        sgn = rng.choice([-1.0, 1.0], 3)
+        p = (ma.cx[j] + sgn[0] * gp * ma.dx[j] / 2, ma.cy[j] + sgn[1] * gp * ma.dy[j] / 2, ma.cz[j] + sgn[2] * gp * ma.dz[j] / 2)
+        add("mantle_mantle_gauss2", p, i, int(rng.integers(0, 6)))
+    # far receivers (5 to 50 times the SMALLEST cell dimension: the corner sums of the closed form lose ~(r/a)^3 ulps
+    # to cancellation, see tests/test_oracle_hex8.py::test_far_field_conditioning) and receivers on the free surface
+    for _ in range(30):
+        i = int(rng.integers(0, ma.n))
+        a = min(ma.dx[i], ma.dy[i], ma.dz[i])
+        r = a * rng.uniform(5, 50)
+        th, ph = rng.uniform(0, 2 * np.pi), rng.uniform(0.05, 0.45) * np.pi
+        c = np.array([ma.cx[i], ma.cy[i], ma.cz[i]])
+        p = c + r * np.array([np.cos(th) * np.sin(ph), np.sin(th) * np.sin(ph), -np.cos(ph)])
+        add("far", tuple(p), i, int(rng.integers(0, 6)))
+    for _ in range(20):
+        i = int(rng.integers(0, ma.n))
+        add("surface", (ma.cx[i] + rng.uniform(-3, 3) * ma.dx[i], ma.cy[i] + rng.uniform(-3, 3) * ma.dy[i], 0.0), i,
+            int(rng.integers(0, 6)))
+    with open(os.path.join(HERE, "hex8_patterns.json"), "w") as fh:
+        json.dump(dict(lam=lam, mu=mu, cases=cases), fh, indent=0)
+    print(len(cases), "hex8 pattern cases")
+
+
 if __name__ == "__main__":
     okada()
     hex8()
+    hex8_patterns()
     print("wrote", os.listdir(HERE))
