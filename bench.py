@@ -402,6 +402,17 @@ def example_extra(oq):
             "tsit5_rhs_per_s": 6 * steps / wall, "one_simulated_year": year}
 
 
+def _matvec_kernel_name(world):
+    """the kernel oq_rhs launches for the dense operands (csrc/rhs.cu: matvec_variant): OQ_MATVEC overrides, else the
+    fused panel kernel on one GPU and the forcing + streaming pair on row shards"""
+    v = os.environ.get("OQ_MATVEC")
+    if v == "ldg":
+        return "matvec_fused_kernel"
+    if v == "stream" or (v != "panel" and world > 1):
+        return "matvec_stream_kernel"
+    return "matvec_panel_kernel"
+
+
 def hbm_only_extra(args):
     """The headline run again in a fresh process with the L2-residency hints and the alternating traversal switched
     off (every byte of the matrix comes from HBM on every evaluation): the plain streaming roofline."""
@@ -587,7 +598,7 @@ def run_ours(args):
         "algorithm": "dense row-sharded fp64 matvec with fused friction epilogue (the form the north star names)",
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                      "frac": achieved / peak_gbs, "traffic": traffic, "traffic_source": traffic_src,
-                     "kernel": "matvec_fused_kernel" if os.environ.get("OQ_MATVEC") == "ldg" else "matvec_stream_kernel",
+                     "kernel": _matvec_kernel_name(world),
                      "kernel_ms": mv_avg_ms, "algorithmic_bytes_per_launch": rhs_bytes, "peak_source": peak_src,
                      "kernel_share_of_step": mv_ms / ms_prof if ms_prof > 0 else None,
                      "timing": "CUDA events around each matvec launch, second pass of the same K steps"},

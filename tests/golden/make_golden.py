@@ -62,6 +62,21 @@ def hex8():
         json.dump(dict(cases=cases), fh, indent=1)
 
 
+def _converged_quadrature(args):
+    from oracle import hex8_numeric as hn
+    p, g, pc, mu, nu = args
+    eps = np.zeros(6)
+    eps[pc] = 1.0
+    prev, nq = None, 64
+    while True:
+        cur = hn.stress_vol_hex8(*p, *g, eps, mu, nu, nquad=nq)
+        if prev is not None:
+            delta = float(np.max(np.abs(cur - prev)) / np.max(np.abs(cur)))
+            if delta < 5e-12 or nq >= 512:
+                return cur, nq, delta
+        prev, nq = cur, nq * 2
+
+
 def hex8_patterns():
     """>= 200 further cases at the reference's CALL PATTERNS (GF.jl:215-221, :277-283), again from the quadrature
     oracle: mantle->fault (receiver = fault-cell centroid, sources = cells of the example's hex8 box,
@@ -78,19 +93,10 @@ def hex8_patterns():
     nu = lam / 2 / (lam + mu)
     cases = []
 
+    todo = []
+
     def add(kind, p, i, pc):
-        eps = np.zeros(6)
-        eps[pc] = 1.0
-        g = (ma.qx[i], ma.qy[i], ma.qz[i], ma.dx[i], ma.dy[i], ma.dz[i])
-        # the cells are strongly anisotropic (20 km x 1.7 km x 4.6-11.6 km): a receiver next to a large face needs a
-        # fine rule (64 points leave 5e-3, 200 points 2e-12 for a neighbouring centroid)
-        lo = np.array([g[0] - g[3] / 2, g[1], g[2] - g[5]])
-        hi = np.array([g[0] + g[3] / 2, g[1] + g[4], g[2]])
-        dist = np.linalg.norm(np.maximum(0.0, np.maximum(lo - np.array(p), np.array(p) - hi)))
-        nq = 256 if dist < 1.5 * max(g[3:]) else 96
-        sg = hn.stress_vol_hex8(*p, *g, eps, mu, nu, nquad=nq)
-        cases.append(dict(kind=kind, point=[float(v) for v in p], geom=[float(v) for v in g], mu=mu, nu=nu,
-                          eps=eps.tolist(), sigma=[float(v) for v in sg], nquad=nq))
+        todo.append((kind, tuple(float(v) for v in p), int(i), int(pc)))
 
     # mantle -> fault: 60 (fault cell, hex8 cell, unit strain) triples of the example
     for _ in range(60):
@@ -124,9 +130,23 @@ def hex8_patterns():
         i = int(rng.integers(0, ma.n))
         add("surface", (ma.cx[i] + rng.uniform(-3, 3) * ma.dx[i], ma.cy[i] + rng.uniform(-3, 3) * ma.dy[i], 0.0), i,
             int(rng.integers(0, 6)))
+    # The cells are strongly anisotropic (20 km x 1.7 km x 4.6-11.6 km): a receiver next to a large face needs a very
+    # fine rule (a neighbouring centroid: 64 points per face axis leave 5e-3, 256 leave 1e-9, 512 reach 1e-15).  Each
+    # case is therefore evaluated with 64, 128, 256, 512 points until two successive rules agree to 5e-12 -- a
+    # criterion internal to the quadrature oracle, independent of the closed form it pins.
+    from multiprocessing import Pool
+    geoms = [(ma.qx[i], ma.qy[i], ma.qz[i], ma.dx[i], ma.dy[i], ma.dz[i]) for (_, _, i, _) in todo]
+    with Pool(min(8, os.cpu_count() or 1)) as pool:
+        res = pool.map(_converged_quadrature, [(p, g, pc, mu, nu) for (_, p, _, pc), g in zip(todo, geoms)])
+    for (kind, p, i, pc), g, (sg, nq, delta) in zip(todo, geoms, res):
+        eps = [0.0] * 6
+        eps[pc] = 1.0
+        cases.append(dict(kind=kind, point=list(p), geom=[float(v) for v in g], mu=mu, nu=nu, eps=eps,
+                          sigma=[float(v) for v in sg], nquad=nq, self_convergence=delta))
     with open(os.path.join(HERE, "hex8_patterns.json"), "w") as fh:
         json.dump(dict(lam=lam, mu=mu, cases=cases), fh, indent=0)
-    print(len(cases), "hex8 pattern cases")
+    print(len(cases), "hex8 pattern cases; rules used:", sorted(set(c["nquad"] for c in cases)),
+          "worst self-convergence", max(c["self_convergence"] for c in cases))
 
 
 if __name__ == "__main__":
