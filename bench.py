@@ -306,8 +306,8 @@ def assembly_extras(oq, fp64_peak):
     ma = oq.gen_mesh("BEMHex8Mesh", *W.box_for(32, 8, 8, fsm).args())
     for name, key, builder in (
             ("okada_fault_mantle", "gf_fault_mantle_kernel<0>", lambda: oq.device_fault_mantle(mfm, ma, W.LAM, W.MU, buffer_ratio=1.0)),
-            ("hex8_mantle_fault", "gf_mantle_fault_kernel<0>", lambda: oq.device_mantle_fault(ma, mfm, W.LAM, W.MU)),
-            ("hex8_mantle_mantle", "gf_mantle_mantle_kernel", lambda: oq.device_mantle_mantle(ma, W.LAM, W.MU))):
+            ("hex8_mantle_fault", "gf_mantle_fault_tile_kernel<0>", lambda: oq.device_mantle_fault(ma, mfm, W.LAM, W.MU)),
+            ("hex8_mantle_mantle", "gf_mantle_mantle_tile_kernel", lambda: oq.device_mantle_mantle(ma, W.LAM, W.MU))):
         best, shape = None, None
         for _ in range(3):
             m = builder()

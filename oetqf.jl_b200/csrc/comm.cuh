@@ -106,6 +106,34 @@ __device__ __forceinline__ void wait_peers(const unsigned long long* flags, int 
     }
 }
 
+// the same wait executed by a whole warp: lane r polls the flag of peer r with relaxed loads (all peers in flight at
+// once instead of one acquire round trip after the other) and confirms with ONE acquire load once the value is there
+// (a system-scope fence here costs ~3 us on the critical path of every evaluation: measured, 49.2 -> 53.6 us at 8 GPUs)
+__device__ __forceinline__ void wait_peers_warp(const unsigned long long* flags, int world, int self,
+                                                unsigned long long epoch, unsigned long long* err, int lane)
+{
+    unsigned long long* epochs = err - kEpError;
+    if (lane < world && lane != self) {
+        unsigned long long t0 = 0;
+        const unsigned long long limit = epochs[kEpTimeoutNs];
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        for (;;) {
+            unsigned long long v;
+            asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + lane) : "memory");
+            if (v >= epoch) {
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + lane) : "memory");
+                break;
+            }
+            if (limit) {
+                unsigned long long t1;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t1 - t0 > limit) { raise_peer_timeout(epochs); break; }
+            }
+        }
+    }
+    __syncwarp();
+}
+
 // Flag store to a peer.  The caller issues ONE system-scope fence before the loop over peers (a release
 // store per peer would pay the fence once per peer, ~microseconds each over NVLink).
 __device__ __forceinline__ void publish_flag(unsigned long long* remote_flag, unsigned long long epoch)

@@ -81,8 +81,11 @@ __device__ __forceinline__ double shear_traction_stress(int slip, const double (
 #ifndef OQ_OKADA_MINB
 #define OQ_OKADA_MINB 4      // resident CTAs per SM the Okada kernels are compiled for (caps registers at 128; measured fastest)
 #endif
+#ifndef OQ_OKADA_STRICT_MINB1
+#define OQ_OKADA_STRICT_MINB1 4
+#endif
 template <int SLIP, bool STRICT>
-__global__ void __launch_bounds__(128, OQ_OKADA_MINB)
+__global__ void __launch_bounds__(128, STRICT ? OQ_OKADA_STRICT_MINB1 : OQ_OKADA_MINB)
 gf_fault_fault_kernel(FaultGeom f, OkadaParams p, double* __restrict__ st)
 {
     extern __shared__ double sm[];

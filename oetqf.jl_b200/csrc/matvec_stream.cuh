@@ -150,59 +150,64 @@ matvec_stream_kernel(const __grid_constant__ MatvecArgs args)
 
     if (warp == kStCWarps) {
         // ------------------------------------------------------------------ producer warp
-        if (lane == 0) {
-            // The matrix does not depend on this evaluation's forcing vector: the first ring of matrix pieces is
-            // requested BEFORE waiting for the forcing kernel / the peers' publication.
-            auto issue = [&](const ChunkIter& c, int stg, bool matrix, bool vector, size_t par) {
-                const MatvecJob& j = args.job[c.job];
-                const int rem = c.rem();
-                const int osel = rem < j.nch[0] ? 0 : 1;
-                const MatOperand& op = j.op[osel];
-                const int c0 = (osel ? rem - j.nch[0] : rem) * kStCH;
-                const int ncol = min(kStCH, (int)op.ld - c0);
-                const unsigned bytes = (unsigned)(ncol * sizeof(double));
-                double* dst = smem + (size_t)stg * kStStageDoubles;
-                if (matrix) {
-                    mbar_arrive_expect_tx(&full_bar[stg], bytes * (kStR + 1));
-                    // L2 residency: the first `keep_chunks` chunks of every span are asked to stay in L2 (evicted
-                    // last), everything else to leave first -- the next evaluation finds the kept part on chip
-                    const long long g = j.chunk_begin + (long long)c.rb * j.chunks_per_rb + rem;
-                    const unsigned long long pol = args.keep_chunks < 0 ? kL2EvictNormal
-                                                   : (g - g_begin < args.keep_chunks ? kL2EvictLast : kL2EvictFirst);
+        // The matrix does not depend on this evaluation's forcing vector: the first ring of matrix pieces is
+        // requested BEFORE waiting for the forcing kernel / the peers' publication.
+        auto issue = [&](const ChunkIter& c, int stg, bool matrix, bool vector, size_t par) {
+            const MatvecJob& j = args.job[c.job];
+            const int rem = c.rem();
+            const int osel = rem < j.nch[0] ? 0 : 1;
+            const MatOperand& op = j.op[osel];
+            const int c0 = (osel ? rem - j.nch[0] : rem) * kStCH;
+            const int ncol = min(kStCH, (int)op.ld - c0);
+            const unsigned bytes = (unsigned)(ncol * sizeof(double));
+            double* dst = smem + (size_t)stg * kStStageDoubles;
+            if (matrix) {
+                mbar_arrive_expect_tx(&full_bar[stg], bytes * (kStR + 1));
+                // L2 residency: the first `keep_chunks` chunks of every span are asked to stay in L2 (evicted
+                // last), everything else to leave first -- the next evaluation finds the kept part on chip
+                const long long g = j.chunk_begin + (long long)c.rb * j.chunks_per_rb + rem;
+                const unsigned long long pol = args.keep_chunks < 0 ? kL2EvictNormal
+                                               : (g - g_begin < args.keep_chunks ? kL2EvictLast : kL2EvictFirst);
 #pragma unroll
-                    for (int r = 0; r < kStR; ++r) {
-                        const int row = min(c.rb * kStR + r, j.nrows - 1);
-                        tma_load_1d_hint(dst + r * kStCH, op.G + (size_t)row * op.ld + c0, bytes, &full_bar[stg], pol);
-                    }
+                for (int r = 0; r < kStR; ++r) {
+                    const int row = min(c.rb * kStR + r, j.nrows - 1);
+                    tma_load_1d_hint(dst + r * kStCH, op.G + (size_t)row * op.ld + c0, bytes, &full_bar[stg], pol);
                 }
-                if (vector)
-                    tma_load_1d_hint(dst + kStR * kStCH, op.x + par * op.x_stride + c0, bytes, &full_bar[stg],
-                                     args.keep_chunks < 0 ? kL2EvictNormal : kL2EvictLast);
-            };
-            ChunkIter cur, pre;
-            cur.start(args, walk);
-            pre = cur;
-            const int npre = (int)min((long long)kStStages, g_end - g_begin);
+            }
+            if (vector)
+                tma_load_1d_hint(dst + kStR * kStCH, op.x + par * op.x_stride + c0, bytes, &full_bar[stg],
+                                 args.keep_chunks < 0 ? kL2EvictNormal : kL2EvictLast);
+        };
+        ChunkIter cur, pre;
+        cur.start(args, walk);
+        pre = cur;
+        const int npre = (int)min((long long)kStStages, g_end - g_begin);
+        if (lane == 0)
             for (int s = 0; s < npre; ++s) { issue(cur, s, true, false, 0); cur.next(args, walk); }
-            pdl_wait();                               // the forcing kernel (predecessor) is complete from here on
-            size_t par = 0;
-            if (args.pw.epochs) {
-                const unsigned long long ep = *(volatile unsigned long long*)(args.pw.epochs + kEpForcing);
-                if (args.pw.world > 1) {
+        __syncwarp();
+        pdl_wait();                                   // the forcing kernel (predecessor) is complete from here on
+        size_t par = 0;
+        if (args.pw.epochs) {
+            const unsigned long long ep = *(volatile unsigned long long*)(args.pw.epochs + kEpForcing);
+            if (args.pw.world > 1) {
+                if (args.pw.warp_poll)                // all peers polled at once, one lane each
+                    wait_peers_warp(args.pw.flags, args.pw.world, args.pw.rank, ep, args.pw.epochs + kEpError, lane);
+                else if (lane == 0)
                     wait_peers(args.pw.flags, args.pw.world, args.pw.rank, ep, args.pw.epochs + kEpError);
-                    fence_proxy_async();              // peer stores -> async-proxy (TMA) reads
-                }
-                par = (size_t)((ep - 1ull) & 1ull);
+                __syncwarp();
+                fence_proxy_async();                  // peer stores -> async-proxy (TMA) reads
             }
-            for (int s = 0; s < npre; ++s) { issue(pre, s, false, true, par); pre.next(args, walk); }
-            int stage = npre % kStStages;
-            unsigned phase = npre >= kStStages ? 1u : 0u;
-            for (long long g = g_begin + npre; g < g_end; ++g) {
-                mbar_wait(&empty_bar[stage], phase ^ 1u);
-                issue(cur, stage, true, true, par);
-                cur.next(args, walk);
-                if (++stage == kStStages) { stage = 0; phase ^= 1u; }
-            }
+            par = (size_t)((ep - 1ull) & 1ull);
+        }
+        if (lane != 0) return;
+        for (int s = 0; s < npre; ++s) { issue(pre, s, false, true, par); pre.next(args, walk); }
+        int stage = npre % kStStages;
+        unsigned phase = npre >= kStStages ? 1u : 0u;
+        for (long long g = g_begin + npre; g < g_end; ++g) {
+            mbar_wait(&empty_bar[stage], phase ^ 1u);
+            issue(cur, stage, true, true, par);
+            cur.next(args, walk);
+            if (++stage == kStStages) { stage = 0; phase ^= 1u; }
         }
         return;
     }
@@ -217,10 +222,13 @@ matvec_stream_kernel(const __grid_constant__ MatvecArgs args)
             long long rb_g0, rb_g1;
             walk.get(args, k, jb, rb, rem0, nch, rb_g0, rb_g1);   // the part of this row block inside my span
             const MatvecJob& j = args.job[jb];
-            mbar_wait(&red_full[buf], rphase[buf]);   // all consumer warps have dropped their partial sums
-            rphase[buf] ^= 1u;
             const int myrow = rb * kStR + lane;
             const bool active = lane < kStR && myrow < j.nrows;
+            // the row's state and properties are fetched while the consumers still stream its chunks
+            FaultRowInputs fin{};
+            if (active && j.epilogue == kEpiFault) fin = load_fault_row(args.fe, myrow);
+            mbar_wait(&red_full[buf], rphase[buf]);   // all consumer warps have dropped their partial sums
+            rphase[buf] ^= 1u;
             double mine = 0.0;
             if (lane < kStR) {
 #pragma unroll
@@ -258,7 +266,7 @@ matvec_stream_kernel(const __grid_constant__ MatvecArgs args)
             }
             if (do_epilogue && active) {
                 if (j.y0) mine += j.y0[myrow];
-                if (j.epilogue == kEpiFault) update_fault_row(args.fe, myrow, mine);
+                if (j.epilogue == kEpiFault) update_fault_row(args.fe, myrow, mine, fin);
                 else j.yout[myrow] = mine;
             }
         }

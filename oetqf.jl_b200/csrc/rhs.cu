@@ -146,10 +146,29 @@ struct FaultEpilogue {
     int dilatancy;
 };
 
-__device__ __forceinline__ void update_fault_row(const FaultEpilogue& e, int i, double dtau)
+// state and properties of one fault row: loaded BEFORE the row's traction rate is known (they do not depend on
+// it), so that at the end of a span only arithmetic separates the last partial sum from the stored derivative
+struct FaultRowInputs {
+    double v, th, a, b, L, sg;
+};
+
+__device__ __forceinline__ FaultRowInputs load_fault_row(const FaultEpilogue& e, int i)
 {
     const FaultParams& p = e.fp;
-    const double v = e.v[i], th = e.theta[i], a = p.a[i], b = p.b[i], L = p.L[i], sg = p.sigma[i];
+    return FaultRowInputs{e.v[i], e.theta[i], p.a[i], p.b[i], p.L[i], p.sigma[i]};
+}
+
+__device__ __forceinline__ void update_fault_row(const FaultEpilogue& e, int i, double dtau, const FaultRowInputs& in);
+
+__device__ __forceinline__ void update_fault_row(const FaultEpilogue& e, int i, double dtau)
+{
+    update_fault_row(e, i, dtau, load_fault_row(e, i));
+}
+
+__device__ __forceinline__ void update_fault_row(const FaultEpilogue& e, int i, double dtau, const FaultRowInputs& in)
+{
+    const FaultParams& p = e.fp;
+    const double v = in.v, th = in.th, a = in.a, b = in.b, L = in.L, sg = in.sg;
     const double dth = 1.0 - v * th / L;                                     // aging law, :279
     if (!e.dilatancy) {
         const double psi1 = exp((p.f0 + b * log(p.v0 * fmax(0.0, th) / L)) / a) / (2.0 * p.v0);
@@ -189,6 +208,7 @@ struct PeerWait {
     const unsigned long long* flags;   // local forcing flags [kMaxWorld]
     unsigned long long* epochs;        // local counters
     int world, rank;
+    int warp_poll;                     // poll all peers at once, one lane each (OQ_WAIT=serial: one after the other)
 };
 
 // every consumer CTA: find the buffer copy of the current evaluation and make sure all peers delivered
@@ -703,7 +723,8 @@ static int rhs_views(OqProblem* p, const StateView& in, const StateView& out, co
     else forcing_kernel<<<(nthr + 255) / 256, 256, 0, st>>>(fa);
     OQ_LAUNCHED();
     }
-    PeerWait pw{p->flags, p->epochs, p->world, p->rank};
+    static const int warp_poll = [] { const char* e = getenv("OQ_WAIT"); return (e && strcmp(e, "serial") == 0) ? 0 : 1; }();
+    PeerWait pw{p->flags, p->epochs, p->world, p->rank, warp_poll};
     // 2. fault-fault interaction in its translation-invariant form (the reference's algorithm) when requested
     FaultEpilogue fe{};
     fe.fp = p->fp; fe.v = in.v; fe.theta = in.theta; fe.pr = in.pr;

@@ -26,10 +26,12 @@ def main(rep, out):
     col = {h: i for i, h in enumerate(hdr)}
     res = {}
     for r in rows[2:]:
-        m = re.search(r"(gf_\w+_kernel(?:<\d>)?)", r[col["Kernel Name"]])
-        if not m or m.group(1) not in ENTRIES:
+        m = re.search(r"(gf_\w+_kernel)(?:<\s*(\d)[^>]*>)?", r[col["Kernel Name"]])
+        if not m:
             continue
-        key = m.group(1)
+        key = m.group(1) + (f"<{m.group(2)}>" if m.group(2) is not None else "")
+        if key not in ENTRIES or key in res:
+            continue
         cyc = num(r[col["sm__cycles_elapsed.avg"]])
         ops = {}
         for op in ("dadd", "dmul", "dfma"):

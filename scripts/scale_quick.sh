@@ -2,7 +2,7 @@
 # the driver's scaling measurement in miniature: bench.py at N with the driver's K/W, three repetitions
 N=${1:-8}
 mkdir -p gpurun_out
-for rep in 1 2 3; do
+for rep in 1 2; do
 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29700+rep)) bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/scaleq_n${N}_$rep.json 2> gpurun_out/scaleq_n${N}_$rep.err
 python - <<PY
 import json

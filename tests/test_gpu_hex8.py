@@ -30,6 +30,41 @@ def test_stress_vol_hex8_pointwise_vs_quadrature_fixture(gpu):
     assert worst < TOL, worst
 
 
+def test_builders_vs_quadrature_at_the_reference_call_patterns(gpu):
+    """tests/golden/hex8_patterns.json (210 cases from the quadrature oracle at the arguments GF.jl:215-221, :277-283
+    pass on the example's meshes): the pointwise kernel AND the entries the tiled assembly kernels write into
+    gf21 / gf22 of the same meshes -- values independent of the closed form and of its generated code"""
+    oq = gpu
+    with open(os.path.join(GOLD, "hex8_patterns.json")) as fh:
+        g = json.load(fh)
+    cases = g["cases"]
+    assert len(cases) >= 200
+    mf_o, mf_p, ma_o, ma_p = meshes(oq, W.C2_FAULT, W.C2_BOX)
+    lam, mu = g["lam"], g["mu"]
+    gf21 = oq.stress_greens_function(ma_p, mf_p, lam, mu)
+    gf22 = oq.stress_greens_function(ma_p, lam, mu)
+    ne = ma_o.n
+    worst_pt = worst_21 = worst_22 = 0.0
+    n21 = n22 = 0
+    for c in cases:
+        p, geom, pc = c["point"], c["geom"], int(np.argmax(c["eps"]))
+        want = np.array(c["sigma"])
+        got = oq.stress_vol_hex8(p[0], p[1], p[2], *geom, c["eps"], c["mu"], c["nu"])[0]
+        worst_pt = max(worst_pt, np.max(np.abs(got - want)) / np.max(np.abs(want)))
+        i = int(np.argmin(np.abs(ma_o.qx - geom[0]) + np.abs(ma_o.qy - geom[1]) + np.abs(ma_o.qz - geom[2])))
+        if c["kind"] == "mantle_fault":
+            f = int(np.argmin(np.abs(mf_o.x - p[0])) + mf_o.nx * np.argmin(np.abs(mf_o.z - p[2])))
+            t = -want[1] * 1.0 + want[2] * 0.0                          # GF.jl:89-92 at dip 90
+            worst_21 = max(worst_21, abs(gf21[f, pc * ne + i] - t) / np.max(np.abs(want)))
+            n21 += 1
+        elif c["kind"] == "mantle_mantle":
+            j = int(np.argmin(np.abs(ma_o.cx - p[0]) + np.abs(ma_o.cy - p[1]) + np.abs(ma_o.cz - p[2])))
+            worst_22 = max(worst_22, np.max(np.abs(gf22[np.arange(6) * ne + j, pc * ne + i] - want)) / np.max(np.abs(want)))
+            n22 += 1
+    assert n21 >= 50 and n22 >= 50
+    assert worst_pt < 2e-10 and worst_21 < 2e-10 and worst_22 < 2e-10, (worst_pt, worst_21, worst_22)
+
+
 def test_stress_vol_hex8_pointwise_vs_oracle(gpu):
     oq = gpu
     rng = np.random.default_rng(3)
@@ -154,3 +189,43 @@ def test_edge_line_regularisation(gpu):
         assert np.max(np.abs(s - want_o)) < 1e-9 * np.max(np.abs(want_o))
         want_q = hn.stress_vol_hex8(*p, *g, eps, mu, nu, nquad=64)
         assert np.max(np.abs(s - want_q)) < 2e-5 * np.max(np.abs(want_q))
+
+
+def test_pair_kernel_twin(gpu):
+    """the one-thread-per-pair hex8 kernels of round 1 (OQ_HEX8=pair) stay correct next to the tiled default; the
+    switch is read once per process, hence the subprocess"""
+    import subprocess
+    import sys
+    if os.environ.get("OQ_HEX8") == "pair":
+        pytest.skip("already the twin")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-q", "-x",
+                          "-k", "mantle_fault or mantle_mantle or call_patterns"],
+                         env={**os.environ, "OQ_HEX8": "pair"}, capture_output=True, text=True, timeout=900, cwd=root)
+    assert res.returncode == 0, res.stdout[-2000:]
+
+
+def test_tiles_on_an_irregular_mesh(gpu):
+    """cells in scrambled order, two different sizes, a gap in the box: tiles share fewer vertices but the entries
+    are those of the pair kernels' mesh order (the tile builder must not assume a full tensor grid)"""
+    oq = gpu
+    rng = np.random.default_rng(11)
+    _, _, ma_o, ma_p = meshes(oq, W.C2_FAULT, W.BoxSpec(-40e3, -2.5e3, -8e3, 80e3, 5e3, -22e3, 6, 5, 5))
+    keep = rng.permutation(ma_o.n)[: ma_o.n - 17]                       # drop 17 cells, scramble the rest
+    sub = {k: getattr(ma_o, k)[keep].copy() for k in ("cx", "cy", "cz", "qx", "qy", "qz", "dx", "dy", "dz")}
+    # split one cell in two along x (non-conforming neighbours)
+    i = 5
+    for k in sub:
+        sub[k] = np.append(sub[k], sub[k][i])
+    half = sub["dx"][i] / 2
+    sub["dx"][i] = half; sub["dx"][-1] = half
+    sub["cx"][i] -= half / 2; sub["qx"][i] -= half / 2
+    sub["cx"][-1] += half / 2; sub["qx"][-1] += half / 2
+    mo = ref.Hex8Mesh(**sub)
+    mp = oq.BEMHex8Mesh(**sub) if hasattr(oq, "BEMHex8Mesh") else None
+    if mp is None:
+        from oetqf_b200.mesh import BEMHex8Mesh
+        mp = BEMHex8Mesh(**sub)
+    want = ref.gf_mantle_mantle(mo, W.LAM, W.MU)
+    got = oq.stress_greens_function(mp, W.LAM, W.MU)
+    assert scaled_err(got, want, axis=0) < TOL
