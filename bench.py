@@ -304,20 +304,51 @@ def assembly_extras(oq, fp64_peak):
     fsm = W.FaultSpec(64e3, 16e3, 1000.0, 1000.0)
     mfm = oq.gen_mesh("RectOkada", fsm.x, fsm.xi, fsm.dx, fsm.dxi, fsm.dip)
     ma = oq.gen_mesh("BEMHex8Mesh", *W.box_for(32, 8, 8, fsm).args())
-    for name, key, builder in (
-            ("okada_fault_mantle", "gf_fault_mantle_kernel<0>", lambda: oq.device_fault_mantle(mfm, ma, W.LAM, W.MU, buffer_ratio=1.0)),
-            ("hex8_mantle_fault", "gf_mantle_fault_tile_kernel<0>", lambda: oq.device_mantle_fault(ma, mfm, W.LAM, W.MU)),
-            ("hex8_mantle_mantle", "gf_mantle_mantle_tile_kernel", lambda: oq.device_mantle_mantle(ma, W.LAM, W.MU))):
-        best, shape = None, None
-        for _ in range(3):
+    hbm_peak, hbm_src = measured_peaks()
+
+    def timed(builder, reps=3):
+        best, shape, info = None, None, None
+        for _ in range(reps):
             m = builder()
             shape = (m.local_rows, m.cols)
             ms = _matrix_kernel_ms(m)
-            best = ms if best is None else min(best, ms)
+            if best is None or ms < best:
+                best, info = ms, m.assembly_info()
             m.free()
+        return best, shape, info
+
+    best, shape, _ = timed(lambda: oq.device_fault_mantle(mfm, ma, W.LAM, W.MU, buffer_ratio=1.0))
+    n = shape[0] * shape[1]
+    out["okada_fault_mantle"] = {"shape": list(shape), "kernel_ms": best, "entries_per_s": n / (best * 1e-3),
+                                 "roofline": _fp64_roofline("gf_fault_mantle_kernel<0>", n, best, fp64_peak, flops)}
+    # hex8 builders.  Default path: one closed-form evaluation per translation class of pairs + dense expansion
+    # (csrc/greens_classes.cuh) -- bounded by the HBM writes of the shard; its fp64-bound twins (every pair through
+    # the tiled kernels, OQ_HEX8=tile) are timed beside it against the DFMA peak.
+    saved = os.environ.get("OQ_HEX8")
+    for name, key, builder in (
+            ("hex8_mantle_fault", "gf_mantle_fault_tile_kernel<0>", lambda: oq.device_mantle_fault(ma, mfm, W.LAM, W.MU)),
+            ("hex8_mantle_mantle", "gf_mantle_mantle_tile_kernel", lambda: oq.device_mantle_mantle(ma, W.LAM, W.MU))):
+        os.environ["OQ_HEX8"] = saved or ""
+        best, shape, info = timed(builder)
         n = shape[0] * shape[1]
-        out[name] = {"shape": list(shape), "kernel_ms": best, "entries_per_s": n / (best * 1e-3),
-                     "roofline": _fp64_roofline(key, n, best, fp64_peak, flops)}
+        rec = {"shape": list(shape), "kernel_ms": best, "entries_per_s": n / (best * 1e-3), "path": info["path"],
+               "pairs": info["pairs"], "closed_form_evaluations": info["unique_pairs"],
+               "table_ms": info["table_ms"], "expand_ms": info["expand_ms"], "roofline": None}
+        if info["path"] == "classes" and info["expand_ms"] > 0:
+            gbs = n * 8 / (info["expand_ms"] * 1e-3) / 1e9
+            rec["roofline"] = {"bound": "hbm", "kernel": "expand_classes_kernel", "achieved": gbs, "peak": hbm_peak,
+                               "unit": "GB/s", "frac": gbs / hbm_peak, "algorithmic_bytes": n * 8,
+                               "note": "bytes of the dense shard written once; the class table is re-read from L2",
+                               "peak_source": hbm_src}
+        os.environ["OQ_HEX8"] = "tile"
+        tbest, _, tinfo = timed(builder)
+        rec["every_pair_tile_kernels"] = {"kernel_ms": tbest, "entries_per_s": n / (tbest * 1e-3), "path": tinfo["path"],
+                                          "roofline": _fp64_roofline(key, n, tbest, fp64_peak, flops)}
+        out[name] = rec
+    if saved is None:
+        os.environ.pop("OQ_HEX8", None)
+    else:
+        os.environ["OQ_HEX8"] = saved
     out["fp64_peak_tflops_measured"] = fp64_peak / 1e12
     return out
 

@@ -144,6 +144,24 @@ int oq_matrix_rows_to_host(const OqMatrix *a, int local_begin, int local_end, do
 int oq_matrix_shape(const OqMatrix *a, int *local_rows, int *cols, int *global_rows);
 /* device time (CUDA events) of the assembly kernel that filled this shard, in ms (0 for uploads) */
 int oq_matrix_kernel_ms(const OqMatrix *a, double *ms);
+/* How a hex8 shard (gf21, gf22) was assembled.  path: 0 = one thread per (receiver, source) pair, 1 = tiles of cells
+ * sharing vertices, 2 = class tables -- the half-space is invariant under horizontal translation, so pairs with equal
+ * (x_r - q_x, y_r - q_y, depths, sizes) share their 6 / 36 entries: the closed form of GF.jl:215-221 / :277-283 is
+ * evaluated once per class (table_ms) and copied into the dense shard (expand_ms); the same invariance the reference
+ * uses for gf11 (GF.jl:31-71).  -1: not a hex8 matrix.  OQ_HEX8 = pair | tile | classes forces a path. */
+typedef struct OqAssemblyInfo {
+    int path;
+    int64_t pairs, unique_pairs;      /* pairs of the shard; closed-form evaluations actually made */
+    double table_ms, expand_ms, kernel_ms;
+} OqAssemblyInfo;
+int oq_matrix_assembly_info(const OqMatrix *a, OqAssemblyInfo *info);
+/* Host-only view of that class decomposition (no device needed): for n sample pairs (recv[k], src[k]) -- receivers are
+ * mantle elements of [begin,end) when mf == NULL (gf22) or fault cells of [begin,end) (gf21) -- the receiver/source
+ * whose coordinates stand for the pair in the x group and in the (y,z) group; counts[0..2] = classes of the x group,
+ * of the (y,z) group (0, 0: the mesh has no exploitable structure) and pairs. */
+int oq_hex8_pair_classes(const OqHex8Mesh *ma, const OqFaultMesh *mf, int begin, int end, int n, const int *recv,
+                         const int *src, int *rep_recv_x, int *rep_src_x, int *rep_recv_yz, int *rep_src_yz,
+                         long long *counts);
 int oq_matrix_destroy(OqMatrix *a);
 
 /* The `matvecmul!` backend slot, src/pref.jl:15-21 as used at src/BEM/equation.jl:201-203:

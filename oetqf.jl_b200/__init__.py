@@ -12,7 +12,7 @@ from . import io
 from .io import wsolve
 from .gf import (max_real_eigval, DeviceMatrix, DipSlip, StrikeSlip, dc3d_gradient, device_fault_fault, device_fault_mantle,
                  device_from_host, device_mantle_fault, device_mantle_mantle, gauss_legendre_hex,
-                 get_quadrature, stress_greens_function, stress_vol_hex8)
+                 get_quadrature, hex8_pair_classes, stress_greens_function, stress_vol_hex8)
 from .mesh import BEMHex8Mesh, RectOkadaMesh, gen_box_hex8, gen_mesh
 from .pref import get_matvecmul, matvecmul, set_matvecmul
 from .property import (CompositePowerLawViscosityProperty, DieterichStateLaw, DilatancyProperty,

@@ -62,6 +62,11 @@ class OqSolveStats(C.Structure):
                 ("naccept", C.c_int64), ("nreject", C.c_int64), ("nrhs", C.c_int64), ("retcode", C.c_int32)]
 
 
+class OqAssemblyInfo(C.Structure):
+    _fields_ = [("path", C.c_int), ("pairs", C.c_int64), ("unique_pairs", C.c_int64),
+                ("table_ms", C.c_double), ("expand_ms", C.c_double), ("kernel_ms", C.c_double)]
+
+
 SNAPSHOT_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_double, C.c_int64,
                           C.POINTER(c_double_p), C.POINTER(c_double_p))
 
@@ -72,7 +77,7 @@ EXPORTS = [
     "oq_gf_fault_fault", "oq_gf_fault_mantle", "oq_gf_mantle_fault", "oq_gf_mantle_mantle",
     "oq_dc3d_gradient", "oq_stress_vol_hex8",
     "oq_matrix_fault_fault", "oq_matrix_from_toeplitz", "oq_matrix_fault_mantle", "oq_matrix_mantle_fault", "oq_matrix_mantle_mantle",
-    "oq_matrix_from_host", "oq_matrix_to_host", "oq_matrix_rows_to_host", "oq_matrix_shape", "oq_matrix_kernel_ms", "oq_matrix_destroy", "oq_gemv",
+    "oq_matrix_from_host", "oq_matrix_to_host", "oq_matrix_rows_to_host", "oq_matrix_shape", "oq_matrix_kernel_ms", "oq_matrix_assembly_info", "oq_hex8_pair_classes", "oq_matrix_destroy", "oq_gemv",
     "oq_problem_create_fault", "oq_problem_create_viscoelastic", "oq_problem_destroy", "oq_problem_layout",
     "oq_profile_enable", "oq_profile_read", "oq_rhs_bytes",
     "oq_rhs", "oq_state_set", "oq_state_get", "oq_state_get_du", "oq_rhs_resident", "oq_solve",

@@ -119,4 +119,7 @@ struct OqMatrix {
     size_t ld = 0;                  // leading dimension in doubles (multiple of 16)
     oq::DevBuf<double> d;           // [local_rows * ld], row-major, padding zeroed
     double kernel_ms = 0.0;         // device time of the assembly kernel(s)
+    int path = -1;                  // hex8 builders: 0 pair, 1 tile, 2 class-table kernels (-1: not a hex8 matrix)
+    long long pairs = 0, unique_pairs = 0;       // (receiver, source) pairs of the shard / closed-form evaluations made
+    double table_ms = 0.0, expand_ms = 0.0;      // class path: evaluation of the classes / dense expansion
 };

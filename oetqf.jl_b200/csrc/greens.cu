@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include "greens_okada.cuh"
 #include "hex8_dev.cuh"
+#include "greens_classes.cuh"
 
 namespace oq {
 
@@ -263,6 +264,63 @@ gf_mantle_mantle_tile_kernel(Hex8TileView T, Hex8Geom a, double mu, double nu, c
             }
             __syncthreads();
         }
+    }
+}
+
+// ---- K3''/K4'': the hex8 kernels on CLASSES of pairs (greens_classes.cuh) --------------------------------------
+// One thread per class (u1, u23): the per-pair code of K3/K4 on the coordinates of a representative receiver and
+// source of the x group and of the (y,z) group.  T[(k*6 + p)][u23][u1]  (K4),  T[p][u23][u1]  (K3).
+template <int SLIP>
+__global__ void __launch_bounds__(kHex8Threads, OQ_HEX8_MINB)
+gf_mantle_fault_class_kernel(Hex8Geom a, FaultGeom f, const int* __restrict__ rep_r1, const int* __restrict__ rep_s1,
+                             const int* __restrict__ rep_r23, const int* __restrict__ rep_s23, int n1, int n23,
+                             double mu, double nu, int slip, double s1, double c1, double s2, double c2,
+                             double* __restrict__ T)
+{
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)n1 * n23) return;
+    const int u1 = (int)(t % n1), u23 = (int)(t / n1);
+    const int q1 = rep_r1[u1] % f.nx, q2 = rep_r23[u23] / f.nx;      // representatives are global cell indices
+    const int i1 = rep_s1[u1], i23 = rep_s23[u23];
+    extern __shared__ double hex8_acc[];
+    constexpr int kNeed = SLIP == kStrikeSlip ? 0x06 : 0x38;
+    double* dst = T + (size_t)u23 * n1 + u1;
+    const size_t stride = (size_t)n1 * n23;
+    hex8_stress_emit<kNeed>(f.x[q1], f.y[q2], f.z[q2], a.qx[i1], a.qy[i23], a.qz[i23], a.dx[i1], a.dy[i23], a.dz[i23], mu, nu,
+                            hex8_acc + threadIdx.x, [&](int pc, const double (&S)[6]) {
+                                dst[(size_t)pc * stride] = shear_traction_stress(slip, S, s1, c1, s2, c2);
+                            });
+}
+
+__global__ void __launch_bounds__(kHex8Threads, OQ_HEX8_MINB)
+gf_mantle_mantle_class_kernel(Hex8Geom a, const int* __restrict__ rep_r1, const int* __restrict__ rep_s1,
+                              const int* __restrict__ rep_r23, const int* __restrict__ rep_s23, int n1, int n23,
+                              double mu, double nu, const double* __restrict__ qc,
+                              const double* __restrict__ qw, int nq, double* __restrict__ T)
+{
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)n1 * n23) return;
+    const int u1 = (int)(t % n1), u23 = (int)(t / n1);
+    const int j1 = rep_r1[u1], j23 = rep_r23[u23], i1 = rep_s1[u1], i23 = rep_s23[u23];   // global elements
+    const double cx = a.cx[j1], cy = a.cy[j23], cz = a.cz[j23];
+    const double hx = a.dx[j1] / 2, hy = a.dy[j23] / 2, hz = a.dz[j23] / 2;
+    const double qx = a.qx[i1], qy = a.qy[i23], qz = a.qz[i23], ex = a.dx[i1], ey = a.dy[i23], ez = a.dz[i23];
+    extern __shared__ double hex8_acc[];
+    double* dst0 = T + (size_t)u23 * n1 + u1;
+    const size_t stride = (size_t)n1 * n23;
+    for (int w = 0; w < nq; ++w) {
+        const double rx = cx + qc[3 * w] * hx;
+        const double ry = cy + qc[3 * w + 1] * hy;
+        const double rz = cz + qc[3 * w + 2] * hz;
+        const double wt = qw[w];
+        hex8_stress_emit(rx, ry, rz, qx, qy, qz, ex, ey, ez, mu, nu, hex8_acc + threadIdx.x,
+                         [&](int pc, const double (&S)[6]) {
+#pragma unroll
+                             for (int k = 0; k < 6; ++k) {
+                                 double* dst = dst0 + (size_t)(k * 6 + pc) * stride;
+                                 *dst = (w == 0) ? S[k] * wt : *dst + S[k] * wt;
+                             }
+                         });
     }
 }
 
@@ -526,11 +584,28 @@ struct DevHex8Tiles {
     }
 };
 
-// hex8 kernels: tiles with shared vertices by default; OQ_HEX8=pair selects the one-thread-per-pair kernels
-static bool hex8_tiles_enabled()
+// hex8 builders: by default the class tables (greens_classes.cuh) when the mesh has at least 4 pairs per class, else
+// the tiles with shared vertices; OQ_HEX8 = pair | tile | classes forces one path (validation twins)
+enum { kHex8Auto = -1, kHex8Pair = 0, kHex8Tile = 1, kHex8Classes = 2 };
+static int hex8_mode()
 {
-    static const bool on = [] { const char* e = getenv("OQ_HEX8"); return !(e && strcmp(e, "pair") == 0); }();
-    return on;
+    const char* e = getenv("OQ_HEX8");           // read on every call: tests switch between the twins
+    if (!e || !*e) return kHex8Auto;
+    if (strcmp(e, "pair") == 0) return kHex8Pair;
+    if (strcmp(e, "tile") == 0) return kHex8Tile;
+    if (strcmp(e, "classes") == 0) return kHex8Classes;
+    return kHex8Auto;
+}
+
+// class path worthwhile?  (forced: always when the classes could be built)
+static bool hex8_use_classes(int mode, bool built, const Hex8PairClasses& pc, int outputs_per_pair)
+{
+    if (!built || (mode != kHex8Auto && mode != kHex8Classes)) return false;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return false;
+    const double table_bytes = (double)pc.classes * outputs_per_pair * sizeof(double);
+    if (table_bytes > 0.5 * (double)free_b) return false;
+    return mode == kHex8Classes || pc.worthwhile;
 }
 
 static int make_okada_params(const OqFaultMesh* mf, double lam, double mu, int ftype, int nrept,
@@ -691,14 +766,51 @@ static int build_fault_mantle(const OqFaultMesh* mf, const OqHex8Mesh* ma, const
     OQ_TRY(dq.upload(quad));
     const int nf = mf->nx * mf->nxi, nel = e_end - e_begin;
     OqMatrix* M = new OqMatrix();
-    if (alloc_matrix(M, OQ_ROWS_MANTLE, e_begin, e_end, 6 * ma->n, nf) || M->d.zero()) { delete M; return 1; }
+    if (alloc_matrix(M, OQ_ROWS_MANTLE, e_begin, e_end, 6 * ma->n, nf)) { delete M; return 1; }
     if (nel > 0) {
         const size_t total = (size_t)nf * nel;
-        const unsigned blocks = (unsigned)((total + 127) / 128);
+        M->pairs = (long long)total;
+        // classes of pairs with bitwise equal dc3d arguments (greens_classes.cuh); OQ_FAULT_MANTLE = pair | classes forces
+        const char* env = getenv("OQ_FAULT_MANTLE");
+        const int mode = !env || !*env ? kHex8Auto : (strcmp(env, "pair") == 0 ? kHex8Pair : (strcmp(env, "classes") == 0 ? kHex8Classes : kHex8Auto));
+        Hex8PairClasses pc;
+        bool built = false;
+        if (mode != kHex8Pair) {
+            static const double c1[3] = {0, 0, 0};
+            built = fault_mantle_classes(mf, ma, quad ? quad->coords : c1, dq.nq, nrept, p.lrept, e_begin, e_end, pc);
+        }
+        const bool classes = hex8_use_classes(mode, built, pc, 6);
+        DevPairClasses dpc;
+        DevBuf<double> table;
+        if (!classes && M->d.zero()) { delete M; return 1; }
+        if (classes && (dpc.upload(pc) || table.alloc((size_t)pc.classes * 6))) { delete M; return 1; }
+        const bool strict = okada_strict_enabled();
         EventTimer tm;
         int rc = tm.start();
-        if (!rc) {
-            if (okada_strict_enabled())
+        if (!rc && classes) {
+            OkadaClassLaunch cl{dq.c.p, dq.w.p, dq.nq, dpc.rep_r1.p, dpc.rep_s1.p, dpc.rep_r23.p, dpc.rep_s23.p, pc.g1.n, pc.g23.n, table.p};
+            const unsigned nb = (unsigned)((pc.classes + 127) / 128);
+            if (strict) launch_fault_mantle_class_strict(ftype, dmf.g, dma.g, p, cl);
+            else if (ftype == OQ_STRIKE_SLIP)
+                gf_fault_mantle_class_kernel<kStrikeSlip, false><<<nb, 128>>>(dmf.g, dma.g, p, cl.qc, cl.qw, cl.nq, cl.rep_r1, cl.rep_s1,
+                                                                              cl.rep_r23, cl.rep_s23, cl.n1, cl.n23, cl.T);
+            else
+                gf_fault_mantle_class_kernel<kDipSlip, false><<<nb, 128>>>(dmf.g, dma.g, p, cl.qc, cl.qw, cl.nq, cl.rep_r1, cl.rep_s1,
+                                                                           cl.rep_r23, cl.rep_s23, cl.n1, cl.n23, cl.T);
+            g_launches.fetch_add(1);
+            rc = tm.stop(&M->table_ms);
+            if (!rc) rc = tm.start();
+            if (!rc) {
+                dim3 grid((unsigned)std::min<size_t>(((size_t)nf + 255) / 256, 64), (unsigned)std::min(nel, 65535));
+                expand_classes_kernel<6, 1><<<grid, 256>>>(table.p, dpc.v, nel, nf, M->ld, M->d.p);
+                g_launches.fetch_add(1);
+                rc = tm.stop(&M->expand_ms);
+            }
+            M->kernel_ms = M->table_ms + M->expand_ms;
+            M->path = kHex8Classes; M->unique_pairs = pc.classes;
+        } else if (!rc) {
+            const unsigned blocks = (unsigned)((total + 127) / 128);
+            if (strict)
                 launch_fault_mantle_strict(ftype, blocks, dmf.g, dma.g, p, dq.c.p, dq.w.p, dq.nq, e_begin, nel, M->ld, M->d.p);
             else if (ftype == OQ_STRIKE_SLIP)
                 gf_fault_mantle_kernel<kStrikeSlip, false><<<blocks, 128>>>(dmf.g, dma.g, p, dq.c.p, dq.w.p, dq.nq, e_begin,
@@ -708,7 +820,9 @@ static int build_fault_mantle(const OqFaultMesh* mf, const OqHex8Mesh* ma, const
                                                                           nel, M->ld, M->d.p);
             g_launches.fetch_add(1);
             rc = tm.stop(&M->kernel_ms);
+            M->path = kHex8Pair; M->unique_pairs = M->pairs;
         }
+        if (!rc && cudaGetLastError() != cudaSuccess) rc = fail("fault->mantle kernels failed to launch");
         if (rc) { delete M; return rc; }
     }
     *out = M;
@@ -745,6 +859,9 @@ static int hex8_smem_optin()
         OQ_CUDA(cudaFuncSetAttribute(gf_mantle_fault_tile_kernel<kStrikeSlip>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHex8SmemBytes));
         OQ_CUDA(cudaFuncSetAttribute(gf_mantle_fault_tile_kernel<kDipSlip>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHex8SmemBytes));
         OQ_CUDA(cudaFuncSetAttribute(gf_mantle_mantle_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHex8SmemBytes));
+        OQ_CUDA(cudaFuncSetAttribute(gf_mantle_fault_class_kernel<kStrikeSlip>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHex8SmemBytes));
+        OQ_CUDA(cudaFuncSetAttribute(gf_mantle_fault_class_kernel<kDipSlip>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHex8SmemBytes));
+        OQ_CUDA(cudaFuncSetAttribute(gf_mantle_mantle_class_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHex8SmemBytes));
         done = true;
     }
     return 0;
@@ -769,15 +886,47 @@ static int build_mantle_fault(const OqHex8Mesh* ma, const OqFaultMesh* mf, doubl
     sincosd(2 * mf->dip, &s2, &c2);
     const double nu = lambda / 2 / (lambda + mu);   // GF.jl:203
     OqMatrix* M = new OqMatrix();
-    if (alloc_matrix(M, OQ_ROWS_FAULT, row_begin, row_end, nf, 6 * ma->n) || M->d.zero()) { delete M; return 1; }
+    if (alloc_matrix(M, OQ_ROWS_FAULT, row_begin, row_end, nf, 6 * ma->n)) { delete M; return 1; }
     if (M->local_rows > 0) {
         const size_t total = (size_t)ma->n * M->local_rows;
+        const int mode = hex8_mode();
+        M->pairs = (long long)total;
+        // classes of (fault cell, hex8 cell) pairs: x group = (x_f - q_x, dx), (y,z) group = (y_f - q_y, dy, z_f, q_z, dz)
+        Hex8PairClasses pc;
+        bool built = false;
+        if (mode == kHex8Auto || mode == kHex8Classes) built = mantle_fault_classes(ma, mf, row_begin, row_end, pc);
+        const bool classes = hex8_use_classes(mode, built, pc, 6);
         DevHex8Tiles tiles;
-        const bool tiled = hex8_tiles_enabled();
+        const bool tiled = !classes && mode != kHex8Pair;
+        if (!classes && M->d.zero()) { delete M; return 1; }
         if (tiled && tiles.build(ma)) { delete M; return 1; }
+        DevPairClasses dpc;
+        DevBuf<double> table;
+        if (classes && (dpc.upload(pc) || table.alloc((size_t)pc.classes * 6))) { delete M; return 1; }
         EventTimer tm;
         int rc = tm.start();
-        if (!rc && tiled) {
+        if (!rc && classes) {
+            const unsigned nb = (unsigned)((pc.classes + kHex8Threads - 1) / kHex8Threads);
+            if (ftype == OQ_STRIKE_SLIP)
+                gf_mantle_fault_class_kernel<kStrikeSlip><<<nb, kHex8Threads, kHex8SmemBytes>>>(
+                    dma.g, dmf.g, dpc.rep_r1.p, dpc.rep_s1.p, dpc.rep_r23.p, dpc.rep_s23.p, pc.g1.n, pc.g23.n, mu, nu,
+                    ftype, s1, c1, s2, c2, table.p);
+            else
+                gf_mantle_fault_class_kernel<kDipSlip><<<nb, kHex8Threads, kHex8SmemBytes>>>(
+                    dma.g, dmf.g, dpc.rep_r1.p, dpc.rep_s1.p, dpc.rep_r23.p, dpc.rep_s23.p, pc.g1.n, pc.g23.n, mu, nu,
+                    ftype, s1, c1, s2, c2, table.p);
+            g_launches.fetch_add(1);
+            rc = tm.stop(&M->table_ms);
+            if (!rc) rc = tm.start();
+            if (!rc) {
+                dim3 grid((unsigned)std::min<size_t>(((size_t)ma->n + 255) / 256, 64), (unsigned)std::min(M->local_rows, 65535));
+                expand_classes_kernel<1, 6><<<grid, 256>>>(table.p, dpc.v, M->local_rows, ma->n, M->ld, M->d.p);
+                g_launches.fetch_add(1);
+                rc = tm.stop(&M->expand_ms);
+            }
+            M->kernel_ms = M->table_ms + M->expand_ms;
+            M->path = kHex8Classes; M->unique_pairs = pc.classes;
+        } else if (!rc && tiled) {
             // receivers per CTA: enough CTAs to fill the GPU several times over, tile data reused across the run
             int rpc = 16;
             while (rpc > 1 && (long long)tiles.v.ntiles * ((M->local_rows + rpc - 1) / rpc) < 148LL * 2 * 8) rpc >>= 1;
@@ -790,6 +939,7 @@ static int build_mantle_fault(const OqHex8Mesh* ma, const OqFaultMesh* mf, doubl
                     tiles.v, dma.g, dmf.g, mu, nu, ftype, s1, c1, s2, c2, row_begin, M->local_rows, rpc, M->ld, M->d.p);
             g_launches.fetch_add(1);
             rc = tm.stop(&M->kernel_ms);
+            M->path = kHex8Tile; M->unique_pairs = M->pairs;
         } else if (!rc) {
             const unsigned nb = (unsigned)((total + kHex8Threads - 1) / kHex8Threads);
             if (ftype == OQ_STRIKE_SLIP)
@@ -800,7 +950,9 @@ static int build_mantle_fault(const OqHex8Mesh* ma, const OqFaultMesh* mf, doubl
                     dma.g, dmf.g, mu, nu, ftype, s1, c1, s2, c2, row_begin, M->local_rows, M->ld, M->d.p);
             g_launches.fetch_add(1);
             rc = tm.stop(&M->kernel_ms);
+            M->path = kHex8Pair; M->unique_pairs = M->pairs;
         }
+        if (!rc && cudaGetLastError() != cudaSuccess) rc = fail("hex8 mantle->fault kernels failed to launch");
         if (rc) { delete M; return rc; }
     }
     *out = M;
@@ -840,15 +992,43 @@ static int build_mantle_mantle(const OqHex8Mesh* ma, const OqQuadrature* quad, d
     const double nu = lambda / 2 / (lambda + mu);   // GF.jl:259
     const int nel = e_end - e_begin;
     OqMatrix* M = new OqMatrix();
-    if (alloc_matrix(M, OQ_ROWS_MANTLE, e_begin, e_end, 6 * ma->n, 6 * ma->n) || M->d.zero()) { delete M; return 1; }
+    if (alloc_matrix(M, OQ_ROWS_MANTLE, e_begin, e_end, 6 * ma->n, 6 * ma->n)) { delete M; return 1; }
     if (nel > 0) {
         const size_t total = (size_t)ma->n * nel;
+        const int mode = hex8_mode();
+        M->pairs = (long long)total;
+        // classes of (receiver cell, source cell) pairs: x group = (c_x - q_x, receiver dx, source dx),
+        // (y,z) group = (c_y - q_y, both dy, receiver c_z and dz, source q_z and dz)
+        Hex8PairClasses pc;
+        bool built = false;
+        if (mode == kHex8Auto || mode == kHex8Classes) built = mantle_mantle_classes(ma, e_begin, e_end, pc);
+        const bool classes = hex8_use_classes(mode, built, pc, 36);
         DevHex8Tiles tiles;
-        const bool tiled = hex8_tiles_enabled();
+        const bool tiled = !classes && mode != kHex8Pair;
+        if (!classes && M->d.zero()) { delete M; return 1; }
         if (tiled && tiles.build(ma)) { delete M; return 1; }
+        DevPairClasses dpc;
+        DevBuf<double> table;
+        if (classes && (dpc.upload(pc) || table.alloc((size_t)pc.classes * 36))) { delete M; return 1; }
         EventTimer tm;
         int rc = tm.start();
-        if (!rc && tiled) {
+        if (!rc && classes) {
+            const unsigned nb = (unsigned)((pc.classes + kHex8Threads - 1) / kHex8Threads);
+            gf_mantle_mantle_class_kernel<<<nb, kHex8Threads, kHex8SmemBytes>>>(
+                dma.g, dpc.rep_r1.p, dpc.rep_s1.p, dpc.rep_r23.p, dpc.rep_s23.p, pc.g1.n, pc.g23.n, mu, nu, dq.c.p,
+                dq.w.p, dq.nq, table.p);
+            g_launches.fetch_add(1);
+            rc = tm.stop(&M->table_ms);
+            if (!rc) rc = tm.start();
+            if (!rc) {
+                dim3 grid((unsigned)std::min<size_t>(((size_t)ma->n + 255) / 256, 64), (unsigned)std::min(nel, 65535));
+                expand_classes_kernel<6, 6><<<grid, 256>>>(table.p, dpc.v, nel, ma->n, M->ld, M->d.p);
+                g_launches.fetch_add(1);
+                rc = tm.stop(&M->expand_ms);
+            }
+            M->kernel_ms = M->table_ms + M->expand_ms;
+            M->path = kHex8Classes; M->unique_pairs = pc.classes;
+        } else if (!rc && tiled) {
             int rpc = 16;
             while (rpc > 1 && (long long)tiles.v.ntiles * ((nel + rpc - 1) / rpc) < 148LL * 2 * 8) rpc >>= 1;
             dim3 grid((unsigned)tiles.v.ntiles, (unsigned)((nel + rpc - 1) / rpc));
@@ -856,12 +1036,15 @@ static int build_mantle_mantle(const OqHex8Mesh* ma, const OqQuadrature* quad, d
                                                                                  e_begin, nel, rpc, M->ld, M->d.p);
             g_launches.fetch_add(1);
             rc = tm.stop(&M->kernel_ms);
+            M->path = kHex8Tile; M->unique_pairs = M->pairs;
         } else if (!rc) {
             gf_mantle_mantle_kernel<<<(unsigned)((total + kHex8Threads - 1) / kHex8Threads), kHex8Threads, kHex8SmemBytes>>>(dma.g, mu, nu, dq.c.p, dq.w.p, dq.nq,
                                                                               e_begin, nel, M->ld, M->d.p);
             g_launches.fetch_add(1);
             rc = tm.stop(&M->kernel_ms);
+            M->path = kHex8Pair; M->unique_pairs = M->pairs;
         }
+        if (!rc && cudaGetLastError() != cudaSuccess) rc = fail("hex8 mantle->mantle kernels failed to launch");
         if (rc) { delete M; return rc; }
     }
     *out = M;
@@ -997,6 +1180,38 @@ int oq_matrix_kernel_ms(const OqMatrix* a, double* ms)
 {
     OQ_CHECK(a && ms, "NULL argument");
     *ms = a->kernel_ms;
+    return 0;
+}
+
+int oq_hex8_pair_classes(const OqHex8Mesh* ma, const OqFaultMesh* mf, int begin, int end, int n, const int* recv,
+                          const int* src, int* rep_recv_x, int* rep_src_x, int* rep_recv_yz, int* rep_src_yz,
+                          long long* counts)
+{
+    OQ_CHECK(ma && ma->n > 0 && counts, "NULL argument");
+    OQ_CHECK(n >= 0 && (n == 0 || (recv && src && rep_recv_x && rep_src_x && rep_recv_yz && rep_src_yz)), "NULL argument");
+    const int limit = mf ? mf->nx * mf->nxi : ma->n;
+    OQ_CHECK(0 <= begin && begin < end && end <= limit, "receiver range [%d,%d) outside [0,%d)", begin, end, limit);
+    Hex8PairClasses pc;
+    const bool built = mf ? mantle_fault_classes(ma, mf, begin, end, pc) : mantle_mantle_classes(ma, begin, end, pc);
+    counts[0] = built ? pc.g1.n : 0; counts[1] = built ? pc.g23.n : 0;
+    counts[2] = (long long)(end - begin) * ma->n;
+    if (!built) return 0;
+    for (int k = 0; k < n; ++k) {
+        OQ_CHECK(begin <= recv[k] && recv[k] < end && 0 <= src[k] && src[k] < ma->n, "sample pair %d out of range", k);
+        const int r = recv[k] - begin;
+        const int c1 = pc.g1.D[(size_t)pc.g1.rcls[r] * pc.g1.ns + pc.g1.scls[src[k]]];
+        const int c23 = pc.g23.D[(size_t)pc.g23.rcls[r] * pc.g23.ns + pc.g23.scls[src[k]]];
+        rep_recv_x[k] = pc.g1.rep_r[c1]; rep_src_x[k] = pc.g1.rep_s[c1];
+        rep_recv_yz[k] = pc.g23.rep_r[c23]; rep_src_yz[k] = pc.g23.rep_s[c23];
+    }
+    return 0;
+}
+
+int oq_matrix_assembly_info(const OqMatrix* a, OqAssemblyInfo* info)
+{
+    OQ_CHECK(a && info, "NULL argument");
+    info->path = a->path; info->pairs = a->pairs; info->unique_pairs = a->unique_pairs;
+    info->table_ms = a->table_ms; info->expand_ms = a->expand_ms; info->kernel_ms = a->kernel_ms;
     return 0;
 }
 

@@ -136,15 +136,17 @@ gf_fault_mantle_kernel(FaultGeom f, Hex8Geom a, OkadaParams p, const double* __r
     const double hx = a.dx[e] / 2, hy = a.dy[e] / 2, hz = a.dz[e] / 2;
     double s[6] = {0, 0, 0, 0, 0, 0};
     for (int w = 0; w < nq; ++w) {
-        const double rx = cx + qc[3 * w] * hx;
+        // strike coordinates: product and sum rounded separately in BOTH builds (no FMA contraction), so that the
+        // host can form the very same differences x - al when it sorts the pairs into classes (greens_classes.cuh)
+        const double rx = __dadd_rn(cx, __dmul_rn(qc[3 * w], hx));
         const double ry = cy + qc[3 * w + 1] * hy;
         const double rz = cz + qc[3 * w + 2] * hz;
         double g[9];
 #pragma unroll
         for (int k = 0; k < 9; ++k) g[k] = 0.0;
         for (int r = -p.nrept; r <= p.nrept; ++r) {
-            const double jump = r * p.lrept;
-            okada_image<SLIP, STRICT>(p.m, rx, ry, rz, f.dep, al1 + jump, al2 + jump, aw1, aw2, g);
+            const double jump = __dmul_rn((double)r, p.lrept);
+            okada_image<SLIP, STRICT>(p.m, rx, ry, rz, f.dep, __dadd_rn(al1, jump), __dadd_rn(al2, jump), aw1, aw2, g);
         }
         okada_finish<STRICT>(g);
         const double lekk = p.lam * (g[0] + g[4] + g[8]);
@@ -161,10 +163,69 @@ gf_fault_mantle_kernel(FaultGeom f, Hex8Geom a, OkadaParams p, const double* __r
 }
 
 
+// ---- K2'': fault -> mantle on CLASSES of pairs (greens_classes.cuh) ----------------------------------------------
+// dc3d reads the strike coordinate of receiver and source only through x - al1, x - al2 (DC3D: XI(1) = X - AL1,
+// XI(2) = X - AL2), for every periodic image.  Pairs whose differences are BITWISE equal therefore have bitwise
+// equal entries: one evaluation per class on the coordinates of a representative pair, the same code as K2, and
+// the table entry is bit-identical to what K2 writes for every pair of the class.  T[k][u23][u1].
+template <int SLIP, bool STRICT>
+__global__ void __launch_bounds__(128, STRICT ? OQ_OKADA_STRICT_MINB : OQ_OKADA_MINB)
+gf_fault_mantle_class_kernel(FaultGeom f, Hex8Geom a, OkadaParams p, const double* __restrict__ qc,
+                             const double* __restrict__ qw, int nq, const int* __restrict__ rep_r1,
+                             const int* __restrict__ rep_s1, const int* __restrict__ rep_r23,
+                             const int* __restrict__ rep_s23, int n1, int n23, double* __restrict__ T)
+{
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)n1 * n23) return;
+    const int u1 = (int)(t % n1), u23 = (int)(t / n1);
+    const int e1 = rep_r1[u1], e23 = rep_r23[u23];
+    const int q1 = rep_s1[u1] % f.nx, q2 = rep_s23[u23] / f.nx;
+    const double al1 = f.ax0[q1], al2 = f.ax1[q1], aw1 = f.axi0[q2], aw2 = f.axi1[q2];
+    const double cx = a.cx[e1], cy = a.cy[e23], cz = a.cz[e23];
+    const double hx = a.dx[e1] / 2, hy = a.dy[e23] / 2, hz = a.dz[e23] / 2;
+    double s[6] = {0, 0, 0, 0, 0, 0};
+    for (int w = 0; w < nq; ++w) {
+        // strike coordinates: product and sum rounded separately in BOTH builds (no FMA contraction), so that the
+        // host can form the very same differences x - al when it sorts the pairs into classes (greens_classes.cuh)
+        const double rx = __dadd_rn(cx, __dmul_rn(qc[3 * w], hx));
+        const double ry = cy + qc[3 * w + 1] * hy;
+        const double rz = cz + qc[3 * w + 2] * hz;
+        double g[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) g[k] = 0.0;
+        for (int r = -p.nrept; r <= p.nrept; ++r) {
+            const double jump = __dmul_rn((double)r, p.lrept);
+            okada_image<SLIP, STRICT>(p.m, rx, ry, rz, f.dep, __dadd_rn(al1, jump), __dadd_rn(al2, jump), aw1, aw2, g);
+        }
+        okada_finish<STRICT>(g);
+        const double lekk = p.lam * (g[0] + g[4] + g[8]);
+        const double wt = qw[w];
+        s[0] += wt * (lekk + 2.0 * p.mu * g[0]);
+        s[1] += wt * (p.mu * (g[1] + g[3]));
+        s[2] += wt * (p.mu * (g[2] + g[6]));
+        s[3] += wt * (lekk + 2.0 * p.mu * g[4]);
+        s[4] += wt * (p.mu * (g[5] + g[7]));
+        s[5] += wt * (lekk + 2.0 * p.mu * g[8]);
+    }
+    const size_t stride = (size_t)n1 * n23;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) T[(size_t)k * stride + (size_t)u23 * n1 + u1] = s[k];
+}
+
+struct OkadaClassLaunch {
+    const double *qc, *qw;
+    int nq;
+    const int *rep_r1, *rep_s1, *rep_r23, *rep_s23;
+    int n1, n23;
+    double* T;
+};
+
 // launchers of the bit-reproducible instantiations (greens_strict.cu)
 void launch_fault_fault_strict(int ftype, unsigned blocks, size_t smem, const FaultGeom& f, const OkadaParams& p, double* st);
 void launch_fault_mantle_strict(int ftype, unsigned blocks, const FaultGeom& f, const Hex8Geom& a, const OkadaParams& p,
                                 const double* qc, const double* qw, int nq, int e_begin, int nel, size_t ld, double* G);
+void launch_fault_mantle_class_strict(int ftype, const FaultGeom& f, const Hex8Geom& a, const OkadaParams& p,
+                                      const OkadaClassLaunch& c);
 void launch_dc3d_gradient_strict(int ftype, int n, const double* x, const double* y, const double* z, const OkadaMedium& m,
                                  double dep, double al1, double al2, double aw1, double aw2, double* out);
 

@@ -36,6 +36,18 @@ void launch_fault_mantle_strict(int ftype, unsigned blocks, const FaultGeom& f, 
         gf_fault_mantle_kernel<kDipSlip, true><<<blocks, 128>>>(f, a, p, qc, qw, nq, e_begin, nel, ld, G);
 }
 
+void launch_fault_mantle_class_strict(int ftype, const FaultGeom& f, const Hex8Geom& a, const OkadaParams& p,
+                                      const OkadaClassLaunch& c)
+{
+    const unsigned blocks = (unsigned)(((size_t)c.n1 * c.n23 + 127) / 128);
+    if (ftype == OQ_STRIKE_SLIP)
+        gf_fault_mantle_class_kernel<kStrikeSlip, true><<<blocks, 128>>>(f, a, p, c.qc, c.qw, c.nq, c.rep_r1, c.rep_s1, c.rep_r23,
+                                                                         c.rep_s23, c.n1, c.n23, c.T);
+    else
+        gf_fault_mantle_class_kernel<kDipSlip, true><<<blocks, 128>>>(f, a, p, c.qc, c.qw, c.nq, c.rep_r1, c.rep_s1, c.rep_r23,
+                                                                      c.rep_s23, c.n1, c.n23, c.T);
+}
+
 void launch_dc3d_gradient_strict(int ftype, int n, const double* x, const double* y, const double* z, const OkadaMedium& m,
                                  double dep, double al1, double al2, double aw1, double aw2, double* out)
 {

@@ -171,6 +171,20 @@ class DeviceMatrix:
         _lib.check(_lib.load().oq_matrix_rows_to_host(self.handle, int(begin), int(end), _lib.dptr(out)))
         return out
 
+    def kernel_ms(self) -> float:
+        ms = C.c_double()
+        _lib.check(_lib.load().oq_matrix_kernel_ms(self.handle, C.byref(ms)))
+        return ms.value
+
+    def assembly_info(self) -> dict:
+        """How the shard was assembled (oq_matrix_assembly_info): path pair / tile / classes, pairs, closed-form
+        evaluations actually made, device times of the class table and of the dense expansion."""
+        info = _lib.OqAssemblyInfo()
+        _lib.check(_lib.load().oq_matrix_assembly_info(self.handle, C.byref(info)))
+        return {"path": {-1: None, 0: "pair", 1: "tile", 2: "classes"}[info.path], "pairs": info.pairs,
+                "unique_pairs": info.unique_pairs, "table_ms": info.table_ms, "expand_ms": info.expand_ms,
+                "kernel_ms": info.kernel_ms}
+
     def gemv(self, x, y=None) -> np.ndarray:
         """The matvecmul! slot (src/pref.jl:15-21): y = A x, or y += A x when y is given."""
         x = _lib.f64(np.asarray(x).reshape(-1, order="F"))
@@ -281,3 +295,21 @@ def max_real_eigval(dm: "DeviceMatrix", k: int = 1, tol: float = 1e-6, maxiter: 
                         dtype=np.float64)
     vals = eigs(op, k=k, which="LR", tol=tol, maxiter=maxiter, return_eigenvectors=False)
     return float(np.max(vals.real))
+
+
+def hex8_pair_classes(ma, mf=None, begin=0, end=None, recv=(), src=()):
+    """Host-only view of the class decomposition behind device_mantle_mantle (mf=None) / device_mantle_fault
+    (oq_hex8_pair_classes): (counts, rep_recv_x, rep_src_x, rep_recv_yz, rep_src_yz) for the sample pairs."""
+    end = (len(ma) if mf is None else mf.nx * mf.nxi) if end is None else end
+    recv = np.ascontiguousarray(recv, dtype=np.int32)
+    src = np.ascontiguousarray(src, dtype=np.int32)
+    n = recv.size
+    reps = [np.zeros(max(n, 1), dtype=np.int32) for _ in range(4)]
+    counts = np.zeros(3, dtype=np.int64)
+    ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))   # noqa: E731
+    cma = ma.c_struct()
+    cmf = mf.c_struct() if mf is not None else None
+    _lib.check(_lib.load().oq_hex8_pair_classes(C.byref(cma), C.byref(cmf) if cmf is not None else None, int(begin), int(end),
+                                                int(n), ip(recv), ip(src), *[ip(r) for r in reps],
+                                                counts.ctypes.data_as(C.POINTER(C.c_longlong))))
+    return (counts,) + tuple(r[:n] for r in reps)

@@ -1,4 +1,6 @@
-"""Assembly kernels at a moderate size (for ncu captures and timing): K1..K4 once each."""
+"""Assembly kernels at a moderate size (for ncu captures and timing): K1..K4 once each; the hex8 builders on their
+default path (class tables + expansion) and with every pair through the tiled / per-pair kernels."""
+import os
 import sys
 sys.path.insert(0, ".")
 import numpy as np
@@ -15,11 +17,17 @@ for ft in (oq.StrikeSlip(), oq.DipSlip(), oq.StrikeSlip(), oq.DipSlip()):
 fsm = W.FaultSpec(64e3, 16e3, 1000.0, 1000.0)
 mfm = oq.gen_mesh("RectOkada", fsm.x, fsm.xi, fsm.dx, fsm.dxi, fsm.dip)
 ma = oq.gen_mesh("BEMHex8Mesh", *W.box_for(32, 8, 8, fsm).args())
-import ctypes as C
-def kms(m):
-    ms = C.c_double(); oq._lib.check(oq._lib.load().oq_matrix_kernel_ms(m.handle, C.byref(ms))); return ms.value
-for name, b in (("K2", lambda: oq.device_fault_mantle(mfm, ma, W.LAM, W.MU, buffer_ratio=1.0)),
-                ("K3", lambda: oq.device_mantle_fault(ma, mfm, W.LAM, W.MU)),
-                ("K4", lambda: oq.device_mantle_mantle(ma, W.LAM, W.MU))):
-    m = b(); ms = kms(m)
-    print(name, (m.local_rows, m.cols), ms, "ms", m.local_rows * m.cols / ms * 1e3, "entries/s"); m.free()
+modes = sys.argv[1:] or ["", "tile"]
+for mode in modes:
+    os.environ["OQ_HEX8"] = mode
+    os.environ["OQ_FAULT_MANTLE"] = "pair" if mode in ("tile", "pair") else ""
+    for name, b in (("K2", lambda: oq.device_fault_mantle(mfm, ma, W.LAM, W.MU, buffer_ratio=1.0)),
+                    ("K3", lambda: oq.device_mantle_fault(ma, mfm, W.LAM, W.MU)),
+                    ("K4", lambda: oq.device_mantle_mantle(ma, W.LAM, W.MU)),
+                    ("K4g2", lambda: oq.device_mantle_mantle(ma, W.LAM, W.MU, qtype="Gauss2"))):
+        for rep in range(2):
+            m = b(); ms = m.kernel_ms(); info = m.assembly_info()
+            print(name, f"mode={mode!r}", (m.local_rows, m.cols), "%.4f ms" % ms, "%.3e entries/s" % (m.local_rows * m.cols / ms * 1e3),
+                  info["path"], info["unique_pairs"], "table %.4f expand %.4f ms" % (info["table_ms"], info["expand_ms"]),
+                  ("expand %.0f GB/s" % (m.local_rows * m.cols * 8 / info["expand_ms"] / 1e6)) if info["expand_ms"] else "")
+            m.free()

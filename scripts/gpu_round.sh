@@ -15,6 +15,6 @@ if [[ " $* " == *" ncu "* ]]; then
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:matvec_panel -s 5 -c 2 -f -o gpurun_out/prof_matvec \
       python bench.py --steps 10 --warmup 3 --no-extra --no-cpu --no-parity > gpurun_out/ncu_matvec.log 2>&1
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:"gf_fault_fault|gf_fault_mantle|gf_mantle_fault|gf_mantle_mantle" \
-      -c 7 -f -o gpurun_out/prof_assembly python scripts/assembly_probe.py > gpurun_out/ncu_assembly.log 2>&1
+      -c 12 -f -o gpurun_out/prof_assembly python scripts/assembly_probe.py > gpurun_out/ncu_assembly.log 2>&1
   ls -la gpurun_out/*.ncu-rep
 fi

@@ -210,3 +210,40 @@ def test_fast_okada_twin(gpu):
                           "-k", "dc3d or fault_fault or fault_mantle or dense_expansion"],
                          env={**os.environ, "OQ_OKADA": "fast"}, capture_output=True, text=True, timeout=900, cwd=root)
     assert res.returncode == 0, res.stdout[-2000:]
+
+
+def test_fault_mantle_class_tables_are_bit_identical(gpu, monkeypatch):
+    """K2'' (csrc/greens_classes.cuh): dc3d sees the strike coordinates only through x - al1, x - al2, so pairs whose
+    differences are bitwise equal share their six entries: one evaluation per class, copied into the dense shard.
+    Every entry is bit-identical to the per-pair kernel's (and hence to the oracle), Gauss1 and Gauss2 receivers,
+    vertical and dipping faults, periodic images, element shards."""
+    oq = gpu
+    cases = [(W.FaultSpec(40e3, 8e3, 2e3, 2e3, 90.0), "Gauss1", 2, 1.0), (W.FaultSpec(40e3, 8e3, 2e3, 2e3, 90.0), "Gauss2", 2, 1.0),
+             (W.FaultSpec(40e3, 8e3, 2.5e3, 2e3, 60.0), "Gauss2", 0, 0.0)]      # last: incommensurate grids
+    for fs, quad, nrept, br in cases:
+        mf_o, mf_p, ma_o, ma_p = meshes(oq, fs, W.box_for(10, 4, 4, fs))
+        out = {}
+        for mode in ("classes", "pair", ""):
+            monkeypatch.setenv("OQ_FAULT_MANTLE", mode)
+            m = oq.device_fault_mantle(mf_p, ma_p, W.LAM, W.MU, qtype=quad, nrept=nrept, buffer_ratio=br)
+            info = m.assembly_info()
+            out[mode] = m.to_host()
+            m.free()
+            if mode:
+                assert info["path"] == mode, (mode, info)
+            elif quad == "Gauss1":
+                # receivers on cell centres of a uniform box: every pair is a translate of a few (Gauss points sit at
+                # irrational offsets, whose differences round differently from cell to cell: fewer bitwise-equal pairs,
+                # and the default keeps the per-pair kernel when fewer than 4 pairs share a class)
+                assert info["path"] == "classes" and 4 * info["unique_pairs"] <= info["pairs"], info
+        assert np.array_equal(out["classes"], out["pair"]) and np.array_equal(out[""], out["pair"])
+        if EXACT:
+            q = ref.gauss_quadrature(int(quad[-1]))
+            want = ref.gf_fault_mantle(mf_o, ma_o, W.LAM, W.MU, ftype=0, quad=q, nrept=nrept, buffer_ratio=br)
+            assert np.array_equal(out[""], want)
+        monkeypatch.setenv("OQ_FAULT_MANTLE", "")
+        ne = len(ma_p)
+        for e0, e1 in ((0, 33), (33, ne)):
+            part = oq.device_fault_mantle(mf_p, ma_p, W.LAM, W.MU, qtype=quad, nrept=nrept, buffer_ratio=br, elems=(e0, e1)).to_host()
+            for k in range(6):
+                assert np.array_equal(part[k * (e1 - e0): (k + 1) * (e1 - e0)], out[""][k * ne + e0: k * ne + e1])

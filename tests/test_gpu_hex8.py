@@ -191,18 +191,76 @@ def test_edge_line_regularisation(gpu):
         assert np.max(np.abs(s - want_q)) < 2e-5 * np.max(np.abs(want_q))
 
 
-def test_pair_kernel_twin(gpu):
-    """the one-thread-per-pair hex8 kernels of round 1 (OQ_HEX8=pair) stay correct next to the tiled default; the
-    switch is read once per process, hence the subprocess"""
+@pytest.mark.parametrize("twin", ["pair", "tile"])
+def test_kernel_twins(gpu, twin):
+    """the one-thread-per-pair kernels of round 1 (OQ_HEX8=pair) and the tiled kernels (OQ_HEX8=tile) stay correct
+    next to the class-table default: the same parity tests, the path forced through the environment"""
     import subprocess
     import sys
-    if os.environ.get("OQ_HEX8") == "pair":
-        pytest.skip("already the twin")
+    if os.environ.get("OQ_HEX8"):
+        pytest.skip("already a twin")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     res = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-q", "-x",
                           "-k", "mantle_fault or mantle_mantle or call_patterns"],
-                         env={**os.environ, "OQ_HEX8": "pair"}, capture_output=True, text=True, timeout=900, cwd=root)
+                         env={**os.environ, "OQ_HEX8": twin}, capture_output=True, text=True, timeout=900, cwd=root)
     assert res.returncode == 0, res.stdout[-2000:]
+
+
+def test_class_tables_equal_the_pair_kernels(gpu, monkeypatch):
+    """K3''/K4'' (csrc/greens_classes.cuh): one closed-form evaluation per translation class of pairs, copied into the
+    dense shard.  Same entries as the per-pair kernels up to the rounding of the representative's coordinates
+    (measured 5e-13 of a column's scale with Gauss2 receivers; bound 1e-11), on a structured box with graded layers, Gauss1 and Gauss2 receivers, a vertical and
+    a dipping fault, full matrices and row shards; the default picks the tables here and the tiles on a mesh
+    without structure."""
+    oq = gpu
+    fs = W.FaultSpec(40e3, 8e3, 2e3, 2e3, 60.0)           # 2 km fault cells under 4 km mantle cells: commensurate grids
+    mf_o, mf_p, ma_o, ma_p = meshes(oq, fs, W.box_for(10, 4, 4, fs))
+    _, mfv_p, _, _ = meshes(oq, W.FaultSpec(40e3, 8e3, 2e3, 2e3, 90.0), W.C2_BOX)
+    builders = {
+        "gf22_gauss1": lambda **kw: oq.device_mantle_mantle(ma_p, W.LAM, W.MU, **kw),
+        "gf22_gauss2": lambda **kw: oq.device_mantle_mantle(ma_p, W.LAM, W.MU, qtype="Gauss2", **kw),
+        "gf21_dipping_ss": lambda **kw: oq.device_mantle_fault(ma_p, mf_p, W.LAM, W.MU, **kw),
+        "gf21_dipping_ds": lambda **kw: oq.device_mantle_fault(ma_p, mf_p, W.LAM, W.MU, ftype=oq.DipSlip(), **kw),
+        "gf21_vertical": lambda **kw: oq.device_mantle_fault(ma_p, mfv_p, W.LAM, W.MU, **kw),
+    }
+    for name, build in builders.items():
+        out = {}
+        for mode in ("classes", "pair", ""):
+            monkeypatch.setenv("OQ_HEX8", mode)
+            m = build()
+            info = m.assembly_info()
+            out[mode] = m.to_host()
+            m.free()
+            assert info["path"] == ("classes" if mode in ("classes", "") else "pair"), (name, mode, info)
+            if mode != "pair":
+                assert info["unique_pairs"] < info["pairs"] and info["table_ms"] > 0 and info["expand_ms"] > 0
+            if mode == "":
+                assert 4 * info["unique_pairs"] <= info["pairs"]
+        assert np.array_equal(out["classes"], out[""])
+        assert scaled_err(out["classes"], out["pair"], axis=0) < 1e-11, name
+    # row shards decompose on their own receivers and tile the full matrix
+    monkeypatch.setenv("OQ_HEX8", "")
+    full = oq.device_mantle_mantle(ma_p, W.LAM, W.MU).to_host()
+    ne = len(ma_p)
+    for e0, e1 in ((0, 33), (33, 160)):
+        part = oq.device_mantle_mantle(ma_p, W.LAM, W.MU, elems=(e0, e1)).to_host()
+        for k in range(6):
+            assert np.array_equal(part[k * (e1 - e0): (k + 1) * (e1 - e0)], full[k * ne + e0: k * ne + e1])
+    nf = mf_p.nx * mf_p.nxi
+    full21 = oq.device_mantle_fault(ma_p, mf_p, W.LAM, W.MU).to_host()
+    parts = [oq.device_mantle_fault(ma_p, mf_p, W.LAM, W.MU, rows=r).to_host() for r in ((0, 21), (21, nf))]
+    assert np.array_equal(np.concatenate(parts, axis=0), full21)
+    # the padding columns of the shard are zero (the matvec streams whole 128-byte lines): gemv == host product
+    d22 = oq.device_mantle_mantle(ma_p, W.LAM, W.MU)
+    x = np.random.default_rng(3).standard_normal(6 * ne)
+    np.testing.assert_allclose(d22.gemv(x), full @ x, rtol=1e-12, atol=1e-12 * np.abs(full).max() * np.abs(x).sum())
+    # no structure -> tiles
+    rng = np.random.default_rng(13)
+    n = 40
+    c = rng.random((3, n)) * 1e4
+    d = 100.0 + rng.random((3, n)) * 500.0
+    mi = oq.BEMHex8Mesh(c[0], c[1], -2e4 - c[2], c[0].copy(), c[1] - d[1] / 2, -2e4 - c[2] + d[2] / 2, d[0], d[1], d[2])
+    assert oq.device_mantle_mantle(mi, W.LAM, W.MU).assembly_info()["path"] == "tile"
 
 
 def test_tiles_on_an_irregular_mesh(gpu):

@@ -132,3 +132,67 @@ def test_solve_option_struct_matches_header():
     assert C.sizeof(_lib.OqSolveOptions) == 5 * 8 + 8 + 4 * 4
     assert [f[0] for f in _lib.OqSolveStats._fields_] == ["t", "dt_last", "dt_next", "naccept", "nreject", "nrhs",
                                                          "retcode"]
+
+
+# ---- class decomposition of the hex8 builders (csrc/greens_classes.cuh), host logic, no device -------------------
+def _check_classes(oq, ma, mf, begin, end, rng, n=4000):
+    nrecv_total = len(ma) if mf is None else mf.nx * mf.nxi
+    recv = rng.integers(begin, end, n).astype(np.int32)
+    src = rng.integers(0, len(ma), n).astype(np.int32)
+    counts, rjx, rix, rjyz, riyz = oq.hex8_pair_classes(ma, mf, begin, end, recv, src)
+    assert counts[2] == (end - begin) * len(ma) and end <= nrecv_total
+    if counts[0] == 0:
+        return counts
+    ext = max(np.ptp(ma.qx) + ma.dx.max(), np.ptp(ma.qy) + ma.dy.max(), 1.0)
+    tol = 4e-12 * ext
+    if mf is None:      # receivers = cells: centre and half sizes enter (quadrature points are centre + qc * half size)
+        x_r, y_r, z_r = ma.cx, ma.cy, ma.cz
+        np.testing.assert_allclose(ma.dx[recv], ma.dx[rjx], rtol=2e-12)
+        np.testing.assert_allclose(ma.dy[recv], ma.dy[rjyz], rtol=2e-12)
+        np.testing.assert_allclose(ma.dz[recv], ma.dz[rjyz], rtol=2e-12)
+    else:               # receivers = fault cells f = i + j nx
+        x_r = np.tile(mf.x, mf.nxi)
+        y_r, z_r = np.repeat(mf.y, mf.nx), np.repeat(mf.z, mf.nx)
+    # the pair and its stand-in agree in everything the closed form reads
+    np.testing.assert_allclose(x_r[recv] - ma.qx[src], x_r[rjx] - ma.qx[rix], atol=tol, rtol=0)
+    np.testing.assert_allclose(ma.dx[src], ma.dx[rix], rtol=2e-12)
+    np.testing.assert_allclose(y_r[recv] - ma.qy[src], y_r[rjyz] - ma.qy[riyz], atol=tol, rtol=0)
+    np.testing.assert_allclose(z_r[recv], z_r[rjyz], atol=tol, rtol=0)
+    np.testing.assert_allclose(ma.qz[src], ma.qz[riyz], atol=tol, rtol=0)
+    np.testing.assert_allclose(ma.dy[src], ma.dy[riyz], rtol=2e-12)
+    np.testing.assert_allclose(ma.dz[src], ma.dz[riyz], rtol=2e-12)
+    return counts
+
+
+def test_hex8_pair_classes_structured_box(oq):
+    """transfinite box (mesh.jl:95-130), uniform in x and y, graded in z: (2nx-1)(2ny-1) nz^2 classes for nx ny nz
+    squared pairs; row shards (the multi-GPU builders) decompose on their own receivers"""
+    rng = np.random.default_rng(11)
+    ma = oq.gen_mesh("BEMHex8Mesh", *W.box_for(12, 6, 5).args())
+    counts = _check_classes(oq, ma, None, 0, len(ma), rng)
+    assert counts[0] == 2 * 12 - 1 and counts[1] == (2 * 6 - 1) * 5 * 5
+    counts = _check_classes(oq, ma, None, 100, 217, rng)
+    assert 0 < counts[0] * counts[1] < counts[2]
+
+
+def test_hex8_pair_classes_fault_receivers(oq):
+    """mantle -> fault: vertical and dipping faults (y and z of a fault row are tied together)"""
+    rng = np.random.default_rng(12)
+    ma = oq.gen_mesh("BEMHex8Mesh", *W.box_for(8, 3, 4).args())
+    for dip in (90.0, 60.0):
+        mf = oq.gen_mesh("RectOkada", W.C2_FAULT.x, W.C2_FAULT.xi, W.C2_FAULT.dx, W.C2_FAULT.dxi, dip)
+        counts = _check_classes(oq, ma, mf, 0, mf.nx * mf.nxi, rng)
+        assert counts[0] > 0 and counts[0] * counts[1] <= counts[2]
+        _check_classes(oq, ma, mf, 5, mf.nx * mf.nxi - 3, rng)
+
+
+def test_hex8_pair_classes_irregular_mesh(oq):
+    """cells of random position and size share nothing: every pair is its own class (the builders then keep the
+    tiled kernels), and the stand-in of a pair is the pair itself"""
+    rng = np.random.default_rng(13)
+    n = 40
+    c = rng.random((3, n)) * 1e4
+    d = 100.0 + rng.random((3, n)) * 500.0
+    ma = oq.BEMHex8Mesh(c[0], c[1], -2e4 - c[2], c[0].copy(), c[1] - d[1] / 2, -2e4 - c[2] + d[2] / 2, d[0], d[1], d[2])
+    counts = _check_classes(oq, ma, None, 0, n, rng)
+    assert counts[0] * counts[1] >= counts[2]
