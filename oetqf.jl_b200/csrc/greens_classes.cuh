@@ -79,28 +79,58 @@ struct AxisClasses {
         const int ntr = cluster_values(tr, tol, itr), nts = cluster_values(ts, tol, its);
         rcls = itr; nr = combine_classes(rcls, ntr, ar, nar);
         scls = its; ns = combine_classes(scls, nts, as, nas);
-        if ((size_t)nr * (size_t)ns > max_combos) return false;
+        if ((size_t)nr * (size_t)ns > max_combos || (size_t)ntr * (size_t)nts > max_combos) return false;
         std::vector<int> rr(nr, -1), ss(ns, -1);          // first member of every class
         for (size_t i = 0; i < rcls.size(); ++i) if (rr[rcls[i]] < 0) rr[rcls[i]] = (int)i;
         for (size_t i = 0; i < scls.size(); ++i) if (ss[scls[i]] < 0) ss[scls[i]] = (int)i;
+        // the offset of a combination depends on the VALUE classes of t only: cluster ntr x nts offsets, not nr x ns
+        std::vector<double> vtr(ntr), vts(nts);
+        {
+            std::vector<char> seen_r(ntr, 0), seen_s(nts, 0);
+            for (size_t i = 0; i < itr.size(); ++i) if (!seen_r[itr[i]]) { seen_r[itr[i]] = 1; vtr[itr[i]] = tr[i]; }
+            for (size_t i = 0; i < its.size(); ++i) if (!seen_s[its[i]]) { seen_s[its[i]] = 1; vts[its[i]] = ts[i]; }
+        }
+        std::vector<double> off((size_t)ntr * nts);
+        for (int a = 0; a < ntr; ++a)
+            for (int b = 0; b < nts; ++b) off[(size_t)a * nts + b] = vtr[a] - vts[b];
+        std::vector<int> offc;
+        const int noff = cluster_values(off, tol, offc);
+        // pair class of (a, b) = (offset class, receiver attributes, source attributes), numbered in order of first
+        // appearance (row-major over receiver classes, then source classes)
         const size_t nc = (size_t)nr * ns;
-        std::vector<double> off(nc);
-        std::vector<int> ka(nc), kb(nc);
-        for (int a = 0; a < nr; ++a)
+        D.assign(nc, 0);
+        rep_r.clear(); rep_s.clear();
+        const unsigned long long space = (unsigned long long)noff * (unsigned long long)nar * (unsigned long long)nas;
+        std::vector<int> direct;
+        std::vector<std::pair<long long, int>> sorted_keys;
+        const bool use_direct = space <= (1ull << 26);
+        if (use_direct) direct.assign((size_t)space, -1);
+        std::vector<long long> keys(use_direct ? 0 : nc);
+        n = 0;
+        for (int a = 0; a < nr; ++a) {
+            const int ia = itr[rr[a]], ka = ar[rr[a]];
             for (int b = 0; b < ns; ++b) {
-                off[(size_t)a * ns + b] = tr[rr[a]] - ts[ss[b]];
-                ka[(size_t)a * ns + b] = ar[rr[a]];
-                kb[(size_t)a * ns + b] = as[ss[b]];
+                const long long key = ((long long)offc[(size_t)ia * nts + its[ss[b]]] * nar + ka) * nas + as[ss[b]];
+                if (use_direct) {
+                    int& c = direct[(size_t)key];
+                    if (c < 0) { c = n++; rep_r.push_back(rr[a]); rep_s.push_back(ss[b]); }
+                    D[(size_t)a * ns + b] = c;
+                } else {
+                    keys[(size_t)a * ns + b] = key;
+                }
             }
-        const int noff = cluster_values(off, tol, D);
-        int nd = combine_classes(D, noff, ka, nar);
-        n = combine_classes(D, nd, kb, nas);
-        rep_r.assign(n, -1); rep_s.assign(n, -1);
-        for (int a = 0; a < nr; ++a)
-            for (int b = 0; b < ns; ++b) {
-                const int c = D[(size_t)a * ns + b];
-                if (rep_r[c] < 0) { rep_r[c] = rr[a]; rep_s[c] = ss[b]; }
+        }
+        if (!use_direct) {      // huge key space: number the keys by sorting, then renumber in order of first appearance
+            std::vector<long long> uniq(keys);
+            std::sort(uniq.begin(), uniq.end());
+            uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+            std::vector<int> first(uniq.size(), -1);
+            for (size_t k = 0; k < nc; ++k) {
+                const size_t u = std::lower_bound(uniq.begin(), uniq.end(), keys[k]) - uniq.begin();
+                if (first[u] < 0) { first[u] = n++; rep_r.push_back(rr[k / ns]); rep_s.push_back(ss[k % ns]); }
+                D[k] = first[u];
             }
+        }
         return true;
     }
 

@@ -212,6 +212,40 @@ function to_host(A::DeviceMatrix)
     out
 end
 
+# how a shard was assembled (include/oetqf_b200.h: OqAssemblyInfo; 48 bytes: Cint + pad, 2 x Int64, 3 x Cdouble)
+struct OqAssemblyInfo
+    path::Cint             # 0 pair, 1 tile, 2 class tables, -1 not an assembled Green's matrix
+    pairs::Int64
+    unique_pairs::Int64    # closed-form evaluations actually made
+    table_ms::Cdouble
+    expand_ms::Cdouble
+    kernel_ms::Cdouble
+end
+
+function assembly_info(A::DeviceMatrix)
+    info = Ref(OqAssemblyInfo(-1, 0, 0, 0.0, 0.0, 0.0))
+    check(ccall((:oq_matrix_assembly_info, LIB), Cint, (Ptr{Cvoid}, Ref{OqAssemblyInfo}), A.h, info))
+    info[]
+end
+
+# host-only view of the translation classes behind device_mantle_mantle (mf === nothing) / device_mantle_fault:
+# the receiver / source whose coordinates stand for each sample pair (0-based indices), and the class counts
+function hex8_pair_classes(ma::BEMHex8Mesh, mf::Union{Nothing,RectOkadaMesh}, range::UnitRange{Int}, recv::Vector{Cint}, src::Vector{Cint})
+    a = cmesh(ma); n = length(recv)
+    reps = [Vector{Cint}(undef, max(n, 1)) for _ in 1:4]; counts = zeros(Clonglong, 3)
+    if mf === nothing
+        GC.@preserve a check(ccall((:oq_hex8_pair_classes, LIB), Cint,
+            (Ref{OqHex8Mesh}, Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Cint}, Ptr{Cint}, Ptr{Cint}, Ptr{Cint}, Ptr{Cint}, Ptr{Cint}, Ptr{Clonglong}),
+            a.s, C_NULL, first(range), last(range), n, recv, src, reps[1], reps[2], reps[3], reps[4], counts))
+    else
+        f = cmesh(mf)
+        GC.@preserve a f check(ccall((:oq_hex8_pair_classes, LIB), Cint,
+            (Ref{OqHex8Mesh}, Ref{OqFaultMesh}, Cint, Cint, Cint, Ptr{Cint}, Ptr{Cint}, Ptr{Cint}, Ptr{Cint}, Ptr{Cint}, Ptr{Cint}, Ptr{Clonglong}),
+            a.s, f.s, first(range), last(range), n, recv, src, reps[1], reps[2], reps[3], reps[4], counts))
+    end
+    counts, reps
+end
+
 # a window of local rows as a row-major matrix (parity checks of shards too large to duplicate)
 function rows_to_host(A::DeviceMatrix, cols::Integer, rows::UnitRange{Int})
     out = Matrix{Float64}(undef, cols, last(rows) - first(rows))     # column-major (cols x rows) == row-major rows x cols

@@ -22,7 +22,9 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--nx", type=int, default=250)
     ap.add_argument("--nxi", type=int, default=80)
-    ap.add_argument("--mantle", type=int, nargs=3, default=[40, 21, 23])   # odd ny: the fault plane y = 0 is not a cell face
+    # odd ny: the fault plane y = 0 is not a cell face; 50 cells along strike = 5 fault cells each (commensurate grids:
+    # the pairs fall into translation classes, csrc/greens_classes.cuh)
+    ap.add_argument("--mantle", type=int, nargs=3, default=[50, 17, 23])
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--out", default="")
@@ -61,6 +63,12 @@ def main():
            "gf12_entries_per_s": d12.local_rows * d12.cols / (kms(d12) * 1e-3),
            "gf21_entries_per_s": d21.local_rows * d21.cols / (kms(d21) * 1e-3),
            "gf22_entries_per_s": d22.local_rows * d22.cols / (kms(d22) * 1e-3)}
+    for key, m in (("gf12", d12), ("gf21", d21), ("gf22", d22)):
+        info = m.assembly_info()
+        asm[key + "_path"] = info["path"]
+        asm[key + "_closed_form_evaluations"] = info["unique_pairs"]
+        asm[key + "_pairs"] = info["pairs"]
+        asm[key + "_table_ms"], asm[key + "_expand_ms"] = info["table_ms"], info["expand_ms"]
     a, b, L, sig = W.fault_properties(mf.x, mf.z, mf.nx, mf.nxi)
     g, n, d0 = W.mantle_properties(ma.cz)
     v, th, eps, sg, dl = W.initial_state(mf.nx, mf.nxi, L, ma.cz, g, n, rng=np.random.default_rng(42))

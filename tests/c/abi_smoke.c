@@ -27,6 +27,7 @@ _Static_assert(sizeof(OqMantleProperty) == 32 && offsetof(OqMantleProperty, gamm
 _Static_assert(sizeof(OqDilatancyProperty) == 32, "OqDilatancyProperty layout");
 _Static_assert(sizeof(OqSolveOptions) == 64 && offsetof(OqSolveOptions, maxiters) == 40 &&
                offsetof(OqSolveOptions, algorithm) == 48 && offsetof(OqSolveOptions, async_snapshots) == 56, "OqSolveOptions layout");
+_Static_assert(sizeof(OqAssemblyInfo) == 48 && offsetof(OqAssemblyInfo, pairs) == 8 && offsetof(OqAssemblyInfo, table_ms) == 24, "OqAssemblyInfo layout");
 _Static_assert(sizeof(OqSolveStats) == 56 && offsetof(OqSolveStats, naccept) == 24 && offsetof(OqSolveStats, retcode) == 48, "OqSolveStats layout");
 
 #define CHECK(call)                                                                         \
@@ -109,6 +110,12 @@ int main(int argc, char **argv)
     CHECK(oq_matrix_fault_mantle(&mf, &ma, NULL, lam, mu, OQ_STRIKE_SLIP, 2, 1.0, 0, NE, &d12));
     CHECK(oq_matrix_mantle_fault(&ma, &mf, lam, mu, OQ_STRIKE_SLIP, 0, NF, &d21));
     CHECK(oq_matrix_mantle_mantle(&ma, NULL, lam, mu, 0, NE, &d22));
+    OqAssemblyInfo info;
+    CHECK(oq_matrix_assembly_info(d22, &info));
+    if (info.path < 0 || info.unique_pairs <= 0 || info.unique_pairs > info.pairs || info.pairs != (int64_t)NE * NE) {
+        fprintf(stderr, "oq_matrix_assembly_info: path %d, %lld of %lld pairs\n", info.path, (long long)info.unique_pairs, (long long)info.pairs);
+        return 1;
+    }
     double xv[6 * NE], yv[NF];
     for (int i = 0; i < 6 * NE; ++i) xv[i] = sin(0.37 * i) * 1e-14;
     CHECK(oq_gemv(d21, xv, yv, 0));
