@@ -317,10 +317,31 @@ def assembly_extras(oq, fp64_peak):
             m.free()
         return best, shape, info
 
-    best, shape, _ = timed(lambda: oq.device_fault_mantle(mfm, ma, W.LAM, W.MU, buffer_ratio=1.0))
+    # Okada fault->mantle.  Default path on commensurate grids: one dc3d evaluation per class of pairs with bitwise
+    # equal arguments + dense expansion (HBM-write bound); its fp64-bound twin (every pair, OQ_FAULT_MANTLE=pair) is
+    # timed beside it against the DFMA peak.
+    saved12 = os.environ.get("OQ_FAULT_MANTLE")
+    build12 = lambda: oq.device_fault_mantle(mfm, ma, W.LAM, W.MU, buffer_ratio=1.0)   # noqa: E731
+    best, shape, info = timed(build12)
     n = shape[0] * shape[1]
-    out["okada_fault_mantle"] = {"shape": list(shape), "kernel_ms": best, "entries_per_s": n / (best * 1e-3),
-                                 "roofline": _fp64_roofline("gf_fault_mantle_kernel<0>", n, best, fp64_peak, flops)}
+    rec = {"shape": list(shape), "kernel_ms": best, "entries_per_s": n / (best * 1e-3), "path": info["path"],
+           "pairs": info["pairs"], "closed_form_evaluations": info["unique_pairs"], "table_ms": info["table_ms"],
+           "expand_ms": info["expand_ms"], "roofline": None}
+    if info["path"] == "classes" and info["expand_ms"] > 0:
+        gbs = n * 8 / (info["expand_ms"] * 1e-3) / 1e9
+        rec["roofline"] = {"bound": "hbm", "kernel": "expand_classes_kernel", "achieved": gbs, "peak": hbm_peak,
+                           "unit": "GB/s", "frac": gbs / hbm_peak, "algorithmic_bytes": n * 8, "peak_source": hbm_src}
+    else:
+        rec["roofline"] = _fp64_roofline("gf_fault_mantle_kernel<0>", n, best, fp64_peak, flops)
+    os.environ["OQ_FAULT_MANTLE"] = "pair"
+    pbest, _, pinfo = timed(build12)
+    rec["every_pair_kernel"] = {"kernel_ms": pbest, "entries_per_s": n / (pbest * 1e-3), "path": pinfo["path"],
+                                "roofline": _fp64_roofline("gf_fault_mantle_kernel<0>", n, pbest, fp64_peak, flops)}
+    if saved12 is None:
+        os.environ.pop("OQ_FAULT_MANTLE", None)
+    else:
+        os.environ["OQ_FAULT_MANTLE"] = saved12
+    out["okada_fault_mantle"] = rec
     # hex8 builders.  Default path: one closed-form evaluation per translation class of pairs + dense expansion
     # (csrc/greens_classes.cuh) -- bounded by the HBM writes of the shard; its fp64-bound twins (every pair through
     # the tiled kernels, OQ_HEX8=tile) are timed beside it against the DFMA peak.
