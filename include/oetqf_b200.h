@@ -129,6 +129,24 @@ int oq_matrix_mantle_fault(const OqHex8Mesh *ma, const OqFaultMesh *mf, double l
 /* mantle<-mantle (gf22, GF.jl:250-296); rows = elements [e_begin,e_end) x 6 */
 int oq_matrix_mantle_mantle(const OqHex8Mesh *ma, const OqQuadrature *quad, double lambda, double mu,
                             int e_begin, int e_end, OqMatrix **out);
+/* The same three mantle operands kept in CLASS FORM instead of dense storage (csrc/classmat.cuh): the table of the
+ * distinct 6x1 / 1x6 / 6x6 kernels of the matrix plus the maps from a (receiver, source) pair to its translation
+ * class.  The handle is accepted wherever the dense one is -- oq_problem_create_viscoelastic (any mix of dense and
+ * class-form operands), oq_gemv (the matvecmul! slot, pref.jl:15-21), oq_matrix_to_host / _rows_to_host (which expand
+ * on request) -- and multiplies straight from the table: equation.jl:201-203 without streaming (6 N_e)^2 doubles.
+ * The entries are those of the dense builders above, bit for bit (same table, same representatives).  Not in the
+ * reference, which keeps these operands dense (GF.jl:123-296); it exploits the same invariance for the fault only
+ * (GF.jl:31-71).  Returns an error (and no handle) when the mesh has no translation structure to exploit -- fewer
+ * than 4 pairs per class -- or when one (y,z) slab of the table exceeds shared memory: keep the dense form then. */
+int oq_matrix_fault_mantle_classes(const OqFaultMesh *mf, const OqHex8Mesh *ma, const OqQuadrature *quad, double lambda,
+                                   double mu, int ftype, int nrept, double buffer_ratio, int e_begin, int e_end,
+                                   OqMatrix **out);
+int oq_matrix_mantle_fault_classes(const OqHex8Mesh *ma, const OqFaultMesh *mf, double lambda, double mu, int ftype,
+                                   int row_begin, int row_end, OqMatrix **out);
+int oq_matrix_mantle_mantle_classes(const OqHex8Mesh *ma, const OqQuadrature *quad, double lambda, double mu,
+                                    int e_begin, int e_end, OqMatrix **out);
+/* form: 0 dense, 1 class form; device_bytes: HBM held by the operand (dense shard, or class table + maps) */
+int oq_matrix_form(const OqMatrix *a, int *form, double *device_bytes);
 /* Upload a user-supplied column-major m x n host matrix (e.g. one loaded from the reference's HDF5
  * cache, examples/otf-with-mantle.jl:39-56).  row_kind says how [row_begin,row_end) is interpreted. */
 int oq_matrix_from_host(const double *a_colmajor, int m, int n, int row_kind, int row_begin, int row_end,

@@ -7,6 +7,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -107,6 +108,38 @@ inline size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
 // sind/cosd on the host with exact values at multiples of 90° (Julia's sincosd)
 void sincosd(double deg, double* s, double* c);
 
+constexpr int kCdG = 8, kCdBlk = 8, kCdSlices = 4;     // class_matvec_diag_kernel: window length, receiver blocks, source slices
+
+// Class form of a Green's operand (classmat.cuh): the table of DISTINCT kernels of a matrix whose (receiver, source)
+// pairs fall into translation classes, and the maps from a pair to its class.  An OqMatrix in this form has no dense
+// storage; the RHS multiplies straight from the table (class_matvec_kernel).
+struct ClassOperand {
+    int K = 1, P = 1;                      // rows per receiver unit, columns per source unit (6x6, 6x1, 1x6)
+    int nr = 0, ns = 0;                    // local receiver units, source units
+    int n1 = 0, n23 = 0, ns1 = 0, ns23 = 0;
+    int ts = 0;                            // doubles per class in Tm (K*P padded so that 128-bit loads of 8 consecutive classes hit 32 distinct banks)
+    DevBuf<double> Tm;                     // [n23][n1][ts]
+    DevBuf<int> rc1, sc1, D1, D23;         // x class of every local receiver / every source; pair-class maps [nr1*ns1], [nr23*ns23]
+    DevBuf<int> rc23, sc23;                // (y,z) classes (dense expansion only)
+    DevBuf<int> sg_order;                  // [nr23][ns23] per row of D23: source groups in ascending class order
+    DevBuf<int> rg_items, sg_ptr, sg_items;// receivers ordered by (y,z) class; sources grouped by (y,z) class (CSR over ns23 groups)
+    DevBuf<int> cta_row, cta_begin, cta_count;   // work list: one CTA = a run of <= rb receivers of one (y,z) class (its row of D23)
+    int nctas = 0, rb = 32, max_sg = 0;
+    size_t smem = 0;
+    double table_bytes = 0;
+    // diagonal fast path (class_matvec_diag_kernel): 6x6 operands whose x classes depend on the DIFFERENCE of integer
+    // x positions only (receivers and sources on one equidistant grid along x: the Toeplitz structure of GF.jl:31-71)
+    bool diag_ok = false;
+    int npos = 0, dL = 0;                  // x positions; source positions per slice (multiple of the window length)
+    DevBuf<int> diag;                      // [2 npos - 1]: (receiver position - source position + npos - 1) -> x class, -1: none
+    DevBuf<int> rg_items_pos;              // receivers ordered by ((y,z) class, x position); every CTA run is contiguous in position
+    DevBuf<int> rpos;                      // [nr] x position of every local receiver
+    DevBuf<int> sg_bypos;                  // [ns23][npos]: the source of a (y,z) group at an x position, -1: none
+    DevBuf<int> dcta_row, dcta_begin, dcta_count;
+    int ndctas = 0;
+    size_t dsmem = 0;
+};
+
 }  // namespace oq
 
 // ---- the opaque handles -----------------------------------------------------------------------
@@ -122,4 +155,5 @@ struct OqMatrix {
     int path = -1;                  // hex8 builders: 0 pair, 1 tile, 2 class-table kernels (-1: not a hex8 matrix)
     long long pairs = 0, unique_pairs = 0;       // (receiver, source) pairs of the shard / closed-form evaluations made
     double table_ms = 0.0, expand_ms = 0.0;      // class path: evaluation of the classes / dense expansion
+    std::unique_ptr<oq::ClassOperand> cls;       // non-null: class form (no dense storage, d is empty)
 };

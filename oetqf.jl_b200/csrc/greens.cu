@@ -625,7 +625,7 @@ static int make_okada_params(const OqFaultMesh* mf, double lam, double mu, int f
     return 0;
 }
 
-static int alloc_matrix(OqMatrix* M, int row_kind, int row_begin, int row_end, int global_rows, int cols)
+static int alloc_matrix(OqMatrix* M, int row_kind, int row_begin, int row_end, int global_rows, int cols, bool dense = true)
 {
     M->row_kind = row_kind; M->row_begin = row_begin; M->row_end = row_end;
     M->global_rows = global_rows; M->cols = cols;
@@ -635,7 +635,7 @@ static int alloc_matrix(OqMatrix* M, int row_kind, int row_begin, int row_end, i
     // on the same HBM channel phase; one extra 128-byte line per row spreads them (OQ_LD_PAD=0 disables).
     static const bool pad = [] { const char* e = getenv("OQ_LD_PAD"); return !(e && e[0] == '0'); }();
     if (pad && M->ld % 1024 == 0) M->ld += 16;
-    return M->d.alloc((size_t)M->local_rows * M->ld);
+    return dense ? M->d.alloc((size_t)M->local_rows * M->ld) : 0;        // class form: no dense storage
 }
 
 // Toeplitz kernel on the device: st[nx*nxi*nxi]
@@ -662,12 +662,24 @@ static int assemble_toeplitz(const OqFaultMesh* mf, double lam, double mu, int f
     return 0;
 }
 
+// dense copy of a class-form shard (parity checks and host copies only; the RHS never expands)
+static int dense_of_class_form(const OqMatrix* M, DevBuf<double>& dense)
+{
+    OQ_TRY(dense.alloc((size_t)M->local_rows * M->ld));
+    OQ_TRY(expand_class_operand(*M->cls, M->ld, dense.p));
+    OQ_CUDA(cudaDeviceSynchronize());
+    return 0;
+}
+
 static int matrix_to_host_colmajor(const OqMatrix* M, double* out)
 {
+    DevBuf<double> dense;
+    if (M->cls) OQ_TRY(dense_of_class_form(M, dense));
+    const double* src = M->cls ? dense.p : M->d.p;
     DevBuf<double> cm;
     OQ_TRY(cm.alloc((size_t)M->local_rows * M->cols));
     dim3 grid((M->cols + 31) / 32, (M->local_rows + 31) / 32), block(32, 8);
-    rowmajor_to_colmajor_kernel<<<grid, block>>>(M->d.p, M->local_rows, M->cols, M->ld, cm.p);
+    rowmajor_to_colmajor_kernel<<<grid, block>>>(src, M->local_rows, M->cols, M->ld, cm.p);
     OQ_LAUNCHED();
     OQ_CUDA(cudaMemcpy(out, cm.p, cm.n * sizeof(double), cudaMemcpyDeviceToHost));
     return 0;
@@ -750,7 +762,7 @@ int oq_matrix_from_toeplitz(const double* st_host, int nx, int nxi, int row_begi
 
 static int build_fault_mantle(const OqFaultMesh* mf, const OqHex8Mesh* ma, const OqQuadrature* quad, double lambda,
                               double mu, int ftype, int nrept, double buffer_ratio, int e_begin, int e_end,
-                              OqMatrix** out)
+                              OqMatrix** out, bool keep = false)
 {
     OQ_CHECK(mf && ma && out, "NULL argument");
     OQ_TRY(enter());
@@ -766,20 +778,21 @@ static int build_fault_mantle(const OqFaultMesh* mf, const OqHex8Mesh* ma, const
     OQ_TRY(dq.upload(quad));
     const int nf = mf->nx * mf->nxi, nel = e_end - e_begin;
     OqMatrix* M = new OqMatrix();
-    if (alloc_matrix(M, OQ_ROWS_MANTLE, e_begin, e_end, 6 * ma->n, nf)) { delete M; return 1; }
+    if (alloc_matrix(M, OQ_ROWS_MANTLE, e_begin, e_end, 6 * ma->n, nf, !keep)) { delete M; return 1; }
     if (nel > 0) {
         const size_t total = (size_t)nf * nel;
         M->pairs = (long long)total;
         // classes of pairs with bitwise equal dc3d arguments (greens_classes.cuh); OQ_FAULT_MANTLE = pair | classes forces
         const char* env = getenv("OQ_FAULT_MANTLE");
-        const int mode = !env || !*env ? kHex8Auto : (strcmp(env, "pair") == 0 ? kHex8Pair : (strcmp(env, "classes") == 0 ? kHex8Classes : kHex8Auto));
+        const int mode = keep ? kHex8Classes : !env || !*env ? kHex8Auto : (strcmp(env, "pair") == 0 ? kHex8Pair : (strcmp(env, "classes") == 0 ? kHex8Classes : kHex8Auto));
         Hex8PairClasses pc;
         bool built = false;
         if (mode != kHex8Pair) {
             static const double c1[3] = {0, 0, 0};
             built = fault_mantle_classes(mf, ma, quad ? quad->coords : c1, dq.nq, nrept, p.lrept, e_begin, e_end, pc);
         }
-        const bool classes = hex8_use_classes(mode, built, pc, 6);
+        const bool classes = hex8_use_classes(mode, built, pc, 6) && (!keep || pc.worthwhile);
+        if (keep && !classes) { delete M; return fail("fault -> mantle: the pairs of these meshes do not fall into translation classes (keep the dense form)"); }
         DevPairClasses dpc;
         DevBuf<double> table;
         if (!classes && M->d.zero()) { delete M; return 1; }
@@ -799,12 +812,17 @@ static int build_fault_mantle(const OqFaultMesh* mf, const OqHex8Mesh* ma, const
                                                                            cl.rep_r23, cl.rep_s23, cl.n1, cl.n23, cl.T);
             g_launches.fetch_add(1);
             rc = tm.stop(&M->table_ms);
+            if (!rc && keep) {
+                M->cls.reset(new ClassOperand());
+                rc = make_class_operand(pc, table, 6, 1, nel, nf, *M->cls);
+            } else {
             if (!rc) rc = tm.start();
             if (!rc) {
                 dim3 grid((unsigned)std::min<size_t>(((size_t)nf + 255) / 256, 64), (unsigned)std::min(nel, 65535));
                 expand_classes_kernel<6, 1><<<grid, 256>>>(table.p, dpc.v, nel, nf, M->ld, M->d.p);
                 g_launches.fetch_add(1);
                 rc = tm.stop(&M->expand_ms);
+            }
             }
             M->kernel_ms = M->table_ms + M->expand_ms;
             M->path = kHex8Classes; M->unique_pairs = pc.classes;
@@ -834,6 +852,13 @@ int oq_matrix_fault_mantle(const OqFaultMesh* mf, const OqHex8Mesh* ma, const Oq
                            OqMatrix** out)
 {
     return build_fault_mantle(mf, ma, quad, lambda, mu, ftype, nrept, buffer_ratio, e_begin, e_end, out);
+}
+
+int oq_matrix_fault_mantle_classes(const OqFaultMesh* mf, const OqHex8Mesh* ma, const OqQuadrature* quad, double lambda,
+                                   double mu, int ftype, int nrept, double buffer_ratio, int e_begin, int e_end,
+                                   OqMatrix** out)
+{
+    return build_fault_mantle(mf, ma, quad, lambda, mu, ftype, nrept, buffer_ratio, e_begin, e_end, out, true);
 }
 
 int oq_gf_fault_mantle(const OqFaultMesh* mf, const OqHex8Mesh* ma, const OqQuadrature* quad, double lambda,
@@ -868,7 +893,7 @@ static int hex8_smem_optin()
 }
 
 static int build_mantle_fault(const OqHex8Mesh* ma, const OqFaultMesh* mf, double lambda, double mu, int ftype,
-                              int row_begin, int row_end, OqMatrix** out)
+                              int row_begin, int row_end, OqMatrix** out, bool keep = false)
 {
     OQ_CHECK(mf && ma && out, "NULL argument");
     OQ_TRY(enter());
@@ -886,16 +911,17 @@ static int build_mantle_fault(const OqHex8Mesh* ma, const OqFaultMesh* mf, doubl
     sincosd(2 * mf->dip, &s2, &c2);
     const double nu = lambda / 2 / (lambda + mu);   // GF.jl:203
     OqMatrix* M = new OqMatrix();
-    if (alloc_matrix(M, OQ_ROWS_FAULT, row_begin, row_end, nf, 6 * ma->n)) { delete M; return 1; }
+    if (alloc_matrix(M, OQ_ROWS_FAULT, row_begin, row_end, nf, 6 * ma->n, !keep)) { delete M; return 1; }
     if (M->local_rows > 0) {
         const size_t total = (size_t)ma->n * M->local_rows;
-        const int mode = hex8_mode();
+        const int mode = keep ? kHex8Classes : hex8_mode();
         M->pairs = (long long)total;
         // classes of (fault cell, hex8 cell) pairs: x group = (x_f - q_x, dx), (y,z) group = (y_f - q_y, dy, z_f, q_z, dz)
         Hex8PairClasses pc;
         bool built = false;
         if (mode == kHex8Auto || mode == kHex8Classes) built = mantle_fault_classes(ma, mf, row_begin, row_end, pc);
-        const bool classes = hex8_use_classes(mode, built, pc, 6);
+        const bool classes = hex8_use_classes(mode, built, pc, 6) && (!keep || pc.worthwhile);
+        if (keep && !classes) { delete M; return fail("mantle -> fault: the pairs of these meshes do not fall into translation classes (keep the dense form)"); }
         DevHex8Tiles tiles;
         const bool tiled = !classes && mode != kHex8Pair;
         if (!classes && M->d.zero()) { delete M; return 1; }
@@ -917,12 +943,17 @@ static int build_mantle_fault(const OqHex8Mesh* ma, const OqFaultMesh* mf, doubl
                     ftype, s1, c1, s2, c2, table.p);
             g_launches.fetch_add(1);
             rc = tm.stop(&M->table_ms);
+            if (!rc && keep) {
+                M->cls.reset(new ClassOperand());
+                rc = make_class_operand(pc, table, 1, 6, M->local_rows, ma->n, *M->cls);
+            } else {
             if (!rc) rc = tm.start();
             if (!rc) {
                 dim3 grid((unsigned)std::min<size_t>(((size_t)ma->n + 255) / 256, 64), (unsigned)std::min(M->local_rows, 65535));
                 expand_classes_kernel<1, 6><<<grid, 256>>>(table.p, dpc.v, M->local_rows, ma->n, M->ld, M->d.p);
                 g_launches.fetch_add(1);
                 rc = tm.stop(&M->expand_ms);
+            }
             }
             M->kernel_ms = M->table_ms + M->expand_ms;
             M->path = kHex8Classes; M->unique_pairs = pc.classes;
@@ -965,6 +996,12 @@ int oq_matrix_mantle_fault(const OqHex8Mesh* ma, const OqFaultMesh* mf, double l
     return build_mantle_fault(ma, mf, lambda, mu, ftype, row_begin, row_end, out);
 }
 
+int oq_matrix_mantle_fault_classes(const OqHex8Mesh* ma, const OqFaultMesh* mf, double lambda, double mu, int ftype,
+                                   int row_begin, int row_end, OqMatrix** out)
+{
+    return build_mantle_fault(ma, mf, lambda, mu, ftype, row_begin, row_end, out, true);
+}
+
 int oq_gf_mantle_fault(const OqHex8Mesh* ma, const OqFaultMesh* mf, double lambda, double mu, int ftype,
                        double* outp, double* kernel_ms)
 {
@@ -978,7 +1015,7 @@ int oq_gf_mantle_fault(const OqHex8Mesh* ma, const OqFaultMesh* mf, double lambd
 }
 
 static int build_mantle_mantle(const OqHex8Mesh* ma, const OqQuadrature* quad, double lambda, double mu,
-                               int e_begin, int e_end, OqMatrix** out)
+                               int e_begin, int e_end, OqMatrix** out, bool keep = false)
 {
     OQ_CHECK(ma && out, "NULL argument");
     OQ_TRY(enter());
@@ -992,17 +1029,18 @@ static int build_mantle_mantle(const OqHex8Mesh* ma, const OqQuadrature* quad, d
     const double nu = lambda / 2 / (lambda + mu);   // GF.jl:259
     const int nel = e_end - e_begin;
     OqMatrix* M = new OqMatrix();
-    if (alloc_matrix(M, OQ_ROWS_MANTLE, e_begin, e_end, 6 * ma->n, 6 * ma->n)) { delete M; return 1; }
+    if (alloc_matrix(M, OQ_ROWS_MANTLE, e_begin, e_end, 6 * ma->n, 6 * ma->n, !keep)) { delete M; return 1; }
     if (nel > 0) {
         const size_t total = (size_t)ma->n * nel;
-        const int mode = hex8_mode();
+        const int mode = keep ? kHex8Classes : hex8_mode();
         M->pairs = (long long)total;
         // classes of (receiver cell, source cell) pairs: x group = (c_x - q_x, receiver dx, source dx),
         // (y,z) group = (c_y - q_y, both dy, receiver c_z and dz, source q_z and dz)
         Hex8PairClasses pc;
         bool built = false;
         if (mode == kHex8Auto || mode == kHex8Classes) built = mantle_mantle_classes(ma, e_begin, e_end, pc);
-        const bool classes = hex8_use_classes(mode, built, pc, 36);
+        const bool classes = hex8_use_classes(mode, built, pc, 36) && (!keep || pc.worthwhile);
+        if (keep && !classes) { delete M; return fail("mantle -> mantle: the cell pairs of this mesh do not fall into translation classes (keep the dense form)"); }
         DevHex8Tiles tiles;
         const bool tiled = !classes && mode != kHex8Pair;
         if (!classes && M->d.zero()) { delete M; return 1; }
@@ -1019,12 +1057,22 @@ static int build_mantle_mantle(const OqHex8Mesh* ma, const OqQuadrature* quad, d
                 dq.w.p, dq.nq, table.p);
             g_launches.fetch_add(1);
             rc = tm.stop(&M->table_ms);
+            if (!rc && keep) {
+                M->cls.reset(new ClassOperand());
+                // integer x positions of receivers (c_x) and sources (q_x) on their common grid: the diagonal fast path
+                std::vector<double> xall(2 * (size_t)ma->n);
+                for (int e = 0; e < ma->n; ++e) { xall[e] = ma->cx[e]; xall[(size_t)ma->n + e] = ma->qx[e]; }
+                std::vector<int> xidx;
+                const int npos = cluster_values(xall, 1e-12 * span_of(xall, xall), xidx);
+                rc = make_class_operand(pc, table, 6, 6, nel, ma->n, *M->cls, xidx.data() + e_begin, xidx.data() + ma->n, npos);
+            } else {
             if (!rc) rc = tm.start();
             if (!rc) {
                 dim3 grid((unsigned)std::min<size_t>(((size_t)ma->n + 255) / 256, 64), (unsigned)std::min(nel, 65535));
                 expand_classes_kernel<6, 6><<<grid, 256>>>(table.p, dpc.v, nel, ma->n, M->ld, M->d.p);
                 g_launches.fetch_add(1);
                 rc = tm.stop(&M->expand_ms);
+            }
             }
             M->kernel_ms = M->table_ms + M->expand_ms;
             M->path = kHex8Classes; M->unique_pairs = pc.classes;
@@ -1055,6 +1103,12 @@ int oq_matrix_mantle_mantle(const OqHex8Mesh* ma, const OqQuadrature* quad, doub
                             int e_end, OqMatrix** out)
 {
     return build_mantle_mantle(ma, quad, lambda, mu, e_begin, e_end, out);
+}
+
+int oq_matrix_mantle_mantle_classes(const OqHex8Mesh* ma, const OqQuadrature* quad, double lambda, double mu,
+                                    int e_begin, int e_end, OqMatrix** out)
+{
+    return build_mantle_mantle(ma, quad, lambda, mu, e_begin, e_end, out, true);
 }
 
 int oq_gf_mantle_mantle(const OqHex8Mesh* ma, const OqQuadrature* quad, double lambda, double mu, double* outp,
@@ -1161,7 +1215,10 @@ int oq_matrix_rows_to_host(const OqMatrix* a, int local_begin, int local_end, do
              "local row range [%d,%d) outside [0,%d)", local_begin, local_end, a->local_rows);
     OQ_TRY(enter());
     if (local_end == local_begin) return 0;
-    OQ_CUDA(cudaMemcpy2D(outp, (size_t)a->cols * sizeof(double), a->d.p + (size_t)local_begin * a->ld,
+    DevBuf<double> dense;
+    if (a->cls) OQ_TRY(dense_of_class_form(a, dense));
+    const double* src = a->cls ? dense.p : a->d.p;
+    OQ_CUDA(cudaMemcpy2D(outp, (size_t)a->cols * sizeof(double), src + (size_t)local_begin * a->ld,
                          a->ld * sizeof(double), (size_t)a->cols * sizeof(double), (size_t)(local_end - local_begin),
                          cudaMemcpyDeviceToHost));
     return 0;
@@ -1173,6 +1230,20 @@ int oq_matrix_shape(const OqMatrix* a, int* local_rows, int* cols, int* global_r
     if (local_rows) *local_rows = a->local_rows;
     if (cols) *cols = a->cols;
     if (global_rows) *global_rows = a->global_rows;
+    return 0;
+}
+
+int oq_matrix_form(const OqMatrix* a, int* form, double* device_bytes)
+{
+    OQ_CHECK(a, "NULL matrix");
+    if (form) *form = a->cls ? 1 : 0;
+    if (device_bytes) {
+        if (a->cls) {
+            const ClassOperand& c = *a->cls;
+            *device_bytes = c.table_bytes + 4.0 * (double)(c.rc1.n + c.sc1.n + c.D1.n + c.D23.n + c.rc23.n + c.sc23.n + c.rg_items.n +
+                                                           c.sg_ptr.n + c.sg_items.n + c.cta_row.n + c.cta_begin.n + c.cta_count.n);
+        } else *device_bytes = 8.0 * (double)a->d.n;
+    }
     return 0;
 }
 

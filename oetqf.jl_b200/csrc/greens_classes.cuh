@@ -152,6 +152,16 @@ struct AxisClasses {
                 if (cmap[c] < 0) { cmap[c] = (int)clist.size(); clist.push_back(c); }
                 newD[al * ns + b] = cmap[c];
             }
+        // local class ids keep the ORDER of the global ones (the class-form matvec walks a receiver's sources in
+        // ascending class order: the order, hence every rounded sum, must not depend on the shard)
+        {
+            std::vector<int> sorted(clist);
+            std::sort(sorted.begin(), sorted.end());
+            for (size_t k = 0; k < sorted.size(); ++k) cmap[sorted[k]] = (int)k;
+            for (size_t al = 0; al < rlist.size(); ++al)
+                for (int b = 0; b < ns; ++b) newD[al * ns + b] = cmap[D[(size_t)rlist[al] * ns + b]];
+            clist.swap(sorted);
+        }
         std::vector<int> nrr(clist.size()), nrs(clist.size());
         for (size_t k = 0; k < clist.size(); ++k) { nrr[k] = rep_r[clist[k]]; nrs[k] = rep_s[clist[k]]; }
         rcls.swap(newr); nr = (int)rlist.size(); D.swap(newD); n = (int)clist.size(); rep_r.swap(nrr); rep_s.swap(nrs);
@@ -352,16 +362,19 @@ struct DevPairClasses {
 // per blockIdx.y step, sources across the threads (consecutive sources are consecutive columns AND, on a mesh
 // numbered x-fastest, consecutive x classes: loads and stores of a warp are contiguous).  The table is small and
 // re-read constantly (L2); the shard is written once and never read here (streaming stores).
+// The table is addressed as T[class * cstride + m * mstride]: (1, n1*n23) for the builders' layout T[m][c23][c1],
+// (ts, 1) for the class-major layout of a class-form operand (ClassOperand::Tm).
 template <int K, int P>
 __global__ void __launch_bounds__(256)
-expand_classes_kernel(const double* __restrict__ T, ClassView c, int nrows, int ne, size_t ld, double* __restrict__ G)
+expand_classes_kernel(const double* __restrict__ T, ClassView c, int nrows, int ne, size_t ld, double* __restrict__ G,
+                      size_t cstride = 1, size_t mstride = 0)
 {
-    const size_t tstride = (size_t)c.n1 * c.n23;
+    const size_t tstride = mstride ? mstride : (size_t)c.n1 * c.n23;
     for (int r = blockIdx.y; r < nrows; r += gridDim.y) {
         const int* d1 = c.D1 + (size_t)c.rc1[r] * c.ns1;
         const int* d23 = c.D23 + (size_t)c.rc23[r] * c.ns23;
         for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ne; i += gridDim.x * blockDim.x) {
-            const double* src = T + (size_t)__ldg(d23 + __ldg(c.sc23 + i)) * c.n1 + __ldg(d1 + __ldg(c.sc1 + i));
+            const double* src = T + ((size_t)__ldg(d23 + __ldg(c.sc23 + i)) * c.n1 + __ldg(d1 + __ldg(c.sc1 + i))) * cstride;
             double v[K * P];
 #pragma unroll
             for (int m = 0; m < K * P; ++m) v[m] = __ldg(src + m * tstride);
@@ -376,6 +389,188 @@ expand_classes_kernel(const double* __restrict__ T, ClassView c, int nrows, int 
 #pragma unroll
                 for (int k = 0; k < K; ++k) G[((size_t)k * nrows + r) * ld + col] = 0.0;
     }
+}
+
+// ---- class form kept for the RHS (classmat.cuh) -------------------------------------------------------------
+// Tm[c][m] (class-major, ts doubles per class) from the builders' T[m][c]
+__global__ void __launch_bounds__(256)
+class_table_transpose_kernel(const double* __restrict__ T, size_t ncls, int KP, int ts, double* __restrict__ Tm)
+{
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ncls * ts) return;
+    const size_t c = t / ts;
+    const int m = (int)(t % ts);
+    Tm[t] = m < KP ? T[(size_t)m * ncls + c] : 0.0;
+}
+
+// The class form of a shard: table (class-major copy), class maps and the work list of class_matvec_kernel.
+// `pc` is restricted to the shard's receivers; `nr` local receiver units, `ns` source units.
+
+// Diagonal structure of a 6x6 operand: rpos / spos = integer x positions of the local receivers / of the sources.
+// Returns false (and leaves c.diag_ok unset) when the x classes are not a function of the position difference, when
+// a CTA run of receivers is not contiguous in position, or when two sources of a (y,z) group share a position.
+static inline bool find_diagonals(const Hex8PairClasses& pc, const int* rpos, const int* spos, int npos, int nr, int ns,
+                                  ClassOperand& c, std::vector<int>& diag, std::vector<int>& ritems_pos, std::vector<int>& bypos,
+                                  std::vector<int>& crow, std::vector<int>& cbeg, std::vector<int>& ccnt)
+{
+    const AxisClasses& g1 = pc.g1;
+    std::vector<int> pa(g1.nr, -1), pb(g1.ns, -1);
+    for (int r = 0; r < nr; ++r) { int& q = pa[g1.rcls[r]]; if (q < 0) q = rpos[r]; else if (q != rpos[r]) return false; }
+    for (int s = 0; s < ns; ++s) { int& q = pb[g1.scls[s]]; if (q < 0) q = spos[s]; else if (q != spos[s]) return false; }
+    diag.assign(2 * (size_t)npos - 1, -1);
+    for (int a = 0; a < g1.nr; ++a)
+        for (int b = 0; b < g1.ns; ++b) {
+            if (pa[a] < 0 || pb[b] < 0) continue;
+            int& q = diag[pa[a] - pb[b] + npos - 1];
+            const int cls = g1.D[(size_t)a * g1.ns + b];
+            if (q < 0) q = cls; else if (q != cls) return false;
+        }
+    // receivers by ((y,z) class, position); runs of <= kCdBlk*kCdG consecutive positions
+    const int nr23 = pc.g23.nr;
+    std::vector<std::vector<int>> groups(nr23);
+    for (int r = 0; r < nr; ++r) groups[pc.g23.rcls[r]].push_back(r);
+    ritems_pos.clear(); crow.clear(); cbeg.clear(); ccnt.clear();
+    const int run = kCdBlk * kCdG;
+    for (int g = 0; g < nr23; ++g) {
+        std::vector<int>& m = groups[g];
+        std::sort(m.begin(), m.end(), [&](int a, int b) { return rpos[a] < rpos[b]; });
+        size_t k = 0;
+        while (k < m.size()) {
+            size_t e = k + 1;
+            while (e < m.size() && e - k < (size_t)run && rpos[m[e]] == rpos[m[e - 1]] + 1) ++e;
+            if (e < m.size() && e - k < (size_t)run && rpos[m[e]] == rpos[m[e - 1]]) return false;   // two receivers, one position
+            crow.push_back(g); cbeg.push_back((int)ritems_pos.size()); ccnt.push_back((int)(e - k));
+            for (size_t q = k; q < e; ++q) ritems_pos.push_back(m[q]);
+            k = e;
+        }
+    }
+    if ((long long)crow.size() > 4LL * nr23 + 64) return false;          // positions too scattered to be worth it
+    bypos.assign((size_t)c.ns23 * npos, -1);
+    for (int s = 0; s < ns; ++s) {
+        int& q = bypos[(size_t)pc.g23.scls[s] * npos + spos[s]];
+        if (q >= 0) return false;
+        q = s;
+    }
+    return true;
+}
+
+static inline int make_class_operand(const Hex8PairClasses& pc, const DevBuf<double>& table, int K, int P, int nr, int ns,
+                                     ClassOperand& c, const int* rpos = nullptr, const int* spos = nullptr, int npos = 0)
+{
+    c.K = K; c.P = P; c.nr = nr; c.ns = ns;
+    c.n1 = pc.g1.n; c.n23 = pc.g23.n; c.ns1 = pc.g1.ns; c.ns23 = pc.g23.ns;
+    const int KP = K * P;
+    // 8 consecutive classes x one 128-bit load each must cover the 32 banks exactly once: ts*2 words = 4 (mod 8) words
+    // apart -> ts = 6 (6x1, 1x6: 12 words) and 38 (6x6: 76 words) both satisfy it
+    c.ts = KP == 36 ? 38 : KP;
+    const size_t ncls = (size_t)c.n1 * c.n23;
+    OQ_CHECK(table.n >= ncls * KP, "class table is smaller than its maps");
+    OQ_TRY(c.Tm.alloc(ncls * c.ts));
+    class_table_transpose_kernel<<<(unsigned)((ncls * c.ts + 255) / 256), 256>>>(table.p, ncls, KP, c.ts, c.Tm.p);
+    OQ_LAUNCHED();
+    OQ_TRY(c.rc1.upload(pc.g1.rcls.data(), pc.g1.rcls.size()));
+    OQ_TRY(c.sc1.upload(pc.g1.scls.data(), pc.g1.scls.size()));
+    OQ_TRY(c.D1.upload(pc.g1.D.data(), pc.g1.D.size()));
+    OQ_TRY(c.D23.upload(pc.g23.D.data(), pc.g23.D.size()));
+    OQ_TRY(c.rc23.upload(pc.g23.rcls.data(), pc.g23.rcls.size()));
+    OQ_TRY(c.sc23.upload(pc.g23.scls.data(), pc.g23.scls.size()));
+    OQ_CHECK((int)pc.g1.rcls.size() == nr && (int)pc.g23.rcls.size() == nr, "class maps do not match the shard's receivers");
+    OQ_CHECK((int)pc.g1.scls.size() == ns && (int)pc.g23.scls.size() == ns, "class maps do not match the sources");
+    // sources grouped by (y,z) class
+    std::vector<int> sptr(c.ns23 + 1, 0), sitems(ns);
+    for (int s = 0; s < ns; ++s) ++sptr[pc.g23.scls[s] + 1];
+    for (int g = 0; g < c.ns23; ++g) sptr[g + 1] += sptr[g];
+    {
+        std::vector<int> fill(sptr.begin(), sptr.end() - 1);
+        for (int s = 0; s < ns; ++s) sitems[fill[pc.g23.scls[s]]++] = s;
+    }
+    c.max_sg = 0;
+    for (int g = 0; g < c.ns23; ++g) c.max_sg = std::max(c.max_sg, sptr[g + 1] - sptr[g]);
+    // receivers ordered by (y,z) class; one CTA per run of <= rb receivers of a class
+    const int nr23 = pc.g23.nr;
+    std::vector<int> rptr(nr23 + 1, 0), ritems(nr > 0 ? nr : 1);
+    for (int r = 0; r < nr; ++r) ++rptr[pc.g23.rcls[r] + 1];
+    for (int g = 0; g < nr23; ++g) rptr[g + 1] += rptr[g];
+    {
+        std::vector<int> fill(rptr.begin(), rptr.end() - 1);
+        for (int r = 0; r < nr; ++r) ritems[fill[pc.g23.rcls[r]]++] = r;
+    }
+    int maxcount = 0;
+    for (int g = 0; g < nr23; ++g) maxcount = std::max(maxcount, rptr[g + 1] - rptr[g]);
+    auto ctas_for = [&](int rb) { long long n = 0; for (int g = 0; g < nr23; ++g) n += (rptr[g + 1] - rptr[g] + rb - 1) / rb; return n; };
+    // a fixed run length: the number of source slices (256 / rb) fixes the association order of a receiver's sum, which
+    // must not depend on the shard
+    const int rb = 64;
+    (void)maxcount; (void)ctas_for;
+    c.rb = rb;
+    std::vector<int> crow, cbeg, ccnt;
+    for (int g = 0; g < nr23; ++g)
+        for (int b = rptr[g]; b < rptr[g + 1]; b += rb) {
+            crow.push_back(g); cbeg.push_back(b); ccnt.push_back(std::min(rb, rptr[g + 1] - b));
+        }
+    c.nctas = (int)crow.size();
+    // every row of D23 walks the source groups in ascending order of their class: receivers of different rows then
+    // need the same table slab at about the same time (one HBM fetch serves them all through L2)
+    {
+        std::vector<int> order((size_t)nr23 * c.ns23);
+        for (int g = 0; g < nr23; ++g) {
+            int* o = &order[(size_t)g * c.ns23];
+            for (int b = 0; b < c.ns23; ++b) o[b] = b;
+            const int* d = &pc.g23.D[(size_t)g * c.ns23];
+            std::stable_sort(o, o + c.ns23, [&](int a, int b) { return d[a] < d[b]; });
+        }
+        OQ_TRY(c.sg_order.upload(order.data(), order.size()));
+    }
+    OQ_TRY(c.rg_items.upload(ritems.data(), ritems.size()));
+    OQ_TRY(c.sg_ptr.upload(sptr.data(), sptr.size()));
+    OQ_TRY(c.sg_items.upload(sitems.data(), sitems.size()));
+    if (c.nctas) {
+        OQ_TRY(c.cta_row.upload(crow.data(), crow.size()));
+        OQ_TRY(c.cta_begin.upload(cbeg.data(), cbeg.size()));
+        OQ_TRY(c.cta_count.upload(ccnt.data(), ccnt.size()));
+    }
+    const int PX = (P + 1) & ~1;
+    const size_t stage = ((size_t)c.n1 * c.ts + (size_t)c.max_sg * PX) * sizeof(double) + round_up((size_t)c.max_sg * sizeof(int), 16);
+    const size_t red = (size_t)256 * K * sizeof(double);
+    c.smem = std::max(stage, red);
+    OQ_CHECK(c.smem <= 226 * 1024, "class form: %d x-classes of %d doubles do not fit shared memory (%zu bytes)", c.n1, c.ts, c.smem);
+    c.table_bytes = (double)ncls * c.ts * sizeof(double);
+    if (K == 6 && P == 6 && rpos && spos && npos > 0 && nr > 0) {
+        std::vector<int> diag, rip, bypos, drow, dbeg, dcnt;
+        c.npos = npos;
+        c.dL = (int)round_up((size_t)(npos + kCdSlices - 1) / kCdSlices, kCdG);
+        const size_t npad = (size_t)kCdSlices * c.dL, ndp = (size_t)kCdBlk * kCdG + npad;
+        c.dsmem = (ndp * c.ts + npad * 6) * sizeof(double);
+        if (c.dsmem <= 226 * 1024 && find_diagonals(pc, rpos, spos, npos, nr, ns, c, diag, rip, bypos, drow, dbeg, dcnt)) {
+            OQ_TRY(c.diag.upload(diag.data(), diag.size()));
+            OQ_TRY(c.rg_items_pos.upload(rip.data(), rip.size()));
+            OQ_TRY(c.rpos.upload(rpos, nr));
+            OQ_TRY(c.sg_bypos.upload(bypos.data(), bypos.size()));
+            OQ_TRY(c.dcta_row.upload(drow.data(), drow.size()));
+            OQ_TRY(c.dcta_begin.upload(dbeg.data(), dbeg.size()));
+            OQ_TRY(c.dcta_count.upload(dcnt.data(), dcnt.size()));
+            c.ndctas = (int)drow.size();
+            c.diag_ok = true;
+        }
+    }
+    OQ_CUDA(cudaDeviceSynchronize());
+    return 0;
+}
+
+// dense rows of a class-form shard (parity checks, oq_matrix_to_host): G [K*nr x ld] row-major
+static inline int expand_class_operand(const ClassOperand& c, size_t ld, double* G)
+{
+    ClassView v{};
+    v.rc1 = c.rc1.p; v.rc23 = c.rc23.p; v.sc1 = c.sc1.p; v.sc23 = c.sc23.p; v.D1 = c.D1.p; v.D23 = c.D23.p;
+    v.ns1 = c.ns1; v.ns23 = c.ns23; v.n1 = c.n1; v.n23 = c.n23;
+    if (c.nr == 0) return 0;
+    dim3 grid((unsigned)std::min<size_t>(((size_t)c.ns + 255) / 256, 64), (unsigned)std::min(c.nr, 65535));
+    if (c.K == 6 && c.P == 6) expand_classes_kernel<6, 6><<<grid, 256>>>(c.Tm.p, v, c.nr, c.ns, ld, G, (size_t)c.ts, 1);
+    else if (c.K == 6 && c.P == 1) expand_classes_kernel<6, 1><<<grid, 256>>>(c.Tm.p, v, c.nr, c.ns, ld, G, (size_t)c.ts, 1);
+    else if (c.K == 1 && c.P == 6) expand_classes_kernel<1, 6><<<grid, 256>>>(c.Tm.p, v, c.nr, c.ns, ld, G, (size_t)c.ts, 1);
+    else return fail("class-form operand with %dx%d blocks is not supported", c.K, c.P);
+    OQ_LAUNCHED();
+    return 0;
 }
 
 }  // namespace oq

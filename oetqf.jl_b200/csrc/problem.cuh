@@ -79,7 +79,8 @@ struct OqProblem {
     oq::DevBuf<double> partial_f, partial_m;        // [rows * nsegTotal]
     oq::DevBuf<unsigned> counters;                  // [row blocks fault + row blocks mantle]
     oq::DevBuf<unsigned long long> ticket;          // matvec pass counter + finished-CTA counter (traversal direction)
-    oq::DevBuf<double> dtau0;                       // Toeplitz-form traction rate [nfl]
+    oq::DevBuf<double> dtau0;                       // Toeplitz-form / class-form traction rate [nfl]
+    oq::DevBuf<double> dsig0;                       // class-form stress rate [6*nel] when a dense mantle operand follows
     // FFT form (toeplitz_fft.cuh): transform length, local receiver-row range, spectrum and work arrays
     int fftN = 0, fj0 = 0, fnj = 0;
     oq::DevBuf<double> Ghat, Rhat, That, Wtw;      // Wtw: N/2 complex twiddles

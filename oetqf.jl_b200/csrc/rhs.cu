@@ -227,6 +227,10 @@ __device__ __forceinline__ size_t consumer_parity(const PeerWait& w)
     return (size_t)((ep_s - 1ull) & 1ull);
 }
 
+}  // namespace oq
+#include "classmat.cuh"
+namespace oq {
+
 __global__ void __launch_bounds__(256)
 toeplitz_conv_kernel(const double* __restrict__ st, const double* relv0, size_t relv_stride, PeerWait pw, int nx,
                      int nxi, int f0, int nfl, double* __restrict__ out)
@@ -716,7 +720,9 @@ static int rhs_views(OqProblem* p, const StateView& in, const StateView& out, co
     // dense fault-fault operand + panel kernel: the forcing front end runs inside the matvec launch (one launch per
     // evaluation); the FFT form needs the forcing vector before its transforms, the older kernels have no prologue
     static const bool split_forcing = [] { const char* e = getenv("OQ_FORCING"); return e && strcmp(e, "split") == 0; }();
-    const bool fused = matvec_variant(p->world) == 0 && p->gf11_form == OQ_GF11_DENSE && !split_forcing && p->nfl + fa.nel > 0;
+    const bool class_ops = (p->g12 && p->g12->cls) || (p->g21 && p->g21->cls) || (p->g22 && p->g22->cls);
+    const bool fused = matvec_variant(p->world) == 0 && p->gf11_form == OQ_GF11_DENSE && !split_forcing && p->nfl + fa.nel > 0 &&
+                       !class_ops;
     if (!direct_fft && !fused) {
     // small shards: ONE block (no cross-block handshake before the publication); large ones: 256-thread blocks
     if (nthr <= 4096) forcing_kernel<<<1, 1024, 0, st>>>(fa);
@@ -756,11 +762,33 @@ static int rhs_views(OqProblem* p, const StateView& in, const StateView& out, co
         }
         y0 = p->dtau0.p;
     }
+    // 2b. operands kept in class form (classmat.cuh) multiply from their tables into the vectors the dense kernel
+    //     starts from (or, with no dense operand on those rows, straight into the result)
+    const int* done = stage ? stage->done : nullptr;
+    const double* ym0 = nullptr;
+    if (class_ops) {
+        const bool dense_f = p->opf[0].G || p->opf[1].G, dense_m = p->opm[0].G || p->opm[1].G;
+        (void)dense_f;
+        if (p->g21->cls && p->nfl > 0) {
+            OQ_TRY(class_matvec(p->g21, p->reldeps, p->wl.reldeps_len, y0, p->dtau0.p, pw, done, st));
+            y0 = p->dtau0.p;
+        }
+        double* ym = dense_m ? p->dsig0.p : out.sig;
+        if (p->g12->cls && p->nel > 0) {
+            OQ_TRY(class_matvec(p->g12, p->relv, p->wl.relv_len, ym0, ym, pw, done, st));
+            ym0 = ym;
+        }
+        if (p->g22->cls && p->nel > 0) {
+            OQ_TRY(class_matvec(p->g22, p->reldeps, p->wl.reldeps_len, ym0, ym, pw, done, st));
+            ym0 = ym;
+        }
+        if (!dense_m) ym0 = nullptr;          // already in out.sig
+    }
     // 3. fused matvec + pointwise physics
     MatvecArgs a{};
     a.fe = fe;
     a.pw = pw;
-    a.done = stage ? stage->done : nullptr;
+    a.done = done;
     a.job[0].op[0] = p->opf[0]; a.job[0].op[1] = p->opf[1];
     a.job[0].partial = p->partial_f.p; a.job[0].counters = p->counters.p;
     a.job[0].y0 = y0; a.job[0].epilogue = kEpiFault;
@@ -768,7 +796,7 @@ static int rhs_views(OqProblem* p, const StateView& in, const StateView& out, co
     a.job[1].op[0] = p->opm[0]; a.job[1].op[1] = p->opm[1];
     a.job[1].partial = p->partial_m.p; a.job[1].counters = p->counters.p + nrbf;
     a.pass = p->ticket.p;
-    a.job[1].yout = out.sig; a.job[1].epilogue = kEpiStore;
+    a.job[1].yout = out.sig; a.job[1].epilogue = kEpiStore; a.job[1].y0 = ym0;
     plan_job(a.job[1], p->kind == kViscoelastic ? 6 * p->nel : 0);
     if (a.job[0].nitems == 0 && p->nfl > 0 && !epilogue_done) {
         // no dense operand on the fault rows (Toeplitz form, fault-only): standalone epilogue
@@ -934,6 +962,9 @@ static int finish_problem(OqProblem* p, const OqFaultProperty* pf, const OqDilat
             }
         }
     }
+    // class-form operands (classmat.cuh) accumulate into the vectors the dense kernel starts from
+    if (p->kind == kViscoelastic && p->g21->cls && !p->dtau0.p) OQ_TRY(p->dtau0.alloc(nfl > 0 ? nfl : 1));
+    if (p->kind == kViscoelastic && (bool)p->g12->cls != (bool)p->g22->cls) OQ_TRY(p->dsig0.alloc(nel > 0 ? 6 * (size_t)nel : 1));
     if (p->kind == kViscoelastic) {
         p->opf[1].G = p->g21->d.p; p->opf[1].ld = p->g21->ld; p->opf[1].x = p->reldeps; p->opf[1].x_stride = p->wl.reldeps_len; p->opf[1].cols = p->g21->cols; p->opf[1].x_kind = 1;
         p->opm[0].G = p->g12->d.p; p->opm[0].ld = p->g12->ld; p->opm[0].x = p->relv; p->opm[0].x_stride = p->wl.relv_len; p->opm[0].cols = p->g12->cols;
@@ -1219,7 +1250,7 @@ int oq_rhs_bytes(const OqProblem* p, double* bytes)
     double b = 0.0;
     const OqMatrix* ms[4] = {p->g11, p->g12, p->g21, p->g22};
     for (const OqMatrix* m : ms)
-        if (m) b += 8.0 * (double)m->local_rows * (double)m->cols;
+        if (m) b += m->cls ? m->cls->table_bytes : 8.0 * (double)m->local_rows * (double)m->cols;
     if (p->gf11_form == OQ_GF11_FFT) b += 8.0 * (double)p->Ghat.n + 16.0 * ((double)p->Rhat.n + (double)p->That.n) / 2;
     // vectors: state in, derivative out, properties, forcing vectors
     b += 8.0 * (2.0 * (double)p->nstate + 4.0 * p->nfl + (double)p->nf + 6.0 * p->ne);
@@ -1232,6 +1263,16 @@ int oq_gemv(const OqMatrix* A, const double* x, double* y, int accumulate)
     OQ_CHECK(A && x && y, "NULL argument");
     OQ_TRY(enter());
     if (A->local_rows == 0) return 0;
+    if (A->cls) {                                       // class form: multiply from the table
+        DevBuf<double> cx, cy;
+        OQ_TRY(cx.upload(x, A->cols));
+        OQ_TRY(cy.alloc(A->local_rows));
+        if (accumulate) OQ_CUDA(cudaMemcpy(cy.p, y, A->local_rows * sizeof(double), cudaMemcpyHostToDevice));
+        const PeerWait none{nullptr, nullptr, 1, 0, 0};
+        OQ_TRY(class_matvec(A, cx.p, 0, accumulate ? cy.p : nullptr, cy.p, none, nullptr, 0));
+        OQ_CUDA(cudaMemcpy(y, cy.p, A->local_rows * sizeof(double), cudaMemcpyDeviceToHost));
+        return 0;
+    }
     DevBuf<double> dx, dy, partial;
     DevBuf<unsigned> counters;
     DevBuf<unsigned long long> ticket;

@@ -185,6 +185,13 @@ class DeviceMatrix:
                 "unique_pairs": info.unique_pairs, "table_ms": info.table_ms, "expand_ms": info.expand_ms,
                 "kernel_ms": info.kernel_ms}
 
+    def form(self) -> dict:
+        """Storage form of the operand (oq_matrix_form): "dense" shard or "classes" (table of distinct kernels + class
+        maps, csrc/classmat.cuh) and the bytes of HBM it holds."""
+        f, b = C.c_int(), C.c_double()
+        _lib.check(_lib.load().oq_matrix_form(self.handle, C.byref(f), C.byref(b)))
+        return {"form": "classes" if f.value else "dense", "device_bytes": b.value}
+
     def gemv(self, x, y=None) -> np.ndarray:
         """The matvecmul! slot (src/pref.jl:15-21): y = A x, or y += A x when y is given."""
         x = _lib.f64(np.asarray(x).reshape(-1, order="F"))
@@ -223,27 +230,35 @@ def device_fault_fault(mf, lam, mu, ftype=StrikeSlip(), nrept=2, buffer_ratio=0.
 
 
 def device_fault_mantle(mf, ma, lam, mu, ftype=StrikeSlip(), qtype="Gauss1", nrept=2, buffer_ratio=0.0,
-                        elems=None) -> DeviceMatrix:
+                        elems=None, form="dense") -> DeviceMatrix:
+    """gf12 on the device.  form="classes": keep the operand as its table of distinct kernels (no dense storage; the RHS
+    multiplies from the table, csrc/classmat.cuh); raises OqError when the meshes have no translation classes."""
     e0, e1 = elems if elems is not None else (0, len(ma))
     sf, sa, q, h = mf.c_struct(), ma.c_struct(), _Quad(qtype), _new_handle()
-    _lib.check(_lib.load().oq_matrix_fault_mantle(C.byref(sf), C.byref(sa), q.ref(), C.c_double(lam),
+    lib = _lib.load()
+    fn = {"dense": lib.oq_matrix_fault_mantle, "classes": lib.oq_matrix_fault_mantle_classes}[form]
+    _lib.check(fn(C.byref(sf), C.byref(sa), q.ref(), C.c_double(lam),
                                                   C.c_double(mu), _ftype_code(ftype), int(nrept),
                                                   C.c_double(buffer_ratio), int(e0), int(e1), C.byref(h)))
     return DeviceMatrix(h)
 
 
-def device_mantle_fault(ma, mf, lam, mu, ftype=StrikeSlip(), rows=None) -> DeviceMatrix:
+def device_mantle_fault(ma, mf, lam, mu, ftype=StrikeSlip(), rows=None, form="dense") -> DeviceMatrix:
     r0, r1 = rows if rows is not None else (0, mf.nx * mf.nxi)
     sf, sa, h = mf.c_struct(), ma.c_struct(), _new_handle()
-    _lib.check(_lib.load().oq_matrix_mantle_fault(C.byref(sa), C.byref(sf), C.c_double(lam), C.c_double(mu),
+    lib = _lib.load()
+    fn = {"dense": lib.oq_matrix_mantle_fault, "classes": lib.oq_matrix_mantle_fault_classes}[form]
+    _lib.check(fn(C.byref(sa), C.byref(sf), C.c_double(lam), C.c_double(mu),
                                                   _ftype_code(ftype), int(r0), int(r1), C.byref(h)))
     return DeviceMatrix(h)
 
 
-def device_mantle_mantle(ma, lam, mu, qtype="Gauss1", elems=None) -> DeviceMatrix:
+def device_mantle_mantle(ma, lam, mu, qtype="Gauss1", elems=None, form="dense") -> DeviceMatrix:
     e0, e1 = elems if elems is not None else (0, len(ma))
     sa, q, h = ma.c_struct(), _Quad(qtype), _new_handle()
-    _lib.check(_lib.load().oq_matrix_mantle_mantle(C.byref(sa), q.ref(), C.c_double(lam), C.c_double(mu),
+    lib = _lib.load()
+    fn = {"dense": lib.oq_matrix_mantle_mantle, "classes": lib.oq_matrix_mantle_mantle_classes}[form]
+    _lib.check(fn(C.byref(sa), q.ref(), C.c_double(lam), C.c_double(mu),
                                                    int(e0), int(e1), C.byref(h)))
     return DeviceMatrix(h)
 

@@ -170,8 +170,13 @@ function device_fault_fault(mf::RectOkadaMesh, λ::Float64, μ::Float64; ftype::
 end
 
 function device_fault_mantle(mf::RectOkadaMesh, ma::BEMHex8Mesh, λ::Float64, μ::Float64; ftype::FaultType = StrikeSlip(),
-    qtype = "Gauss1", nrept::Integer = 2, buffer_ratio::Real = 0, elems::UnitRange{Int} = 0:length(ma.cx))
+    qtype = "Gauss1", nrept::Integer = 2, buffer_ratio::Real = 0, elems::UnitRange{Int} = 0:length(ma.cx), form::Symbol = :dense)
     f, a, q = cmesh(mf), cmesh(ma), cquad(qtype); h = Ref{Ptr{Cvoid}}(C_NULL)
+    # form = :classes keeps the operand as its table of distinct kernels (no dense storage; csrc/classmat.cuh)
+    form === :classes && (GC.@preserve f a q check(ccall((:oq_matrix_fault_mantle_classes, LIB), Cint,
+        (Ref{OqFaultMesh}, Ref{OqHex8Mesh}, Ref{OqQuadrature}, Cdouble, Cdouble, Cint, Cint, Cdouble, Cint, Cint, Ptr{Ptr{Cvoid}}),
+        f.s, a.s, q.s, λ, μ, ftype_code(ftype), nrept, buffer_ratio, first(elems), last(elems), h));
+        return DeviceMatrix(h[], 6 * (last(elems) - first(elems))))
     GC.@preserve f a q check(ccall((:oq_matrix_fault_mantle, LIB), Cint,
         (Ref{OqFaultMesh}, Ref{OqHex8Mesh}, Ref{OqQuadrature}, Cdouble, Cdouble, Cint, Cint, Cdouble, Cint, Cint, Ptr{Ptr{Cvoid}}),
         f.s, a.s, q.s, λ, μ, ftype_code(ftype), nrept, buffer_ratio, first(elems), last(elems), h))
@@ -179,16 +184,25 @@ function device_fault_mantle(mf::RectOkadaMesh, ma::BEMHex8Mesh, λ::Float64, μ
 end
 
 function device_mantle_fault(ma::BEMHex8Mesh, mf::RectOkadaMesh, λ::Float64, μ::Float64; ftype::FaultType = StrikeSlip(),
-    rows::UnitRange{Int} = 0:(mf.nx * mf.nξ))
+    rows::UnitRange{Int} = 0:(mf.nx * mf.nξ), form::Symbol = :dense)
     f, a = cmesh(mf), cmesh(ma); h = Ref{Ptr{Cvoid}}(C_NULL)
+    form === :classes && (GC.@preserve f a check(ccall((:oq_matrix_mantle_fault_classes, LIB), Cint,
+        (Ref{OqHex8Mesh}, Ref{OqFaultMesh}, Cdouble, Cdouble, Cint, Cint, Cint, Ptr{Ptr{Cvoid}}),
+        a.s, f.s, λ, μ, ftype_code(ftype), first(rows), last(rows), h));
+        return DeviceMatrix(h[], last(rows) - first(rows)))
     GC.@preserve f a check(ccall((:oq_matrix_mantle_fault, LIB), Cint,
         (Ref{OqHex8Mesh}, Ref{OqFaultMesh}, Cdouble, Cdouble, Cint, Cint, Cint, Ptr{Ptr{Cvoid}}),
         a.s, f.s, λ, μ, ftype_code(ftype), first(rows), last(rows), h))
     DeviceMatrix(h[], last(rows) - first(rows))
 end
 
-function device_mantle_mantle(ma::BEMHex8Mesh, λ::Float64, μ::Float64; qtype = "Gauss1", elems::UnitRange{Int} = 0:length(ma.cx))
+function device_mantle_mantle(ma::BEMHex8Mesh, λ::Float64, μ::Float64; qtype = "Gauss1", elems::UnitRange{Int} = 0:length(ma.cx),
+    form::Symbol = :dense)
     a, q = cmesh(ma), cquad(qtype); h = Ref{Ptr{Cvoid}}(C_NULL)
+    form === :classes && (GC.@preserve a q check(ccall((:oq_matrix_mantle_mantle_classes, LIB), Cint,
+        (Ref{OqHex8Mesh}, Ref{OqQuadrature}, Cdouble, Cdouble, Cint, Cint, Ptr{Ptr{Cvoid}}),
+        a.s, q.s, λ, μ, first(elems), last(elems), h));
+        return DeviceMatrix(h[], 6 * (last(elems) - first(elems))))
     GC.@preserve a q check(ccall((:oq_matrix_mantle_mantle, LIB), Cint,
         (Ref{OqHex8Mesh}, Ref{OqQuadrature}, Cdouble, Cdouble, Cint, Cint, Ptr{Ptr{Cvoid}}),
         a.s, q.s, λ, μ, first(elems), last(elems), h))
@@ -220,6 +234,13 @@ struct OqAssemblyInfo
     table_ms::Cdouble
     expand_ms::Cdouble
     kernel_ms::Cdouble
+end
+
+# (form, device bytes) of an operand: 0 dense shard, 1 class form
+function matrix_form(A::DeviceMatrix)
+    f = Ref{Cint}(0); b = Ref{Cdouble}(0.0)
+    check(ccall((:oq_matrix_form, LIB), Cint, (Ptr{Cvoid}, Ref{Cint}, Ref{Cdouble}), A.h, f, b))
+    (f[] == 1 ? :classes : :dense, b[])
 end
 
 function assembly_info(A::DeviceMatrix)

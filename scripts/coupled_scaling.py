@@ -2,6 +2,8 @@
 row shards, RHS throughput, roofline.  Run directly (1 GPU) or under torchrun (N GPUs).
 
   python scripts/coupled_scaling.py --nx 250 --nxi 80 --mantle 40 20 24     # 20k fault cells + 19.2k hex8 cells
+  python scripts/coupled_scaling.py --form classes --gf11 fft --mantle 50 40 40   # configs[3] as written: 20k + 80k cells,
+                                                                                  # mantle operands in class form (csrc/classmat.cuh)
 """
 import argparse
 import json
@@ -28,6 +30,11 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--out", default="")
+    ap.add_argument("--form", default="dense", choices=["dense", "classes"],
+                    help="storage of gf12 / gf21 / gf22: dense row shards (the north star's form) or class form")
+    ap.add_argument("--gf11", default="dense", choices=["dense", "fft"])
+    ap.add_argument("--check-sources", type=int, default=3,
+                    help="class form: check gf22 x against columns evaluated pointwise (oq_stress_vol_hex8) for this many sources")
     args = ap.parse_args()
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
     torch.cuda.set_device(local)
@@ -53,13 +60,16 @@ def main():
         oq._lib.check(oq._lib.load().oq_matrix_kernel_ms(m.handle, C.byref(ms)))
         return ms.value
 
-    d11 = oq.device_fault_fault(mf, W.LAM, W.MU, buffer_ratio=1.0, rows=rows)
-    d12 = oq.device_fault_mantle(mf, ma, W.LAM, W.MU, buffer_ratio=1.0, elems=elems)
-    d21 = oq.device_mantle_fault(ma, mf, W.LAM, W.MU, rows=rows)
-    d22 = oq.device_mantle_mantle(ma, W.LAM, W.MU, elems=elems)
+    if args.gf11 == "dense":
+        d11 = oq.device_fault_fault(mf, W.LAM, W.MU, buffer_ratio=1.0, rows=rows)
+    else:
+        d11 = oq.stress_greens_function(mf, W.LAM, W.MU, buffer_ratio=1.0)      # Fourier form, as the reference passes it
+    d12 = oq.device_fault_mantle(mf, ma, W.LAM, W.MU, buffer_ratio=1.0, elems=elems, form=args.form)
+    d21 = oq.device_mantle_fault(ma, mf, W.LAM, W.MU, rows=rows, form=args.form)
+    d22 = oq.device_mantle_mantle(ma, W.LAM, W.MU, elems=elems, form=args.form)
     torch.cuda.synchronize()
     asm_wall = time.perf_counter() - t0
-    asm = {"gf11_ms": kms(d11), "gf12_ms": kms(d12), "gf21_ms": kms(d21), "gf22_ms": kms(d22),
+    asm = {"gf11_ms": kms(d11) if args.gf11 == "dense" else oq.gf.last_kernel_ms["value"], "gf12_ms": kms(d12), "gf21_ms": kms(d21), "gf22_ms": kms(d22),
            "gf12_entries_per_s": d12.local_rows * d12.cols / (kms(d12) * 1e-3),
            "gf21_entries_per_s": d21.local_rows * d21.cols / (kms(d21) * 1e-3),
            "gf22_entries_per_s": d22.local_rows * d22.cols / (kms(d22) * 1e-3)}
@@ -75,7 +85,7 @@ def main():
     pf = oq.RateStateQuasiDynamicProperty(a, b, L, sig, W.ETA, W.VPL, W.F0, W.V0)
     pa = oq.PowerLawViscosityProperty(g, n, d0)
     u0 = oq.ArrayPartition(v, th, eps, sg, dl)
-    prob = oq.assemble(d11, d12, d21, d22, pf, pa, u0, (0.0, 1.0))
+    prob = oq.assemble(d11, d12, d21, d22, pf, pa, u0, (0.0, 1.0), gf11_form=args.gf11, fault_rows=rows)
     p = prob.p
     if world > 1:
         oq.dist.connect(p)
@@ -100,14 +110,46 @@ def main():
     du = [np.zeros(k) for k in p.local_lengths]
     p.get_du(du)
     finite = all(np.all(np.isfinite(x)) for x in du)
+    # class form at full scale: gf22 x for x supported on a few source cells == the same columns evaluated pointwise
+    # through the closed form (oq_stress_vol_hex8), on every receiver of this rank's shard
+    col_err = None
+    if args.form == "classes" and args.check_sources > 0 and elems[1] > elems[0]:
+        rng = np.random.default_rng(7)
+        src = rng.choice(ne, size=args.check_sources, replace=False)
+        x = np.zeros(6 * ne)
+        e0, e1 = elems
+        want = np.zeros((6, e1 - e0))
+        nu = W.LAM / 2 / (W.LAM + W.MU)
+        for i in src:
+            for pc in range(6):
+                c = rng.uniform(0.5, 1.5)
+                x[pc * ne + i] = c
+                eps6 = np.zeros(6)
+                eps6[pc] = 1.0
+                col = oq.stress_vol_hex8(ma.cx[e0:e1], ma.cy[e0:e1], ma.cz[e0:e1], ma.qx[i], ma.qy[i], ma.qz[i],
+                                         ma.dx[i], ma.dy[i], ma.dz[i], eps6, W.MU, nu)       # [receivers, 6]
+                want += c * col.T
+        got = d22.gemv(x).reshape(6, e1 - e0)
+        col_err = float(np.max(np.abs(got - want)) / np.max(np.abs(want)))
+    forms = {k: m.form() for k, m in (("gf12", d12), ("gf21", d21), ("gf22", d22))}
+    fma = sum((m.local_rows * m.cols) for m in (d12, d21, d22)) if args.form == "classes" else 0
     if rank == 0:
         byts = p.rhs_bytes()
         line = {"workload": f"coupled: {nf} fault cells + {ne} hex8 cells ({6 * ne} mantle rows)", "n_gpus": world,
                 "rhs_evals_per_s": args.steps / (float(t[0]) * 1e-3), "ms_per_eval": float(t[0]) / args.steps,
                 "matrix_bytes_per_rank": byts, "matvec_ms": mv_ms / max(1, mv_n),
-                "matvec_gbs": byts / (mv_ms / max(1, mv_n) * 1e-3) / 1e9, "finite": bool(finite),
+                "matvec_gbs": byts / (mv_ms / max(1, mv_n) * 1e-3) / 1e9 if mv_ms > 0 else None, "finite": bool(finite),
                 "assembly_ms_max_over_ranks": {"gf22": float(t[1]), "gf21": float(t[2]), "gf12": float(t[3])},
-                "assembly_rank0": asm, "assembly_wall_s": asm_wall}
+                "assembly_rank0": asm, "assembly_wall_s": asm_wall,
+                "form": args.form, "gf11": args.gf11, "operands_rank0": forms,
+                "dense_equivalent_bytes_total": 8.0 * (nf * nf + 2 * 6 * ne * nf + (6 * ne) ** 2)}
+        if args.form == "classes":
+            peak = oq.measure_fp64_peak()
+            line["class_form"] = {"fma_per_eval_rank0": fma, "achieved_tflops": 2 * fma / (float(t[0]) / args.steps * 1e-3) / 1e12,
+                                  "fp64_peak_tflops": peak / 1e12,
+                                  "frac_of_fp64_peak": 2 * fma / (float(t[0]) / args.steps * 1e-3) / peak,
+                                  "gf22_columns_vs_pointwise_closed_form_max_rel_err": col_err,
+                                  "note": "evaluation bound by shared-memory bandwidth: every FMA reads one table entry (cap 25 % of the DFMA peak)"}
         print(json.dumps(line))
         if args.out:
             with open(args.out, "w") as fh:

@@ -120,6 +120,23 @@ int main(int argc, char **argv)
     for (int i = 0; i < 6 * NE; ++i) xv[i] = sin(0.37 * i) * 1e-14;
     CHECK(oq_gemv(d21, xv, yv, 0));
     put(out, "gemv21", yv, NF);
+    /* the same operand kept in class form (no dense storage): same handle type, same product */
+    {
+        OqMatrix *c22;
+        int form = -1;
+        double bytes = 0, yd[6 * NE], yc[6 * NE], worst = 0, scale = 0;
+        CHECK(oq_matrix_mantle_mantle_classes(&ma, NULL, lam, mu, 0, NE, &c22));
+        CHECK(oq_matrix_form(c22, &form, &bytes));
+        CHECK(oq_gemv(d22, xv, yd, 0));
+        CHECK(oq_gemv(c22, xv, yc, 0));
+        for (int i = 0; i < 6 * NE; ++i) { worst = fmax(worst, fabs(yd[i] - yc[i])); scale = fmax(scale, fabs(yd[i])); }
+        if (form != 1 || bytes <= 0 || !(worst <= 1e-12 * scale)) {
+            fprintf(stderr, "class form: form %d, %g bytes, gemv differs by %g of %g\n", form, bytes, worst, scale);
+            return 1;
+        }
+        put(out, "gemv22_classes", yc, 6 * NE);
+        oq_matrix_destroy(c22);
+    }
 
     /* ---- assemble (equation.jl:141-154) with the example's properties ---- */
     double a[NF], b[NF], L[NF], sg[NF], gam[NE], npw[NE], deps0[6] = {0, -1e-12, 0, 0, 0, 0};

@@ -67,6 +67,8 @@ def test_c_program_end_to_end(gpu, tmp_path):
     xv = np.sin(0.37 * np.arange(6 * ne)) * 1e-14
     want = ref.gemv(o21, xv)
     assert np.max(np.abs(d["gemv21"] - want)) <= 1e-10 * np.max(np.abs(want))
+    want22 = ref.gemv(o22, xv)                       # the class-form operand (oq_matrix_mantle_mantle_classes) through oq_gemv
+    assert np.max(np.abs(d["gemv22_classes"] - want22)) <= 1e-10 * np.max(np.abs(want22))
     # the (du, u, p, t) call
     shp = (mfo.nx, mfo.nxi)
     pf = ref.FaultProp(*(d[k].reshape(shp, order="F") for k in ("a", "b", "L", "sigma")), W.ETA, W.VPL, 0.6, 1e-6)
