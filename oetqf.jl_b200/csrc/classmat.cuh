@@ -5,43 +5,86 @@
 // (Gmsh transfinite boxes, mesh.jl:95-130; the equidistant fault, mesh.jl:39-56) their (receiver, source) pairs fall
 // into translation classes (greens_classes.cuh): G[(k, r), (p, s)] = T[class(r, s)][k][p] with a few thousand to a
 // few million distinct 6x6 (6x1, 1x6) blocks instead of (6 N_e)² entries -- the same invariance the reference itself
-// exploits for the fault (Toeplitz kernel, GF.jl:31-71), extended to the mantle.  This kernel multiplies straight
+// exploits for the fault (Toeplitz kernel, GF.jl:31-71), extended to the mantle.  These kernels multiply straight
 // from the table:
 //
 //     y[k, r] = y_in[k, r] + Σ_s Σ_p T[D23[rc23(r), sc23(s)]][D1[rc1(r), sc1(s)]][k][p] · x[p, s]
 //
-// so a problem whose dense gf₂₂ would need 1.84 TB (BASELINE configs[3]: 80 000 cells) keeps a 3.6 GB table, and the
+// so a problem whose dense gf₂₂ would need 1.84 TB (BASELINE configs[3]: 80 000 cells) keeps a few GB of tables, and the
 // evaluation is bound by the fp64 pipe / shared-memory bandwidth instead of HBM.  Nothing about the mesh is assumed
 // beyond what the class maps say (they are found numerically); a mesh without structure has no class form and keeps
 // the dense operands.
 //
-// One CTA = a run of <= rb receivers of one (y,z) class (they share the row D23[rc23, :]) x all sources.  Sources are
-// walked group by group ((y,z) class of the source): the slab T[c23][:][:] of the group (n1 classes x K*P doubles,
-// class-major, padded so that 128-bit loads of consecutive classes are bank-conflict free) and the group's forcing
-// values are staged in shared memory, then thread (slice, receiver) accumulates its K outputs over every nsl-th
-// source of the group.  Sums are formed in a fixed order (sources ascending within a slice, slices folded in order):
-// results are bitwise reproducible and independent of the number of ranks (a rank's receivers see all sources).
+// Common structure.  One CTA = a run of receivers of one (y,z) class (they share the row D23[rc23, :]) x all sources.
+// Sources are walked group by group ((y,z) class of the source) in ascending order of the pair's (y,z) class.  Per
+// group the CTA needs the slab T[c23][:][:] (n1 classes x K*P doubles), the group's forcing values and the x classes
+// of its sources: a producer warp fetches them with 1-D bulk TMA copies into a two-stage ring in shared memory
+// (full/empty mbarriers), so the fetch of group i+1 overlaps the arithmetic on group i.  The forcing values are
+// gathered once per evaluation into group order by class_gather_x_kernel (which is also the kernel that waits for the
+// peers' slices of the forcing vector).  Sums are formed in a fixed order (sources ascending within a slice, slices
+// folded in order): results are bitwise reproducible and independent of the number of ranks.
 #pragma once
+
+#include "tma.cuh"
 
 namespace oq {
 
-constexpr int kCmThreads = 256;
+constexpr int kCmRb = 64;                    // receivers per CTA of the general kernel
+constexpr int kCmSlices = 4;                 // source slices
+constexpr int kCmConsumers = kCmRb * kCmSlices;      // 256 compute threads
+constexpr int kCmThreads = kCmConsumers + 32;        // + the producer warp
+constexpr int kCmStages = 2;
 
 struct ClassMvArgs {
-    const double* Tm;
+    const double* Tm;             // general: [n23][n1][ts]; diagonal: [n23][noff][ts] (offset order, zero padded)
     int ts, n1, ns1, ns23;
-    const int *rc1, *sc1, *D1, *D23;
-    const int *rg_items, *sg_ptr, *sg_items, *sg_order, *cta_row, *cta_begin, *cta_count;
-    int rb, max_sg;
-    int nr, ns;                   // local receiver units, source units (= stride between the P planes of x)
-    const double* x;              // copy 0 of the forcing vector
-    size_t x_stride;              // distance to copy 1 (parity of the evaluation)
+    const int *rc1, *D1, *D23;
+    const int *rg_items, *sg_ptr, *sg_order, *cta_row, *cta_begin, *cta_count;
+    const double* xg;             // forcing values in group order [ns23][xstride][PX] (class_gather_x_kernel)
+    const int* csg;               // x class of the sources in group order [ns23][xstride]
+    int xstride;                  // slots per group (multiple of 8)
+    int nr;                       // local receiver units
     const double* y_in;           // optional: accumulate onto (may alias y_out)
     double* y_out;                // [K][nr]
-    PeerWait pw;
     const int* done;              // optional device flag: integration complete, skip
+    // diagonal kernel
+    const int *rpos, *rg_items_pos;
+    int noff, L;
+    int d1_smem;                  // general kernel: the receivers' rows of D1 are staged in shared memory
 };
 
+// xg[slot][p] = x[p*ns + xmap[slot]] (0 where xmap < 0): the forcing vector in the order the CTAs consume it.  Also the
+// one kernel of the class-form path that waits for the peers' slices (consumer_parity).
+template <int P>
+__global__ void __launch_bounds__(256)
+class_gather_x_kernel(const int* __restrict__ xmap, size_t nslots, int ns, const double* x0, size_t x_stride, PeerWait pw,
+                      const int* done, double* __restrict__ xg)
+{
+    constexpr int PX = (P + 1) & ~1;
+    if (done && *reinterpret_cast<const volatile int*>(done)) return;
+    const double* x = x0 + consumer_parity(pw) * x_stride;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < nslots; t += (size_t)gridDim.x * blockDim.x) {
+        const int s = __ldg(xmap + t);
+#pragma unroll
+        for (int p = 0; p < PX; ++p) xg[t * PX + p] = (s >= 0 && p < P) ? x[(size_t)p * ns + s] : 0.0;
+    }
+}
+
+__device__ __forceinline__ void cm_bulk_load(void* dst, const void* src, unsigned bytes, uint64_t* bar)
+{
+    // pieces of <= 16 KB (every piece a multiple of 16 bytes)
+    char* d = static_cast<char*>(dst);
+    const char* s = static_cast<const char*>(src);
+    while (bytes) {
+        const unsigned n = bytes > 16384u ? 16384u : bytes;
+        tma_load_1d(d, s, n, bar);
+        d += n; s += n; bytes -= n;
+    }
+}
+
+// ---- general kernel: every (receiver, source) pair looks its x class up in D1 ------------------------------
+// The rows of D1 of the CTA's receivers sit in shared memory as 16-bit class ids (row stride = 2 mod 4 entries, i.e. an
+// odd number of 32-bit words: conflict free) when they fit (d1_smem).
 template <int K, int P>
 __global__ void __launch_bounds__(kCmThreads)
 class_matvec_kernel(const __grid_constant__ ClassMvArgs a)
@@ -50,44 +93,68 @@ class_matvec_kernel(const __grid_constant__ ClassMvArgs a)
     constexpr int PX = (P + 1) & ~1;
     static_assert(KP % 2 == 0, "class blocks are loaded as double2");
     extern __shared__ __align__(16) double cm_smem[];
+    __shared__ __align__(8) uint64_t full_bar[kCmStages], empty_bar[kCmStages];
     if (a.done && *reinterpret_cast<const volatile int*>(a.done)) return;
-    double* Ts = cm_smem;                                       // [n1][ts]
-    double* xs = Ts + (size_t)a.n1 * a.ts;                      // [max_sg][PX]
-    int* cs = reinterpret_cast<int*>(xs + (size_t)a.max_sg * PX);   // [max_sg] x class of the group's sources
-    const double* x = a.x + consumer_parity(a.pw) * a.x_stride;
+    const unsigned slab_bytes = (unsigned)((size_t)a.n1 * a.ts * sizeof(double));
+    const unsigned x_bytes = (unsigned)((size_t)a.xstride * PX * sizeof(double));
+    const unsigned c_bytes = (unsigned)((size_t)a.xstride * sizeof(int));
+    const size_t stage_doubles = ((size_t)slab_bytes + x_bytes + c_bytes) / sizeof(double);      // all multiples of 16 bytes
     const int row = a.cta_row[blockIdx.x], begin = a.cta_begin[blockIdx.x], count = a.cta_count[blockIdx.x];
-    const int rb = a.rb, nsl = kCmThreads / rb;
-    const int i = threadIdx.x % rb, sl = threadIdx.x / rb;
+    const int* d23row = a.D23 + (size_t)row * a.ns23;
+    const int* order = a.sg_order + (size_t)row * a.ns23;
+    const int t = threadIdx.x;
+    if (t == 0) {
+        for (int s = 0; s < kCmStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kCmConsumers); }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (t >= kCmConsumers) {                                    // ---- producer warp: one lane fetches group after group
+        if (t == kCmConsumers) {
+            for (int it = 0; it < a.ns23; ++it) {
+                const int stage = it % kCmStages;
+                const int sg = order[it];
+                const int c23 = d23row[sg];
+                mbar_wait(&empty_bar[stage], (((unsigned)(it / kCmStages)) & 1u) ^ 1u);
+                double* st = cm_smem + (size_t)stage * stage_doubles;
+                mbar_arrive_expect_tx(&full_bar[stage], slab_bytes + x_bytes + c_bytes);
+                cm_bulk_load(st, a.Tm + (size_t)c23 * a.n1 * a.ts, slab_bytes, &full_bar[stage]);
+                cm_bulk_load(reinterpret_cast<char*>(st) + slab_bytes, a.xg + (size_t)sg * a.xstride * PX, x_bytes, &full_bar[stage]);
+                cm_bulk_load(reinterpret_cast<char*>(st) + slab_bytes + x_bytes, a.csg + (size_t)sg * a.xstride, c_bytes, &full_bar[stage]);
+            }
+        }
+        return;
+    }
+    // thread (slice, receiver)
+    const int i = t % kCmRb, sl = t / kCmRb;
     const bool active = i < count;
     const int r = active ? a.rg_items[begin + i] : 0;
     const int* d1row = a.D1 + (size_t)(active ? a.rc1[r] : 0) * a.ns1;
-    const int* d23row = a.D23 + (size_t)row * a.ns23;
+    // the receivers' rows of D1 in shared memory (behind the stages and the fold area)
+    unsigned short* d1s = reinterpret_cast<unsigned short*>(cm_smem + (size_t)kCmStages * stage_doubles + (size_t)kCmConsumers * K);
+    const int ns1p = cm_d1_stride(a.ns1);
+    if (a.d1_smem) {
+        for (int q = t; q < count * a.ns1; q += kCmConsumers) {
+            const int ii = q / a.ns1, b = q - ii * a.ns1;
+            d1s[ii * ns1p + b] = (unsigned short)__ldg(a.D1 + (size_t)a.rc1[a.rg_items[begin + ii]] * a.ns1 + b);
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kCmConsumers) : "memory");
+    }
+    const unsigned short* d1mine = d1s + i * ns1p;
     double acc[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) acc[k] = 0.0;
-    const int n2 = a.n1 * a.ts / 2;
-    const int* order = a.sg_order + (size_t)row * a.ns23;
     for (int it = 0; it < a.ns23; ++it) {
+        const int stage = it % kCmStages;
         const int sg = order[it];
-        const int s0 = a.sg_ptr[sg], sn = a.sg_ptr[sg + 1] - s0;
-        if (sn == 0) continue;
-        const int c23 = d23row[sg];
-        __syncthreads();                                        // the previous group has been consumed
-        {
-            const double2* src = reinterpret_cast<const double2*>(a.Tm + (size_t)c23 * a.n1 * a.ts);
-            double2* dst = reinterpret_cast<double2*>(Ts);
-            for (int q = threadIdx.x; q < n2; q += kCmThreads) dst[q] = __ldg(src + q);
-        }
-        for (int j = threadIdx.x; j < sn; j += kCmThreads) {
-            const int s = a.sg_items[s0 + j];
-            cs[j] = a.sc1[s];
-#pragma unroll
-            for (int p = 0; p < P; ++p) xs[j * PX + p] = x[(size_t)p * a.ns + s];
-        }
-        __syncthreads();
+        const int sn = a.sg_ptr[sg + 1] - a.sg_ptr[sg];
+        const double* Ts = cm_smem + (size_t)stage * stage_doubles;
+        const double* xs = Ts + (size_t)a.n1 * a.ts;
+        const int* cs = reinterpret_cast<const int*>(xs + (size_t)a.xstride * PX);
+        mbar_wait(&full_bar[stage], ((unsigned)(it / kCmStages)) & 1u);
         if (active) {
-            for (int j = sl; j < sn; j += nsl) {
-                const int c1 = __ldg(d1row + cs[j]);
+#pragma unroll 2
+            for (int j = sl; j < sn; j += kCmSlices) {
+                const int c1 = a.d1_smem ? (int)d1mine[cs[j]] : __ldg(d1row + cs[j]);
                 const double2* t2 = reinterpret_cast<const double2*>(Ts + (size_t)c1 * a.ts);
                 double tv[KP];
 #pragma unroll
@@ -101,19 +168,19 @@ class_matvec_kernel(const __grid_constant__ ClassMvArgs a)
                 }
             }
         }
+        mbar_arrive(&empty_bar[stage]);
     }
-    // fold the slices in order
-    __syncthreads();
-    double* red = cm_smem;                                      // [nsl][rb][K]
+    // fold the slices in order (own region behind the stages)
+    double* red = cm_smem + (size_t)kCmStages * stage_doubles;  // [slices][rb][K]
     if (sl > 0 && active) {
 #pragma unroll
-        for (int k = 0; k < K; ++k) red[((size_t)sl * rb + i) * K + k] = acc[k];
+        for (int k = 0; k < K; ++k) red[((size_t)sl * kCmRb + i) * K + k] = acc[k];
     }
-    __syncthreads();
+    asm volatile("bar.sync 1, %0;" ::"n"(kCmConsumers) : "memory");
     if (sl == 0 && active) {
-        for (int s = 1; s < nsl; ++s) {
+        for (int s = 1; s < kCmSlices; ++s) {
 #pragma unroll
-            for (int k = 0; k < K; ++k) acc[k] += red[((size_t)s * rb + i) * K + k];
+            for (int k = 0; k < K; ++k) acc[k] += red[((size_t)s * kCmRb + i) * K + k];
         }
 #pragma unroll
         for (int k = 0; k < K; ++k) {
@@ -123,69 +190,77 @@ class_matvec_kernel(const __grid_constant__ ClassMvArgs a)
     }
 }
 
-
 // ---- diagonal fast path (6x6 operands on one equidistant x grid) ---------------------------------------------
 // In class_matvec_kernel every FMA reads its own table entry from shared memory (128 B/clk per SM against 64 DFMA/clk:
 // at most 25 % of the fp64 pipe).  When the x class of a pair depends on the DIFFERENCE of the integer x positions
 // only (the Toeplitz structure of GF.jl:31-71), the pairs (r+1, s+1) and (r, s) share their 6x6 block: a thread that
 // owns G consecutive receivers (one output component k) and walks the sources in position order keeps a sliding
-// window of G blocks-rows (6 doubles each) in registers -- one new row (48 B) per G*6 FMAs instead of one per 6.
+// window of G block-rows (6 doubles each) in registers -- one new row (48 B) per G*6 FMAs instead of one per 6.
+// The table is stored in OFFSET order (offset = receiver position - source position), zero padded on both sides, so
+// the window of a CTA run starting at position p0 is ONE contiguous piece of the slab: padded offsets [p0, p0 + ndp).
 //   thread (slice, blk, k): receivers p0 + blk*G + g (g < G), output k, source positions [slice*L, (slice+1)*L)
-//   Td[dd] = row-block of the class of offset (p0 + dd - (npad - 1)), dd = (blk*G + g) - j + npad - 1   (zero outside)
-constexpr int kCdThreads = kCdBlk * 6 * kCdSlices;      // 192
+//   Td[dd] = block of offset (p0 + dd - (npad - 1)), dd = (blk*G + g) - j + npad - 1
+// Shared-memory layout of a slab: class dd at dd*ts + 4*(dd >> 3) doubles -- every run of 8 classes starts 32 bytes
+// later than a dense layout would put it, which makes the 128-bit loads of a warp (6 lanes of one receiver block read
+// 288 contiguous bytes, the next block sits 8 classes = 19 x 128 bytes further) bank-conflict free.  One bulk copy per run.
+constexpr int kCdConsumers = kCdBlk * 6 * kCdSlices;    // 192 compute threads
+constexpr int kCdThreads = kCdConsumers + 32;           // + the producer warp
 
-struct ClassDiagArgs {
-    ClassMvArgs b;
-    const int *diag, *rpos, *sg_bypos, *rg_items_pos;
-    int npos, L;
-};
+__device__ __forceinline__ int cd_slab_off(int dd, int ts) { return dd * ts + 4 * (dd >> 3); }
 
-__global__ void __launch_bounds__(kCdThreads)
-class_matvec_diag_kernel(const __grid_constant__ ClassDiagArgs A)
+__global__ void __launch_bounds__(kCdThreads, 2)
+class_matvec_diag_kernel(const __grid_constant__ ClassMvArgs a)
 {
     constexpr int G = kCdG;
-    const ClassMvArgs& a = A.b;
     extern __shared__ __align__(16) double cm_smem[];
+    __shared__ __align__(8) uint64_t full_bar[kCmStages], empty_bar[kCmStages];
     if (a.done && *reinterpret_cast<const volatile int*>(a.done)) return;
-    const int npad = kCdSlices * A.L;                           // padded source positions
-    const int ndp = kCdBlk * G + npad;                          // padded diagonals
-    const int ts = a.ts, ts2 = ts / 2;
-    double* Td = cm_smem;                                       // [ndp][ts]
-    double* xs = Td + (size_t)ndp * ts;                         // [npad][6]
-    const double* x = a.x + consumer_parity(a.pw) * a.x_stride;
+    const int npad = kCdSlices * a.L;                           // padded source positions (= xstride)
+    const int ndp = kCdBlk * G + npad;                          // padded diagonals of a run (multiple of 8)
+    const int ts = a.ts;
+    const unsigned run_bytes = (unsigned)(8 * ts * sizeof(double));
+    const unsigned slab_bytes = (unsigned)((size_t)ndp * ts * sizeof(double));
+    const unsigned x_bytes = (unsigned)((size_t)npad * 6 * sizeof(double));
+    const size_t slab_doubles = (size_t)ndp * ts + (size_t)ndp / 2;
+    const size_t stage_doubles = slab_doubles + (size_t)npad * 6;
     const int row = a.cta_row[blockIdx.x], begin = a.cta_begin[blockIdx.x], count = a.cta_count[blockIdx.x];
-    const int p0 = A.rpos[A.rg_items_pos[begin]];
-    const int t = threadIdx.x, sl = t / (kCdBlk * 6), u = t % (kCdBlk * 6), blk = u / 6, k = u % 6;
+    const int t = threadIdx.x;
+    if (t == 0) {
+        for (int s = 0; s < kCmStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kCdConsumers); }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (t >= kCdConsumers) {                                    // ---- producer warp: one lane fetches group after group
+        if (t == kCdConsumers) {
+            const int p0 = a.rpos[a.rg_items_pos[begin]];
+            const int* d23row = a.D23 + (size_t)row * a.ns23;
+            const int* order = a.sg_order + (size_t)row * a.ns23;
+            for (int it = 0; it < a.ns23; ++it) {
+                const int stage = it % kCmStages;
+                const int sg = order[it];
+                const int c23 = d23row[sg];
+                mbar_wait(&empty_bar[stage], (((unsigned)(it / kCmStages)) & 1u) ^ 1u);
+                double* st = cm_smem + (size_t)stage * stage_doubles;
+                mbar_arrive_expect_tx(&full_bar[stage], slab_bytes + x_bytes);
+                const double* src = a.Tm + ((size_t)c23 * a.noff + p0) * ts;
+                for (int q = 0; q < ndp / 8; ++q)
+                    tma_load_1d(st + cd_slab_off(8 * q, ts), src + (size_t)8 * q * ts, run_bytes, &full_bar[stage]);
+                cm_bulk_load(st + slab_doubles, a.xg + (size_t)sg * npad * 6, x_bytes, &full_bar[stage]);
+            }
+        }
+        return;
+    }
+    const int sl = t / (kCdBlk * 6), u = t % (kCdBlk * 6), blk = u / 6, k = u % 6;
     const bool active = blk * G < count;
-    const int* d23row = a.D23 + (size_t)row * a.ns23;
-    const int* order = a.sg_order + (size_t)row * a.ns23;
     double acc[G];
 #pragma unroll
     for (int g = 0; g < G; ++g) acc[g] = 0.0;
-    const int jb = sl * A.L;
+    const int jb = sl * a.L;
     for (int it = 0; it < a.ns23; ++it) {
-        const int sg = order[it];
-        if (a.sg_ptr[sg + 1] == a.sg_ptr[sg]) continue;
-        const int c23 = d23row[sg];
-        __syncthreads();                                        // the previous group has been consumed
-        {
-            const double2* slab = reinterpret_cast<const double2*>(a.Tm + (size_t)c23 * a.n1 * ts);
-            double2* dst = reinterpret_cast<double2*>(Td);
-            for (int q = t; q < ndp * ts2; q += kCdThreads) {
-                const int dd = q / ts2, w = q - dd * ts2;
-                const int off = p0 + dd - (npad - 1) + A.npos - 1;          // receiver position - source position + npos - 1
-                int cls = -1;
-                if (off >= 0 && off < 2 * A.npos - 1) cls = __ldg(A.diag + off);
-                dst[q] = cls >= 0 ? __ldg(slab + (size_t)cls * ts2 + w) : make_double2(0.0, 0.0);
-            }
-            const int* bypos = A.sg_bypos + (size_t)sg * A.npos;
-            for (int q = t; q < npad * 6; q += kCdThreads) {
-                const int j = q / 6, p = q - j * 6;
-                const int s = j < A.npos ? __ldg(bypos + j) : -1;
-                xs[q] = s >= 0 ? x[(size_t)p * a.ns + s] : 0.0;
-            }
-        }
-        __syncthreads();
+        const int stage = it % kCmStages;
+        const double* Td = cm_smem + (size_t)stage * stage_doubles;
+        const double* xs = Td + slab_doubles;
+        mbar_wait(&full_bar[stage], ((unsigned)(it / kCmStages)) & 1u);
         if (active) {
             // window: logical g at source position j sits at dd = blk*G + g - j + npad - 1; physical slot (g - jj) mod G
             double W[G][6];
@@ -193,17 +268,16 @@ class_matvec_diag_kernel(const __grid_constant__ ClassDiagArgs A)
             int dd0 = blk * G - jb + npad - 1;                  // logical 0 at j = jb
 #pragma unroll
             for (int g = 1; g < G; ++g) {
-                const double2* s2 = reinterpret_cast<const double2*>(trow + (size_t)(dd0 + g) * ts);
+                const double2* s2 = reinterpret_cast<const double2*>(trow + cd_slab_off(dd0 + g, ts));
                 const double2 v0 = s2[0], v1 = s2[1], v2 = s2[2];
                 W[g][0] = v0.x; W[g][1] = v0.y; W[g][2] = v1.x; W[g][3] = v1.y; W[g][4] = v2.x; W[g][5] = v2.y;
             }
-            for (int j = jb; j < jb + A.L; j += G) {
+            for (int j = jb; j < jb + a.L; j += G) {
 #pragma unroll
                 for (int jj = 0; jj < G; ++jj) {
                     {
-                        constexpr int dummy = 0; (void)dummy;
                         const int slot = (G - jj) % G;
-                        const double2* s2 = reinterpret_cast<const double2*>(trow + (size_t)(dd0 - jj) * ts);
+                        const double2* s2 = reinterpret_cast<const double2*>(trow + cd_slab_off(dd0 - jj, ts));
                         const double2 v0 = s2[0], v1 = s2[1], v2 = s2[2];
                         W[slot][0] = v0.x; W[slot][1] = v0.y; W[slot][2] = v1.x; W[slot][3] = v1.y; W[slot][4] = v2.x; W[slot][5] = v2.y;
                     }
@@ -221,15 +295,15 @@ class_matvec_diag_kernel(const __grid_constant__ ClassDiagArgs A)
                 dd0 -= G;
             }
         }
+        mbar_arrive(&empty_bar[stage]);
     }
-    // fold the slices in order
-    __syncthreads();
-    double* red = cm_smem;                                      // [slices][blk][G][6]
+    // fold the slices in order (own region behind the stages)
+    double* red = cm_smem + (size_t)kCmStages * stage_doubles;  // [slices][blk][G][6]
     if (sl > 0 && active) {
 #pragma unroll
         for (int g = 0; g < G; ++g) red[(((size_t)sl * kCdBlk + blk) * G + g) * 6 + k] = acc[g];
     }
-    __syncthreads();
+    asm volatile("bar.sync 1, %0;" ::"n"(kCdConsumers) : "memory");
     if (sl == 0 && active) {
         for (int s = 1; s < kCdSlices; ++s) {
 #pragma unroll
@@ -239,11 +313,21 @@ class_matvec_diag_kernel(const __grid_constant__ ClassDiagArgs A)
         for (int g = 0; g < G; ++g) {
             const int m = blk * G + g;
             if (m < count) {
-                const size_t o = (size_t)k * a.nr + A.rg_items_pos[begin + m];
+                const size_t o = (size_t)k * a.nr + a.rg_items_pos[begin + m];
                 a.y_out[o] = (a.y_in ? a.y_in[o] : 0.0) + acc[g];
             }
         }
     }
+}
+
+template <class Kern>
+static int cm_set_smem(Kern kern, size_t need, size_t& have)
+{
+    if (need > have) {
+        OQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+        have = need;
+    }
+    return 0;
 }
 
 // y_out = (y_in) + A x for a class-form operand; x / x_stride as in MatOperand
@@ -252,42 +336,48 @@ static int class_matvec(const OqMatrix* A, const double* x, size_t x_stride, con
 {
     const ClassOperand& c = *A->cls;
     if (c.nctas == 0) return 0;
-    ClassMvArgs a{};
-    a.Tm = c.Tm.p; a.ts = c.ts; a.n1 = c.n1; a.ns1 = c.ns1; a.ns23 = c.ns23;
-    a.rc1 = c.rc1.p; a.sc1 = c.sc1.p; a.D1 = c.D1.p; a.D23 = c.D23.p;
-    a.rg_items = c.rg_items.p; a.sg_ptr = c.sg_ptr.p; a.sg_items = c.sg_items.p; a.sg_order = c.sg_order.p;
-    a.cta_row = c.cta_row.p; a.cta_begin = c.cta_begin.p; a.cta_count = c.cta_count.p;
-    a.rb = c.rb; a.max_sg = c.max_sg; a.nr = c.nr; a.ns = c.ns;
-    a.x = x; a.x_stride = x_stride; a.y_in = y_in; a.y_out = y_out; a.pw = pw; a.done = done;
     // OQ_CLASSMV=generic keeps the general kernel (validation twin of the diagonal fast path)
     const char* env = getenv("OQ_CLASSMV");
-    if (c.diag_ok && c.ndctas > 0 && !(env && strcmp(env, "generic") == 0)) {
-        ClassDiagArgs d{};
-        d.b = a;
-        d.b.cta_row = c.dcta_row.p; d.b.cta_begin = c.dcta_begin.p; d.b.cta_count = c.dcta_count.p;
-        d.diag = c.diag.p; d.rpos = c.rpos.p; d.sg_bypos = c.sg_bypos.p; d.rg_items_pos = c.rg_items_pos.p;
-        d.npos = c.npos; d.L = c.dL;
+    const bool diag = c.diag_ok && c.ndctas > 0 && !(env && strcmp(env, "generic") == 0);
+    ClassMvArgs a{};
+    a.ts = c.ts; a.n1 = c.n1; a.ns1 = c.ns1; a.ns23 = c.ns23;
+    a.rc1 = c.rc1.p; a.D1 = c.D1.p; a.D23 = c.D23.p;
+    a.rg_items = c.rg_items.p; a.sg_ptr = c.sg_ptr.p; a.sg_order = c.sg_order.p;
+    a.nr = c.nr; a.y_in = y_in; a.y_out = y_out; a.done = done;
+    // 1. the forcing vector in group order (waits for the peers)
+    const int* xmap = diag ? c.dxmap.p : c.xmap.p;
+    const int xstride = diag ? kCdSlices * c.dL : c.xstride;
+    double* xg = diag ? c.dxg.p : c.xg.p;
+    const size_t nslots = (size_t)c.ns23 * xstride;
+    const unsigned gblocks = (unsigned)std::min<size_t>((nslots + 255) / 256, 148 * 8);
+    if (c.P == 6) class_gather_x_kernel<6><<<gblocks, 256, 0, st>>>(xmap, nslots, c.ns, x, x_stride, pw, done, xg);
+    else class_gather_x_kernel<1><<<gblocks, 256, 0, st>>>(xmap, nslots, c.ns, x, x_stride, pw, done, xg);
+    OQ_LAUNCHED();
+    a.xg = xg; a.xstride = xstride;
+    // 2. the product
+    if (diag) {
+        a.Tm = c.Td.p; a.noff = c.noff; a.L = c.dL;
+        a.cta_row = c.dcta_row.p; a.cta_begin = c.dcta_begin.p; a.cta_count = c.dcta_count.p;
+        a.rpos = c.rpos.p; a.rg_items_pos = c.rg_items_pos.p;
         static size_t dsmem_set = 48 * 1024;
-        if (c.dsmem > dsmem_set) {
-            OQ_CUDA(cudaFuncSetAttribute(class_matvec_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.dsmem));
-            dsmem_set = c.dsmem;
-        }
-        class_matvec_diag_kernel<<<c.ndctas, kCdThreads, c.dsmem, st>>>(d);
+        OQ_TRY(cm_set_smem(class_matvec_diag_kernel, c.dsmem, dsmem_set));
+        class_matvec_diag_kernel<<<c.ndctas, kCdThreads, c.dsmem, st>>>(a);
         OQ_LAUNCHED();
         return 0;
     }
-    void (*kern)(const ClassMvArgs) = nullptr;
-    int which = -1;
-    if (c.K == 6 && c.P == 6) { kern = class_matvec_kernel<6, 6>; which = 0; }
-    else if (c.K == 6 && c.P == 1) { kern = class_matvec_kernel<6, 1>; which = 1; }
-    else if (c.K == 1 && c.P == 6) { kern = class_matvec_kernel<1, 6>; which = 2; }
-    OQ_CHECK(kern, "class-form operand with %dx%d blocks is not supported", c.K, c.P);
+    a.Tm = c.Tm.p; a.csg = c.csg.p; a.d1_smem = c.d1_smem ? 1 : 0;
+    a.cta_row = c.cta_row.p; a.cta_begin = c.cta_begin.p; a.cta_count = c.cta_count.p;
     static size_t smem_set[3] = {48 * 1024, 48 * 1024, 48 * 1024};
-    if (c.smem > smem_set[which]) {
-        OQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
-        smem_set[which] = c.smem;
-    }
-    kern<<<c.nctas, kCmThreads, c.smem, st>>>(a);
+    if (c.K == 6 && c.P == 6) {
+        OQ_TRY(cm_set_smem(class_matvec_kernel<6, 6>, c.smem, smem_set[0]));
+        class_matvec_kernel<6, 6><<<c.nctas, kCmThreads, c.smem, st>>>(a);
+    } else if (c.K == 6 && c.P == 1) {
+        OQ_TRY(cm_set_smem(class_matvec_kernel<6, 1>, c.smem, smem_set[1]));
+        class_matvec_kernel<6, 1><<<c.nctas, kCmThreads, c.smem, st>>>(a);
+    } else if (c.K == 1 && c.P == 6) {
+        OQ_TRY(cm_set_smem(class_matvec_kernel<1, 6>, c.smem, smem_set[2]));
+        class_matvec_kernel<1, 6><<<c.nctas, kCmThreads, c.smem, st>>>(a);
+    } else return fail("class-form operand with %dx%d blocks is not supported", c.K, c.P);
     OQ_LAUNCHED();
     return 0;
 }

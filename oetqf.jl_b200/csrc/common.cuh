@@ -110,6 +110,9 @@ void sincosd(double deg, double* s, double* c);
 
 constexpr int kCdG = 8, kCdBlk = 8, kCdSlices = 4;     // class_matvec_diag_kernel: window length, receiver blocks, source slices
 
+// row stride (16-bit entries) of the D1 rows class_matvec_kernel keeps in shared memory: smallest value >= ns1 that is 2 mod 4
+inline __host__ __device__ int cm_d1_stride(int ns1) { return ns1 + ((6 - (ns1 & 3)) & 3); }
+
 // Class form of a Green's operand (classmat.cuh): the table of DISTINCT kernels of a matrix whose (receiver, source)
 // pairs fall into translation classes, and the maps from a pair to its class.  An OqMatrix in this form has no dense
 // storage; the RHS multiplies straight from the table (class_matvec_kernel).
@@ -122,19 +125,24 @@ struct ClassOperand {
     DevBuf<int> rc1, sc1, D1, D23;         // x class of every local receiver / every source; pair-class maps [nr1*ns1], [nr23*ns23]
     DevBuf<int> rc23, sc23;                // (y,z) classes (dense expansion only)
     DevBuf<int> sg_order;                  // [nr23][ns23] per row of D23: source groups in ascending class order
-    DevBuf<int> rg_items, sg_ptr, sg_items;// receivers ordered by (y,z) class; sources grouped by (y,z) class (CSR over ns23 groups)
-    DevBuf<int> cta_row, cta_begin, cta_count;   // work list: one CTA = a run of <= rb receivers of one (y,z) class (its row of D23)
-    int nctas = 0, rb = 32, max_sg = 0;
+    DevBuf<int> rg_items, sg_ptr;          // receivers ordered by (y,z) class; sources grouped by (y,z) class (CSR over ns23 groups)
+    DevBuf<int> xmap, csg;                 // [ns23][xstride]: source of a group slot (-1: padding) and its x class
+    DevBuf<double> xg;                     // [ns23][xstride][PX] forcing values in group order (scratch of an evaluation)
+    int xstride = 0;
+    DevBuf<int> cta_row, cta_begin, cta_count;   // work list: one CTA = a run of <= 64 receivers of one (y,z) class (its row of D23)
+    int nctas = 0, max_sg = 0;
     size_t smem = 0;
+    bool d1_smem = false;                  // the D1 rows of a CTA's receivers fit shared memory beside the stages
     double table_bytes = 0;
     // diagonal fast path (class_matvec_diag_kernel): 6x6 operands whose x classes depend on the DIFFERENCE of integer
     // x positions only (receivers and sources on one equidistant grid along x: the Toeplitz structure of GF.jl:31-71)
     bool diag_ok = false;
-    int npos = 0, dL = 0;                  // x positions; source positions per slice (multiple of the window length)
-    DevBuf<int> diag;                      // [2 npos - 1]: (receiver position - source position + npos - 1) -> x class, -1: none
+    int npos = 0, dL = 0, noff = 0;        // x positions; source positions per slice (multiple of the window length); padded offsets
+    DevBuf<double> Td;                     // [n23][noff][ts] the table in offset order, zero padded
     DevBuf<int> rg_items_pos;              // receivers ordered by ((y,z) class, x position); every CTA run is contiguous in position
     DevBuf<int> rpos;                      // [nr] x position of every local receiver
-    DevBuf<int> sg_bypos;                  // [ns23][npos]: the source of a (y,z) group at an x position, -1: none
+    DevBuf<int> dxmap;                     // [ns23][4 dL]: the source of a (y,z) group at an x position, -1: none
+    DevBuf<double> dxg;                    // [ns23][4 dL][6]
     DevBuf<int> dcta_row, dcta_begin, dcta_count;
     int ndctas = 0;
     size_t dsmem = 0;

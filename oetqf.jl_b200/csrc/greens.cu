@@ -1240,8 +1240,10 @@ int oq_matrix_form(const OqMatrix* a, int* form, double* device_bytes)
     if (device_bytes) {
         if (a->cls) {
             const ClassOperand& c = *a->cls;
-            *device_bytes = c.table_bytes + 4.0 * (double)(c.rc1.n + c.sc1.n + c.D1.n + c.D23.n + c.rc23.n + c.sc23.n + c.rg_items.n +
-                                                           c.sg_ptr.n + c.sg_items.n + c.cta_row.n + c.cta_begin.n + c.cta_count.n);
+            *device_bytes = c.table_bytes + 8.0 * (double)(c.xg.n + c.dxg.n) +
+                            4.0 * (double)(c.rc1.n + c.sc1.n + c.D1.n + c.D23.n + c.rc23.n + c.sc23.n + c.rg_items.n + c.sg_ptr.n +
+                                           c.sg_order.n + c.xmap.n + c.csg.n + c.dxmap.n + c.rg_items_pos.n + c.rpos.n +
+                                           c.cta_row.n + c.cta_begin.n + c.cta_count.n + c.dcta_row.n + c.dcta_begin.n + c.dcta_count.n);
         } else *device_bytes = 8.0 * (double)a->d.n;
     }
     return 0;

@@ -403,6 +403,22 @@ class_table_transpose_kernel(const double* __restrict__ T, size_t ncls, int KP, 
     Tm[t] = m < KP ? T[(size_t)m * ncls + c] : 0.0;
 }
 
+// Td[c23][o][:] = Tm[c23][diag[o - pl]][:] (zeros where there is no such offset): the table in offset order
+__global__ void __launch_bounds__(256)
+class_table_offset_kernel(const double* __restrict__ Tm, const int* __restrict__ diag, size_t n23, int n1, int noff, int pl,
+                          int ndiag, int ts, double* __restrict__ Td)
+{
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n23 * noff * ts) return;
+    const int m = (int)(t % ts);
+    const size_t co = t / ts;
+    const int o = (int)(co % noff);
+    const size_t c23 = co / noff;
+    const int idx = o - pl;
+    const int cls = (idx >= 0 && idx < ndiag) ? diag[idx] : -1;
+    Td[t] = cls >= 0 ? Tm[(c23 * n1 + cls) * ts + m] : 0.0;
+}
+
 // The class form of a shard: table (class-major copy), class maps and the work list of class_matvec_kernel.
 // `pc` is restricted to the shard's receivers; `nr` local receiver units, `ns` source units.
 
@@ -500,9 +516,8 @@ static inline int make_class_operand(const Hex8PairClasses& pc, const DevBuf<dou
     auto ctas_for = [&](int rb) { long long n = 0; for (int g = 0; g < nr23; ++g) n += (rptr[g + 1] - rptr[g] + rb - 1) / rb; return n; };
     // a fixed run length: the number of source slices (256 / rb) fixes the association order of a receiver's sum, which
     // must not depend on the shard
-    const int rb = 64;
+    const int rb = 64;                                          // = kCmRb of classmat.cuh
     (void)maxcount; (void)ctas_for;
-    c.rb = rb;
     std::vector<int> crow, cbeg, ccnt;
     for (int g = 0; g < nr23; ++g)
         for (int b = rptr[g]; b < rptr[g + 1]; b += rb) {
@@ -523,16 +538,33 @@ static inline int make_class_operand(const Hex8PairClasses& pc, const DevBuf<dou
     }
     OQ_TRY(c.rg_items.upload(ritems.data(), ritems.size()));
     OQ_TRY(c.sg_ptr.upload(sptr.data(), sptr.size()));
-    OQ_TRY(c.sg_items.upload(sitems.data(), sitems.size()));
     if (c.nctas) {
         OQ_TRY(c.cta_row.upload(crow.data(), crow.size()));
         OQ_TRY(c.cta_begin.upload(cbeg.data(), cbeg.size()));
         OQ_TRY(c.cta_count.upload(ccnt.data(), ccnt.size()));
     }
     const int PX = (P + 1) & ~1;
-    const size_t stage = ((size_t)c.n1 * c.ts + (size_t)c.max_sg * PX) * sizeof(double) + round_up((size_t)c.max_sg * sizeof(int), 16);
-    const size_t red = (size_t)256 * K * sizeof(double);
-    c.smem = std::max(stage, red);
+    // the sources of every group in slot order (padded to a multiple of 8 slots): what class_gather_x_kernel gathers by
+    // and the x classes the CTAs fetch beside the forcing values
+    c.xstride = (int)round_up((size_t)std::max(c.max_sg, 1), 8);
+    {
+        std::vector<int> xmap((size_t)c.ns23 * c.xstride, -1), csg((size_t)c.ns23 * c.xstride, 0);
+        for (int g = 0; g < c.ns23; ++g)
+            for (int j = sptr[g]; j < sptr[g + 1]; ++j) {
+                xmap[(size_t)g * c.xstride + (j - sptr[g])] = sitems[j];
+                csg[(size_t)g * c.xstride + (j - sptr[g])] = pc.g1.scls[sitems[j]];
+            }
+        OQ_TRY(c.xmap.upload(xmap.data(), xmap.size()));
+        OQ_TRY(c.csg.upload(csg.data(), csg.size()));
+        OQ_TRY(c.xg.alloc((size_t)c.ns23 * c.xstride * PX));
+    }
+    const size_t stage = (size_t)c.n1 * c.ts * sizeof(double) + (size_t)c.xstride * PX * sizeof(double) + (size_t)c.xstride * sizeof(int);
+    c.smem = 2 * stage + (size_t)256 * K * sizeof(double);
+    {   // the receivers' rows of D1 (64 rows, odd stride) behind the stages, if they fit and leave room for 2 CTAs per SM
+        const size_t d1b = round_up((size_t)64 * cm_d1_stride(c.ns1) * sizeof(unsigned short), 16);
+        c.d1_smem = c.n1 < 65536 && c.smem + d1b <= 110 * 1024;
+        if (c.d1_smem) c.smem += d1b;
+    }
     OQ_CHECK(c.smem <= 226 * 1024, "class form: %d x-classes of %d doubles do not fit shared memory (%zu bytes)", c.n1, c.ts, c.smem);
     c.table_bytes = (double)ncls * c.ts * sizeof(double);
     if (K == 6 && P == 6 && rpos && spos && npos > 0 && nr > 0) {
@@ -540,17 +572,33 @@ static inline int make_class_operand(const Hex8PairClasses& pc, const DevBuf<dou
         c.npos = npos;
         c.dL = (int)round_up((size_t)(npos + kCdSlices - 1) / kCdSlices, kCdG);
         const size_t npad = (size_t)kCdSlices * c.dL, ndp = (size_t)kCdBlk * kCdG + npad;
-        c.dsmem = (ndp * c.ts + npad * 6) * sizeof(double);
-        if (c.dsmem <= 226 * 1024 && find_diagonals(pc, rpos, spos, npos, nr, ns, c, diag, rip, bypos, drow, dbeg, dcnt)) {
-            OQ_TRY(c.diag.upload(diag.data(), diag.size()));
+        c.noff = (int)(npos - 1 + ndp);
+        c.dsmem = 2 * (ndp * c.ts + ndp / 2 + npad * 6) * sizeof(double) + (size_t)kCdSlices * kCdBlk * kCdG * 6 * sizeof(double);
+        size_t free_b = 0, total_b = 0;
+        const double td_bytes = (double)c.n23 * c.noff * c.ts * sizeof(double);
+        const bool fits = cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && td_bytes < 0.5 * (double)free_b;
+        if (fits && c.dsmem <= 226 * 1024 && find_diagonals(pc, rpos, spos, npos, nr, ns, c, diag, rip, bypos, drow, dbeg, dcnt)) {
+            DevBuf<int> ddiag;
+            OQ_TRY(ddiag.upload(diag.data(), diag.size()));
+            OQ_TRY(c.Td.alloc((size_t)c.n23 * c.noff * c.ts));
+            const size_t tot = (size_t)c.n23 * c.noff * c.ts;
+            class_table_offset_kernel<<<(unsigned)((tot + 255) / 256), 256>>>(c.Tm.p, ddiag.p, (size_t)c.n23, c.n1, c.noff, (int)(npad - npos),
+                                                                              2 * npos - 1, c.ts, c.Td.p);
+            OQ_LAUNCHED();
+            OQ_CUDA(cudaDeviceSynchronize());
+            std::vector<int> dxmap((size_t)c.ns23 * npad, -1);
+            for (int g = 0; g < c.ns23; ++g)
+                for (int j = 0; j < npos; ++j) dxmap[(size_t)g * npad + j] = bypos[(size_t)g * npos + j];
+            OQ_TRY(c.dxmap.upload(dxmap.data(), dxmap.size()));
+            OQ_TRY(c.dxg.alloc((size_t)c.ns23 * npad * 6));
             OQ_TRY(c.rg_items_pos.upload(rip.data(), rip.size()));
             OQ_TRY(c.rpos.upload(rpos, nr));
-            OQ_TRY(c.sg_bypos.upload(bypos.data(), bypos.size()));
             OQ_TRY(c.dcta_row.upload(drow.data(), drow.size()));
             OQ_TRY(c.dcta_begin.upload(dbeg.data(), dbeg.size()));
             OQ_TRY(c.dcta_count.upload(dcnt.data(), dcnt.size()));
             c.ndctas = (int)drow.size();
             c.diag_ok = true;
+            c.table_bytes += td_bytes;
         }
     }
     OQ_CUDA(cudaDeviceSynchronize());
