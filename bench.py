@@ -454,6 +454,44 @@ def example_extra(oq):
             "tsit5_rhs_per_s": 6 * steps / wall, "one_simulated_year": year}
 
 
+def class_form_extra(oq):
+    """A coupled problem (4 096 fault cells + 4 608 hex8 cells) with the three mantle operands dense (what the north
+    star streams) and in class form (csrc/classmat.cuh: tables of the distinct kernels, no dense storage): bytes held,
+    RHS evaluations/s, and the two derivatives against each other."""
+    fs = W.FaultSpec(32e3, 8e3, 250.0, 250.0)                                   # 128 x 32
+    bs = W.BoxSpec(-fs.x / 2, -10e3, -fs.xi, fs.x, 20e3, -40e3, 32, 9, 16, tuple(np.cumprod(np.ones(16) * 1.1)))
+    mf = oq.gen_mesh("RectOkada", fs.x, fs.xi, fs.dx, fs.dxi, fs.dip)
+    ma = oq.gen_mesh("BEMHex8Mesh", *bs.args())
+    a, b, L, sig = W.fault_properties(mf.x, mf.z, mf.nx, mf.nxi)
+    g, n, d0 = W.mantle_properties(ma.cz)
+    v, th, eps, sg, dl = W.initial_state(mf.nx, mf.nxi, L, ma.cz, g, n, rng=np.random.default_rng(42))
+    v = v * (1 + 0.3 * np.random.default_rng(1).uniform(-1, 1, v.shape))
+    pf = oq.RateStateQuasiDynamicProperty(a, b, L, sig, W.ETA, W.VPL, W.F0, W.V0)
+    pa = oq.PowerLawViscosityProperty(g, n, d0)
+    u0 = oq.ArrayPartition(v, th, eps, sg, dl)
+    gf11 = oq.stress_greens_function(mf, W.LAM, W.MU, buffer_ratio=1.0)
+    out = {"workload": f"coupled RHS, {mf.nx * mf.nxi} fault cells + {len(ma)} hex8 cells, gf11 in FFT form"}
+    dus = {}
+    for form in ("dense", "classes"):
+        ops = (oq.device_fault_mantle(mf, ma, W.LAM, W.MU, buffer_ratio=1.0, form=form),
+               oq.device_mantle_fault(ma, mf, W.LAM, W.MU, form=form),
+               oq.device_mantle_mantle(ma, W.LAM, W.MU, form=form))
+        prob = oq.assemble(gf11, *ops, pf, pa, u0, (0.0, 1.0), gf11_form="fft")
+        prob.p.set_state(u0.x)
+        prob.p.rhs_resident(5)
+        ms = prob.p.rhs_resident(50) / 50
+        du = u0.similar()
+        prob.p.get_du(du.x)
+        dus[form] = du
+        out[form] = {"rhs_evals_per_s": 1e3 / ms, "rhs_ms": ms, "operand_bytes": sum(m.form()["device_bytes"] for m in ops)}
+        del prob
+        for m in ops:
+            m.free()
+    out["speedup"] = out["dense"]["rhs_ms"] / out["classes"]["rhs_ms"]
+    out["max_rel_diff_vs_dense"] = max(comp_rel_err(x, y) for x, y in zip(dus["classes"].x, dus["dense"].x))
+    return out
+
+
 def _matvec_kernel_name(world):
     """the kernel oq_rhs launches for the dense operands (csrc/rhs.cu: matvec_variant): OQ_MATVEC overrides, else the
     fused panel kernel on one GPU and the forcing + streaming pair on row shards"""
@@ -667,7 +705,7 @@ def run_ours(args):
             try:
                 fp64_peak = oq.measure_fp64_peak()
                 line["extra"] = {"assembly": assembly_extras(oq, fp64_peak), "example": example_extra(oq),
-                                 "fft_form": fft_form_extra(oq),
+                                 "fft_form": fft_form_extra(oq), "class_form": class_form_extra(oq),
                                  "hbm_only": hbm_only_extra(args),
                                  "hbm_copy_gbs_own_kernel": oq.measure_hbm_copy(1 << 30) / 1e9}
                 # the plain streaming fraction (every byte from HBM on every evaluation) belongs next to the

@@ -85,7 +85,7 @@ __device__ __forceinline__ void cm_bulk_load(void* dst, const void* src, unsigne
 // ---- general kernel: every (receiver, source) pair looks its x class up in D1 ------------------------------
 // The rows of D1 of the CTA's receivers sit in shared memory as 16-bit class ids (row stride = 2 mod 4 entries, i.e. an
 // odd number of 32-bit words: conflict free) when they fit (d1_smem).
-template <int K, int P>
+template <int K, int P, bool D1S>
 __global__ void __launch_bounds__(kCmThreads)
 class_matvec_kernel(const __grid_constant__ ClassMvArgs a)
 {
@@ -132,7 +132,7 @@ class_matvec_kernel(const __grid_constant__ ClassMvArgs a)
     // the receivers' rows of D1 in shared memory (behind the stages and the fold area)
     unsigned short* d1s = reinterpret_cast<unsigned short*>(cm_smem + (size_t)kCmStages * stage_doubles + (size_t)kCmConsumers * K);
     const int ns1p = cm_d1_stride(a.ns1);
-    if (a.d1_smem) {
+    if (D1S) {
         for (int q = t; q < count * a.ns1; q += kCmConsumers) {
             const int ii = q / a.ns1, b = q - ii * a.ns1;
             d1s[ii * ns1p + b] = (unsigned short)__ldg(a.D1 + (size_t)a.rc1[a.rg_items[begin + ii]] * a.ns1 + b);
@@ -140,9 +140,25 @@ class_matvec_kernel(const __grid_constant__ ClassMvArgs a)
         asm volatile("bar.sync 1, %0;" ::"n"(kCmConsumers) : "memory");
     }
     const unsigned short* d1mine = d1s + i * ns1p;
-    double acc[K];
+    // two interleaved partial sums per output (sources j and j + 4 of a slice are in flight together: twice the
+    // independent work per thread; the association order stays a function of the source index alone)
+    double acc[K], acc2[K];
 #pragma unroll
-    for (int k = 0; k < K; ++k) acc[k] = 0.0;
+    for (int k = 0; k < K; ++k) { acc[k] = 0.0; acc2[k] = 0.0; }
+    auto lookup = [&](int b) -> int { return D1S ? (int)d1mine[b] : __ldg(d1row + b); };
+    auto pair_fma = [&](const double* Ts, const double* xs, int c1, int j, double (&sum)[K]) {
+        const double2* t2 = reinterpret_cast<const double2*>(Ts + (size_t)c1 * a.ts);
+        double tv[KP];
+#pragma unroll
+        for (int q = 0; q < KP / 2; ++q) { const double2 v = t2[q]; tv[2 * q] = v.x; tv[2 * q + 1] = v.y; }
+        const double* xv = xs + j * PX;
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            const double xp = xv[p];
+#pragma unroll
+            for (int k = 0; k < K; ++k) sum[k] = fma(tv[k * P + p], xp, sum[k]);
+        }
+    };
     for (int it = 0; it < a.ns23; ++it) {
         const int stage = it % kCmStages;
         const int sg = order[it];
@@ -152,24 +168,18 @@ class_matvec_kernel(const __grid_constant__ ClassMvArgs a)
         const int* cs = reinterpret_cast<const int*>(xs + (size_t)a.xstride * PX);
         mbar_wait(&full_bar[stage], ((unsigned)(it / kCmStages)) & 1u);
         if (active) {
-#pragma unroll 2
-            for (int j = sl; j < sn; j += kCmSlices) {
-                const int c1 = a.d1_smem ? (int)d1mine[cs[j]] : __ldg(d1row + cs[j]);
-                const double2* t2 = reinterpret_cast<const double2*>(Ts + (size_t)c1 * a.ts);
-                double tv[KP];
-#pragma unroll
-                for (int q = 0; q < KP / 2; ++q) { const double2 v = t2[q]; tv[2 * q] = v.x; tv[2 * q + 1] = v.y; }
-                const double* xv = xs + j * PX;
-#pragma unroll
-                for (int p = 0; p < P; ++p) {
-                    const double xp = xv[p];
-#pragma unroll
-                    for (int k = 0; k < K; ++k) acc[k] = fma(tv[k * P + p], xp, acc[k]);
-                }
+            int j = sl;
+            for (; j + kCmSlices < sn; j += 2 * kCmSlices) {
+                const int ca = lookup(cs[j]), cb = lookup(cs[j + kCmSlices]);
+                pair_fma(Ts, xs, ca, j, acc);
+                pair_fma(Ts, xs, cb, j + kCmSlices, acc2);
             }
+            if (j < sn) pair_fma(Ts, xs, lookup(cs[j]), j, acc);
         }
         mbar_arrive(&empty_bar[stage]);
     }
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[k] += acc2[k];
     // fold the slices in order (own region behind the stages)
     double* red = cm_smem + (size_t)kCmStages * stage_doubles;  // [slices][rb][K]
     if (sl > 0 && active) {
@@ -367,17 +377,17 @@ static int class_matvec(const OqMatrix* A, const double* x, size_t x_stride, con
     }
     a.Tm = c.Tm.p; a.csg = c.csg.p; a.d1_smem = c.d1_smem ? 1 : 0;
     a.cta_row = c.cta_row.p; a.cta_begin = c.cta_begin.p; a.cta_count = c.cta_count.p;
-    static size_t smem_set[3] = {48 * 1024, 48 * 1024, 48 * 1024};
-    if (c.K == 6 && c.P == 6) {
-        OQ_TRY(cm_set_smem(class_matvec_kernel<6, 6>, c.smem, smem_set[0]));
-        class_matvec_kernel<6, 6><<<c.nctas, kCmThreads, c.smem, st>>>(a);
-    } else if (c.K == 6 && c.P == 1) {
-        OQ_TRY(cm_set_smem(class_matvec_kernel<6, 1>, c.smem, smem_set[1]));
-        class_matvec_kernel<6, 1><<<c.nctas, kCmThreads, c.smem, st>>>(a);
-    } else if (c.K == 1 && c.P == 6) {
-        OQ_TRY(cm_set_smem(class_matvec_kernel<1, 6>, c.smem, smem_set[2]));
-        class_matvec_kernel<1, 6><<<c.nctas, kCmThreads, c.smem, st>>>(a);
-    } else return fail("class-form operand with %dx%d blocks is not supported", c.K, c.P);
+    static size_t smem_set[6] = {48 * 1024, 48 * 1024, 48 * 1024, 48 * 1024, 48 * 1024, 48 * 1024};
+#define OQ_CM_LAUNCH(KK, PP, DD, IDX)                                                          \
+    do {                                                                                        \
+        OQ_TRY(cm_set_smem(class_matvec_kernel<KK, PP, DD>, c.smem, smem_set[IDX]));           \
+        class_matvec_kernel<KK, PP, DD><<<c.nctas, kCmThreads, c.smem, st>>>(a);               \
+    } while (0)
+    if (c.K == 6 && c.P == 6) { if (c.d1_smem) OQ_CM_LAUNCH(6, 6, true, 0); else OQ_CM_LAUNCH(6, 6, false, 1); }
+    else if (c.K == 6 && c.P == 1) { if (c.d1_smem) OQ_CM_LAUNCH(6, 1, true, 2); else OQ_CM_LAUNCH(6, 1, false, 3); }
+    else if (c.K == 1 && c.P == 6) { if (c.d1_smem) OQ_CM_LAUNCH(1, 6, true, 4); else OQ_CM_LAUNCH(1, 6, false, 5); }
+    else return fail("class-form operand with %dx%d blocks is not supported", c.K, c.P);
+#undef OQ_CM_LAUNCH
     OQ_LAUNCHED();
     return 0;
 }

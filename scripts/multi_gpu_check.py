@@ -1,5 +1,8 @@
 """Multi-GPU parity check (run under torchrun, one rank per GPU): row-sharded RHS and integrator vs the
-single-GPU result of the same problem.  Exit code 0 = all ranks agree."""
+single-GPU result of the same problem.  Exit code 0 = all ranks agree.
+
+  multi_gpu_check.py [dense|classes]     storage of the three mantle operands on the shards (the single-GPU reference
+                                         is always the dense form); classes = csrc/classmat.cuh"""
 import os
 import sys
 
@@ -24,6 +27,8 @@ def main():
     oq.init(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ok = True
+    form = sys.argv[1] if len(sys.argv) > 1 else "dense"
+    rhs_tol = 1e-11 if form == "dense" else 1e-10      # class form: same entries, other summation order
 
     # ---------------- coupled problem: example geometry refined (fault 16x8, mantle 8x3x4) ----------------
     fs = W.FaultSpec(80e3, 8e3, 5e3, 1e3)
@@ -40,11 +45,11 @@ def main():
     u0 = oq.ArrayPartition(v, th, eps, sg, dl)
     tspan = (0.0, 0.05 * W.YEAR)
 
-    def build(rows, elems):
+    def build(rows, elems, form="dense"):
         d11 = oq.device_fault_fault(mf, W.LAM, W.MU, buffer_ratio=1.0, rows=rows)
-        d12 = oq.device_fault_mantle(mf, ma, W.LAM, W.MU, buffer_ratio=1.0, elems=elems)
-        d21 = oq.device_mantle_fault(ma, mf, W.LAM, W.MU, rows=rows)
-        d22 = oq.device_mantle_mantle(ma, W.LAM, W.MU, elems=elems)
+        d12 = oq.device_fault_mantle(mf, ma, W.LAM, W.MU, buffer_ratio=1.0, elems=elems, form=form)
+        d21 = oq.device_mantle_fault(ma, mf, W.LAM, W.MU, rows=rows, form=form)
+        d22 = oq.device_mantle_mantle(ma, W.LAM, W.MU, elems=elems, form=form)
         return oq.assemble(d11, d12, d21, d22, pf, pa, u0, tspan)
 
     def slices(rows, elems):
@@ -55,7 +60,7 @@ def main():
         return [fl(v), fl(th), ml(eps), ml(sg), fl(dl)]
 
     rows, elems = shard(nf, world, rank), shard(ne, world, rank)
-    prob = build(rows, elems)
+    prob = build(rows, elems, form)
     handles = [None] * world
     dist.all_gather_object(handles, prob.p.comm_export(rank, world))
     prob.p.comm_connect(handles)
@@ -75,10 +80,15 @@ def main():
     want = [wf[0].reshape(-1, order="F")[f0:f1], wf[1].reshape(-1, order="F")[f0:f1],
             wf[2][e0:e1, :].reshape(-1, order="F"), wf[3][e0:e1, :].reshape(-1, order="F"),
             wf[4].reshape(-1, order="F")[f0:f1]]
+    # components crossing zero are measured against a fraction of the field's maximum: 1e-9 for the dense shards (same
+    # entries, same summation order up to the shard boundaries), 1e-6 (the bound of tests/test_gpu_rhs.py) for the class form
+    floor = 1e-9 if form == "dense" else 1e-6
     for k, (gt, w) in enumerate(zip(du, want)):
-        den = np.maximum(np.abs(w), 1e-9 * np.max(np.abs(w)) + 1e-300)
+        den = np.maximum(np.abs(w), floor * np.max(np.abs(w)) + 1e-300)
         err = float(np.max(np.abs(gt - w) / den)) if w.size else 0.0
-        if err > 1e-11:
+        if form != "dense":
+            print(f"[rank {rank}] RHS partition {k}: rel err {err:.3e} (form {form})", flush=True)
+        if err > rhs_tol:
             ok = False
             print(f"[rank {rank}] RHS partition {k}: rel err {err:.3e}", flush=True)
 
