@@ -1132,7 +1132,10 @@ int oq_rhs(OqProblem* p, double t, const double* const* u_parts, double* const* 
     // copy-engine launches: the evaluation is two kernel launches and one synchronisation); pageable arrays are
     // staged through device buffers.
     double *du_dev[5], *u_dev[5];
-    if (zero_copy_enabled() && mapped_parts(p, u_parts, u_dev) &&
+    // (operands in class form accumulate into the result vector: they take the staged path, their evaluations are
+    // milliseconds long and two copies of the state do not matter)
+    const bool class_ops = (p->g12 && p->g12->cls) || (p->g21 && p->g21->cls) || (p->g22 && p->g22->cls);
+    if (zero_copy_enabled() && !class_ops && mapped_parts(p, u_parts, u_dev) &&
         mapped_parts(p, const_cast<const double* const*>(du_parts), du_dev)) {
         comm_clear_error(p);
         OQ_TRY(rhs_views(p, view_of_parts(p, u_dev), view_of_parts(p, du_dev), nullptr, nullptr));

@@ -115,7 +115,8 @@ def main():
     col_err = None
     if args.form == "classes" and args.check_sources > 0 and elems[1] > elems[0]:
         rng = np.random.default_rng(7)
-        src = rng.choice(ne, size=args.check_sources, replace=False)
+        src = elems[0] + rng.choice(elems[1] - elems[0], size=args.check_sources, replace=False)   # sources inside the shard:
+        # the columns' largest entries (self and neighbour terms) are then among the receivers checked
         x = np.zeros(6 * ne)
         e0, e1 = elems
         want = np.zeros((6, e1 - e0))
