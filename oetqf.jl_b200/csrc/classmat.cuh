@@ -22,7 +22,8 @@
 // (full/empty mbarriers), so the fetch of group i+1 overlaps the arithmetic on group i.  The forcing values are
 // gathered once per evaluation into group order by class_gather_x_kernel (which is also the kernel that waits for the
 // peers' slices of the forcing vector).  Sums are formed in a fixed order (sources ascending within a slice, slices
-// folded in order): results are bitwise reproducible and independent of the number of ranks.
+// folded in order; kCmParts CTAs per run each walk a quarter of the groups and class_fold_kernel adds the quarters in order):
+// results are bitwise reproducible and independent of the number of ranks.
 #pragma once
 
 #include "tma.cuh"
@@ -34,6 +35,7 @@ constexpr int kCmSlices = 4;                 // source slices
 constexpr int kCmConsumers = kCmRb * kCmSlices;      // 256 compute threads
 constexpr int kCmThreads = kCmConsumers + 32;        // + the producer warp
 constexpr int kCmStages = 2;
+constexpr int kCmParts = 4;                  // CTAs per receiver run: each walks a quarter of the source groups (class_fold_kernel adds them up)
 constexpr int kCmU = 4;                      // interleaved partial sums per output in the general kernel
 
 struct ClassMvArgs {
@@ -48,6 +50,7 @@ struct ClassMvArgs {
     const double* y_in;           // optional: accumulate onto (may alias y_out)
     double* y_out;                // [K][nr]
     const int* done;              // optional device flag: integration complete, skip
+    double* part;                 // [kCmParts][K][nr] partial sums of the source-group quarters (blockIdx.y)
     // diagonal kernel
     const int *rpos, *rg_items_pos;
     int noff, L;
@@ -103,6 +106,7 @@ class_matvec_kernel(const __grid_constant__ ClassMvArgs a)
     const int row = a.cta_row[blockIdx.x], begin = a.cta_begin[blockIdx.x], count = a.cta_count[blockIdx.x];
     const int* d23row = a.D23 + (size_t)row * a.ns23;
     const int* order = a.sg_order + (size_t)row * a.ns23;
+    const int it0 = (int)((long long)a.ns23 * blockIdx.y / kCmParts), it1 = (int)((long long)a.ns23 * (blockIdx.y + 1) / kCmParts);
     const int t = threadIdx.x;
     if (t == 0) {
         for (int s = 0; s < kCmStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kCmConsumers); }
@@ -111,11 +115,11 @@ class_matvec_kernel(const __grid_constant__ ClassMvArgs a)
     __syncthreads();
     if (t >= kCmConsumers) {                                    // ---- producer warp: one lane fetches group after group
         if (t == kCmConsumers) {
-            for (int it = 0; it < a.ns23; ++it) {
-                const int stage = it % kCmStages;
+            for (int it = it0; it < it1; ++it) {
+                const int stage = (it - it0) % kCmStages;
                 const int sg = order[it];
                 const int c23 = d23row[sg];
-                mbar_wait(&empty_bar[stage], (((unsigned)(it / kCmStages)) & 1u) ^ 1u);
+                mbar_wait(&empty_bar[stage], (((unsigned)((it - it0) / kCmStages)) & 1u) ^ 1u);
                 double* st = cm_smem + (size_t)stage * stage_doubles;
                 mbar_arrive_expect_tx(&full_bar[stage], slab_bytes + x_bytes + c_bytes);
                 cm_bulk_load(st, a.Tm + (size_t)c23 * a.n1 * a.ts, slab_bytes, &full_bar[stage]);
@@ -162,14 +166,14 @@ class_matvec_kernel(const __grid_constant__ ClassMvArgs a)
             for (int k = 0; k < K; ++k) sum[k] = fma(tv[k * P + p], xp, sum[k]);
         }
     };
-    for (int it = 0; it < a.ns23; ++it) {
-        const int stage = it % kCmStages;
+    for (int it = it0; it < it1; ++it) {
+        const int stage = (it - it0) % kCmStages;
         const int sg = order[it];
         const int sn = a.sg_ptr[sg + 1] - a.sg_ptr[sg];
         const double* Ts = cm_smem + (size_t)stage * stage_doubles;
         const double* xs = Ts + (size_t)a.n1 * a.ts;
         const int* cs = reinterpret_cast<const int*>(xs + (size_t)a.xstride * PX);
-        mbar_wait(&full_bar[stage], ((unsigned)(it / kCmStages)) & 1u);
+        mbar_wait(&full_bar[stage], ((unsigned)((it - it0) / kCmStages)) & 1u);
         if (active) {
             int j = sl;
             for (; j + (kCmU - 1) * kCmSlices < sn; j += kCmU * kCmSlices) {
@@ -202,10 +206,7 @@ class_matvec_kernel(const __grid_constant__ ClassMvArgs a)
             for (int k = 0; k < K; ++k) acc[0][k] += red[((size_t)s * kCmRb + i) * K + k];
         }
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const size_t o = (size_t)k * a.nr + r;
-            a.y_out[o] = (a.y_in ? a.y_in[o] : 0.0) + acc[0][k];
-        }
+        for (int k = 0; k < K; ++k) a.part[((size_t)blockIdx.y * K + k) * a.nr + r] = acc[0][k];
     }
 }
 
@@ -245,6 +246,7 @@ class_matvec_diag_kernel(const __grid_constant__ ClassMvArgs a)
     const size_t slab_doubles = (size_t)ndp * ts + (size_t)ndp / 2;
     const size_t stage_doubles = slab_doubles + (size_t)npad * 6;
     const int row = a.cta_row[blockIdx.x], begin = a.cta_begin[blockIdx.x], count = a.cta_count[blockIdx.x];
+    const int it0 = (int)((long long)a.ns23 * blockIdx.y / kCmParts), it1 = (int)((long long)a.ns23 * (blockIdx.y + 1) / kCmParts);
     const int t = threadIdx.x;
     if (t == 0) {
         for (int s = 0; s < kCmStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kCdConsumers); }
@@ -256,11 +258,11 @@ class_matvec_diag_kernel(const __grid_constant__ ClassMvArgs a)
             const int p0 = a.rpos[a.rg_items_pos[begin]];
             const int* d23row = a.D23 + (size_t)row * a.ns23;
             const int* order = a.sg_order + (size_t)row * a.ns23;
-            for (int it = 0; it < a.ns23; ++it) {
-                const int stage = it % kCmStages;
+            for (int it = it0; it < it1; ++it) {
+                const int stage = (it - it0) % kCmStages;
                 const int sg = order[it];
                 const int c23 = d23row[sg];
-                mbar_wait(&empty_bar[stage], (((unsigned)(it / kCmStages)) & 1u) ^ 1u);
+                mbar_wait(&empty_bar[stage], (((unsigned)((it - it0) / kCmStages)) & 1u) ^ 1u);
                 double* st = cm_smem + (size_t)stage * stage_doubles;
                 mbar_arrive_expect_tx(&full_bar[stage], slab_bytes + x_bytes);
                 const double* src = a.Tm + ((size_t)c23 * a.noff + p0) * ts;
@@ -277,11 +279,11 @@ class_matvec_diag_kernel(const __grid_constant__ ClassMvArgs a)
 #pragma unroll
     for (int g = 0; g < G; ++g) acc[g] = 0.0;
     const int jb = sl * a.L;
-    for (int it = 0; it < a.ns23; ++it) {
-        const int stage = it % kCmStages;
+    for (int it = it0; it < it1; ++it) {
+        const int stage = (it - it0) % kCmStages;
         const double* Td = cm_smem + (size_t)stage * stage_doubles;
         const double* xs = Td + slab_doubles;
-        mbar_wait(&full_bar[stage], ((unsigned)(it / kCmStages)) & 1u);
+        mbar_wait(&full_bar[stage], ((unsigned)((it - it0) / kCmStages)) & 1u);
         if (active) {
             // window: logical g at source position j sits at dd = blk*G + g - j + npad - 1; physical slot (g - jj) mod G
             double W[G][6];
@@ -333,12 +335,22 @@ class_matvec_diag_kernel(const __grid_constant__ ClassMvArgs a)
 #pragma unroll
         for (int g = 0; g < G; ++g) {
             const int m = blk * G + g;
-            if (m < count) {
-                const size_t o = (size_t)k * a.nr + a.rg_items_pos[begin + m];
-                a.y_out[o] = (a.y_in ? a.y_in[o] : 0.0) + acc[g];
-            }
+            if (m < count) a.part[((size_t)blockIdx.y * 6 + k) * a.nr + a.rg_items_pos[begin + m]] = acc[g];
         }
     }
+}
+
+// y_out = (y_in) + the quarters in order
+__global__ void __launch_bounds__(256)
+class_fold_kernel(const double* __restrict__ part, size_t n, const double* y_in, double* y_out, const int* done)
+{
+    if (done && *reinterpret_cast<const volatile int*>(done)) return;
+    const size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= n) return;
+    double v = part[o];
+#pragma unroll
+    for (int p = 1; p < kCmParts; ++p) v += part[(size_t)p * n + o];
+    y_out[o] = (y_in ? y_in[o] : 0.0) + v;
 }
 
 template <class Kern>
@@ -364,7 +376,9 @@ static int class_matvec(const OqMatrix* A, const double* x, size_t x_stride, con
     a.ts = c.ts; a.n1 = c.n1; a.ns1 = c.ns1; a.ns23 = c.ns23;
     a.rc1 = c.rc1.p; a.D1 = c.D1.p; a.D23 = c.D23.p;
     a.rg_items = c.rg_items.p; a.sg_ptr = c.sg_ptr.p; a.sg_order = c.sg_order.p;
-    a.nr = c.nr; a.y_in = y_in; a.y_out = y_out; a.done = done;
+    a.nr = c.nr; a.y_in = y_in; a.y_out = y_out; a.done = done; a.part = c.part.p;
+    const size_t nout = (size_t)c.K * c.nr;
+    const unsigned fblocks = (unsigned)((nout + 255) / 256);
     // 1. the forcing vector in group order (waits for the peers)
     const int* xmap = diag ? c.dxmap.p : c.xmap.p;
     const int xstride = diag ? kCdSlices * c.dL : c.xstride;
@@ -383,11 +397,13 @@ static int class_matvec(const OqMatrix* A, const double* x, size_t x_stride, con
         static size_t dsmem_set[2] = {48 * 1024, 48 * 1024};
         if (c.dblk == 8) {
             OQ_TRY(cm_set_smem(class_matvec_diag_kernel<8>, c.dsmem, dsmem_set[0]));
-            class_matvec_diag_kernel<8><<<c.ndctas, 8 * 6 * kCdSlices + 32, c.dsmem, st>>>(a);
+            class_matvec_diag_kernel<8><<<dim3(c.ndctas, kCmParts), 8 * 6 * kCdSlices + 32, c.dsmem, st>>>(a);
         } else {
             OQ_TRY(cm_set_smem(class_matvec_diag_kernel<4>, c.dsmem, dsmem_set[1]));
-            class_matvec_diag_kernel<4><<<c.ndctas, 4 * 6 * kCdSlices + 32, c.dsmem, st>>>(a);
+            class_matvec_diag_kernel<4><<<dim3(c.ndctas, kCmParts), 4 * 6 * kCdSlices + 32, c.dsmem, st>>>(a);
         }
+        OQ_LAUNCHED();
+        class_fold_kernel<<<fblocks, 256, 0, st>>>(c.part.p, nout, y_in, y_out, done);
         OQ_LAUNCHED();
         return 0;
     }
@@ -397,13 +413,15 @@ static int class_matvec(const OqMatrix* A, const double* x, size_t x_stride, con
 #define OQ_CM_LAUNCH(KK, PP, DD, IDX)                                                          \
     do {                                                                                        \
         OQ_TRY(cm_set_smem(class_matvec_kernel<KK, PP, DD>, c.smem, smem_set[IDX]));           \
-        class_matvec_kernel<KK, PP, DD><<<c.nctas, kCmThreads, c.smem, st>>>(a);               \
+        class_matvec_kernel<KK, PP, DD><<<dim3(c.nctas, kCmParts), kCmThreads, c.smem, st>>>(a); \
     } while (0)
     if (c.K == 6 && c.P == 6) { if (c.d1_smem) OQ_CM_LAUNCH(6, 6, true, 0); else OQ_CM_LAUNCH(6, 6, false, 1); }
     else if (c.K == 6 && c.P == 1) { if (c.d1_smem) OQ_CM_LAUNCH(6, 1, true, 2); else OQ_CM_LAUNCH(6, 1, false, 3); }
     else if (c.K == 1 && c.P == 6) { if (c.d1_smem) OQ_CM_LAUNCH(1, 6, true, 4); else OQ_CM_LAUNCH(1, 6, false, 5); }
     else return fail("class-form operand with %dx%d blocks is not supported", c.K, c.P);
 #undef OQ_CM_LAUNCH
+    OQ_LAUNCHED();
+    class_fold_kernel<<<fblocks, 256, 0, st>>>(c.part.p, nout, y_in, y_out, done);
     OQ_LAUNCHED();
     return 0;
 }

@@ -128,6 +128,7 @@ struct ClassOperand {
     DevBuf<int> rg_items, sg_ptr;          // receivers ordered by (y,z) class; sources grouped by (y,z) class (CSR over ns23 groups)
     DevBuf<int> xmap, csg;                 // [ns23][xstride]: source of a group slot (-1: padding) and its x class
     DevBuf<double> xg;                     // [ns23][xstride][PX] forcing values in group order (scratch of an evaluation)
+    DevBuf<double> part;                   // [4][K][nr] partial sums of the source-group quarters (scratch of an evaluation)
     int xstride = 0;
     DevBuf<int> cta_row, cta_begin, cta_count;   // work list: one CTA = a run of <= 64 receivers of one (y,z) class (its row of D23)
     int nctas = 0, max_sg = 0;

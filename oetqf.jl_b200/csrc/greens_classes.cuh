@@ -564,6 +564,7 @@ static inline int make_class_operand(const Hex8PairClasses& pc, const DevBuf<dou
         OQ_TRY(c.xmap.upload(xmap.data(), xmap.size()));
         OQ_TRY(c.csg.upload(csg.data(), csg.size()));
         OQ_TRY(c.xg.alloc((size_t)c.ns23 * c.xstride * PX));
+        OQ_TRY(c.part.alloc((size_t)4 * K * (nr > 0 ? nr : 1)));
     }
     const size_t stage = (size_t)c.n1 * c.ts * sizeof(double) + (size_t)c.xstride * PX * sizeof(double) + (size_t)c.xstride * sizeof(int);
     c.smem = 2 * stage + (size_t)256 * K * sizeof(double);
@@ -585,7 +586,7 @@ static inline int make_class_operand(const Hex8PairClasses& pc, const DevBuf<dou
         const double td_bytes = (double)c.n23 * c.noff * c.ts * sizeof(double);
         const bool fits = cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && td_bytes < 0.5 * (double)free_b;
         if (fits && c.dsmem <= 226 * 1024 && find_diagonals(pc, rpos, spos, npos, nr, ns, c, diag, rip, bypos, drow, dbeg, dcnt)) {
-            if (drow.size() < 3 * 148) {        // too few runs of 64 receivers to fill the GPU: runs of 32, three CTAs per SM
+            if (drow.size() * 4 < 3 * 148) {    // too few runs of 64 receivers (x 4 source quarters) to fill the GPU: runs of 32
                 c.dblk = 4;
                 find_diagonals(pc, rpos, spos, npos, nr, ns, c, diag, rip, bypos, drow, dbeg, dcnt, 4);
                 const size_t ndp4 = (size_t)4 * kCdG + npad;
