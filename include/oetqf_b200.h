@@ -137,7 +137,10 @@ int oq_matrix_mantle_mantle(const OqHex8Mesh *ma, const OqQuadrature *quad, doub
  * The entries are those of the dense builders above, bit for bit (same table, same representatives).  Not in the
  * reference, which keeps these operands dense (GF.jl:123-296); it exploits the same invariance for the fault only
  * (GF.jl:31-71).  Returns an error (and no handle) when the mesh has no translation structure to exploit -- fewer
- * than 4 pairs per class -- or when one (y,z) slab of the table exceeds shared memory: keep the dense form then. */
+ * than 4 pairs per class -- or when one (y,z) slab of the table exceeds shared memory: keep the dense form then.
+ * A class-form handle owns the scratch of its evaluation (the forcing vector in group order, the partial sums): one
+ * evaluation at a time per handle (evaluations of one OqProblem are stream-ordered; do not share one class-form
+ * operand between problems that run concurrently). */
 int oq_matrix_fault_mantle_classes(const OqFaultMesh *mf, const OqHex8Mesh *ma, const OqQuadrature *quad, double lambda,
                                    double mu, int ftype, int nrept, double buffer_ratio, int e_begin, int e_end,
                                    OqMatrix **out);

@@ -16,5 +16,7 @@ if [[ " $* " == *" ncu "* ]]; then
       python bench.py --steps 10 --warmup 3 --no-extra --no-cpu --no-parity > gpurun_out/ncu_matvec.log 2>&1
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:"gf_fault_fault|gf_fault_mantle|gf_mantle_fault|gf_mantle_mantle" \
       -c 12 -f -o gpurun_out/prof_assembly python scripts/assembly_probe.py > gpurun_out/ncu_assembly.log 2>&1
+  timeout 400 ncu --set full --clock-control none --import-source on -k regex:class_matvec -c 3 -f -o gpurun_out/prof_classmv \
+      python scripts/coupled_scaling.py --form classes --gf11 fft --steps 1 --warmup 1 --check-sources 0 > gpurun_out/ncu_classmv.log 2>&1
   ls -la gpurun_out/*.ncu-rep
 fi
