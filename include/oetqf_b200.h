@@ -148,6 +148,11 @@ int oq_matrix_mantle_fault_classes(const OqHex8Mesh *ma, const OqFaultMesh *mf, 
                                    int row_begin, int row_end, OqMatrix **out);
 int oq_matrix_mantle_mantle_classes(const OqHex8Mesh *ma, const OqQuadrature *quad, double lambda, double mu,
                                     int e_begin, int e_end, OqMatrix **out);
+/* Host-only view of the plan behind oq_matrix_mantle_mantle_classes for the receivers [e_begin, e_end) (no device is
+ * touched): out8 = { x classes, (y,z) classes, worthwhile (>= 4 pairs per class over the whole mesh), diagonal fast
+ * path available (x class = function of the position difference), receiver runs of the diagonal kernel, x positions,
+ * largest source group, (y,z) classes of the shard's receivers }. */
+int oq_class_form_plan(const OqHex8Mesh *ma, int e_begin, int e_end, long long *out8);
 /* form: 0 dense, 1 class form; device_bytes: HBM held by the operand (dense shard, or class table + maps) */
 int oq_matrix_form(const OqMatrix *a, int *form, double *device_bytes);
 /* Upload a user-supplied column-major m x n host matrix (e.g. one loaded from the reference's HDF5

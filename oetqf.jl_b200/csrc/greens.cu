@@ -1280,6 +1280,31 @@ int oq_hex8_pair_classes(const OqHex8Mesh* ma, const OqFaultMesh* mf, int begin,
     return 0;
 }
 
+int oq_class_form_plan(const OqHex8Mesh* ma, int e_begin, int e_end, long long* out8)
+{
+    OQ_CHECK(ma && ma->n > 0 && out8, "NULL argument");
+    OQ_CHECK(0 <= e_begin && e_begin < e_end && e_end <= ma->n, "element range [%d,%d) outside [0,%d)", e_begin, e_end, ma->n);
+    for (int i = 0; i < 8; ++i) out8[i] = 0;
+    Hex8PairClasses pc;
+    if (!mantle_mantle_classes(ma, e_begin, e_end, pc)) return 0;
+    const int nel = e_end - e_begin;
+    out8[0] = pc.g1.n; out8[1] = pc.g23.n; out8[2] = pc.worthwhile ? 1 : 0;
+    std::vector<double> xall(2 * (size_t)ma->n);
+    for (int e = 0; e < ma->n; ++e) { xall[e] = ma->cx[e]; xall[(size_t)ma->n + e] = ma->qx[e]; }
+    std::vector<int> xidx;
+    const int npos = cluster_values(xall, 1e-12 * span_of(xall, xall), xidx);
+    ClassOperand c;
+    c.ns23 = pc.g23.ns;
+    std::vector<int> diag, rip, bypos, drow, dbeg, dcnt;
+    const bool ok = find_diagonals(pc, xidx.data() + e_begin, xidx.data() + ma->n, npos, nel, ma->n, c, diag, rip, bypos, drow, dbeg, dcnt);
+    out8[3] = ok ? 1 : 0; out8[4] = ok ? (long long)drow.size() : 0; out8[5] = npos;
+    int max_sg = 0;
+    std::vector<int> cnt(pc.g23.ns, 0);
+    for (int s2 = 0; s2 < ma->n; ++s2) max_sg = std::max(max_sg, ++cnt[pc.g23.scls[s2]]);
+    out8[6] = max_sg; out8[7] = pc.g23.nr;
+    return 0;
+}
+
 int oq_matrix_assembly_info(const OqMatrix* a, OqAssemblyInfo* info)
 {
     OQ_CHECK(a && info, "NULL argument");

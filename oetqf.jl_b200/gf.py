@@ -312,6 +312,16 @@ def max_real_eigval(dm: "DeviceMatrix", k: int = 1, tol: float = 1e-6, maxiter: 
     return float(np.max(vals.real))
 
 
+def class_form_plan(ma, elems=None) -> dict:
+    """Host-only plan of device_mantle_mantle(..., form="classes") for the receivers `elems` (oq_class_form_plan)."""
+    e0, e1 = elems if elems is not None else (0, len(ma))
+    out = np.zeros(8, dtype=np.int64)
+    cma = ma.c_struct()
+    _lib.check(_lib.load().oq_class_form_plan(C.byref(cma), int(e0), int(e1), out.ctypes.data_as(C.POINTER(C.c_longlong))))
+    keys = ("x_classes", "yz_classes", "worthwhile", "diagonal", "runs", "x_positions", "max_source_group", "receiver_yz_classes")
+    return {k: (bool(v) if k in ("worthwhile", "diagonal") else int(v)) for k, v in zip(keys, out)}
+
+
 def hex8_pair_classes(ma, mf=None, begin=0, end=None, recv=(), src=()):
     """Host-only view of the class decomposition behind device_mantle_mantle (mf=None) / device_mantle_fault
     (oq_hex8_pair_classes): (counts, rep_recv_x, rep_src_x, rep_recv_yz, rep_src_yz) for the sample pairs."""

@@ -196,3 +196,39 @@ def test_hex8_pair_classes_irregular_mesh(oq):
     ma = oq.BEMHex8Mesh(c[0], c[1], -2e4 - c[2], c[0].copy(), c[1] - d[1] / 2, -2e4 - c[2] + d[2] / 2, d[0], d[1], d[2])
     counts = _check_classes(oq, ma, None, 0, n, rng)
     assert counts[0] * counts[1] >= counts[2]
+
+
+def test_class_form_plan(oq):
+    """the host-side plan of the class-form mantle->mantle operand (csrc/classmat.cuh): an equidistant x grid takes
+    the diagonal kernel (x class = function of the position difference: 2 nx - 1 classes), one run per (y,z) row of
+    receivers, also on row shards; a graded x grid keeps its classes but not the diagonal structure; an irregular
+    mesh has nothing worth a class form"""
+    from oetqf_b200 import gf
+    nx, ny, nz = 12, 5, 4
+    ma = oq.gen_mesh("BEMHex8Mesh", *W.box_for(nx, ny, nz).args())
+    plan = gf.class_form_plan(ma)
+    assert plan["worthwhile"] and plan["diagonal"]
+    assert plan["x_classes"] == 2 * nx - 1 and plan["x_positions"] == nx and plan["max_source_group"] == nx
+    assert plan["yz_classes"] == (2 * ny - 1) * nz * nz and plan["runs"] == ny * nz == plan["receiver_yz_classes"]
+    # a shard that starts and ends inside a row of cells: partial rows are runs of their own
+    shard = gf.class_form_plan(ma, (nx * 3 + 5, nx * 9 + 2))
+    assert shard["diagonal"] and shard["worthwhile"] and shard["runs"] == 7 == shard["receiver_yz_classes"]
+    assert shard["x_classes"] == plan["x_classes"]
+    # cells growing along x: offsets no longer repeat along x (no diagonal structure), y still does
+    xe = np.concatenate([[0.0], np.cumsum(1000.0 * 1.2 ** np.arange(nx))])
+    j, i = np.meshgrid(np.arange(ny), np.arange(nx), indexing="ij")
+    i, j = i.ravel(), j.ravel()
+    cx, dx = (xe[i] + xe[i + 1]) / 2, xe[i + 1] - xe[i]
+    cy, dy = -2e3 + 1e3 * j + 500.0, np.full(i.size, 1e3)
+    cz, dz = np.full(i.size, -9e3), np.full(i.size, 2e3)
+    graded = oq.BEMHex8Mesh(cx, cy, cz, cx.copy(), cy - dy / 2, cz + dz / 2, dx, dy, dz)
+    gp = gf.class_form_plan(graded)
+    assert not gp["diagonal"] and gp["x_classes"] == nx * nx and gp["yz_classes"] == 2 * ny - 1
+    # irregular cells
+    rng = np.random.default_rng(3)
+    n = 30
+    c = rng.random((3, n)) * 1e4
+    d = 100.0 + rng.random((3, n)) * 500.0
+    irr = oq.BEMHex8Mesh(c[0], c[1], -2e4 - c[2], c[0].copy(), c[1] - d[1] / 2, -2e4 - c[2] + d[2] / 2, d[0], d[1], d[2])
+    ip = gf.class_form_plan(irr)
+    assert not ip["worthwhile"] and not ip["diagonal"]
