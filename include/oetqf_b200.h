@@ -153,6 +153,11 @@ int oq_matrix_mantle_mantle_classes(const OqHex8Mesh *ma, const OqQuadrature *qu
  * path available (x class = function of the position difference), receiver runs of the diagonal kernel, x positions,
  * largest source group, (y,z) classes of the shard's receivers }. */
 int oq_class_form_plan(const OqHex8Mesh *ma, int e_begin, int e_end, long long *out8);
+/* Host-only self check of the sliding-window plan of a fault <-> mantle class operand (which = 1: mantle -> fault,
+ * receivers = fault cells [begin, end); 2: fault -> mantle, receivers = elements [begin, end)): every (receiver, source)
+ * pair reached through the plan's maps must get the class the general maps give it.  out6 = { plan found, residues,
+ * runs, pairs checked, mismatches, receivers the plan does not reach }. */
+int oq_class_window_check(const OqHex8Mesh *ma, const OqFaultMesh *mf, int which, int begin, int end, long long *out6);
 /* form: 0 dense, 1 class form; device_bytes: HBM held by the operand (dense shard, or class table + maps) */
 int oq_matrix_form(const OqMatrix *a, int *form, double *device_bytes);
 /* Upload a user-supplied column-major m x n host matrix (e.g. one loaded from the reference's HDF5

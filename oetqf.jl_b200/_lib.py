@@ -77,7 +77,7 @@ EXPORTS = [
     "oq_gf_fault_fault", "oq_gf_fault_mantle", "oq_gf_mantle_fault", "oq_gf_mantle_mantle",
     "oq_dc3d_gradient", "oq_stress_vol_hex8",
     "oq_matrix_fault_fault", "oq_matrix_from_toeplitz", "oq_matrix_fault_mantle", "oq_matrix_mantle_fault", "oq_matrix_mantle_mantle",
-    "oq_matrix_fault_mantle_classes", "oq_matrix_mantle_fault_classes", "oq_matrix_mantle_mantle_classes", "oq_matrix_form", "oq_class_form_plan",
+    "oq_matrix_fault_mantle_classes", "oq_matrix_mantle_fault_classes", "oq_matrix_mantle_mantle_classes", "oq_matrix_form", "oq_class_form_plan", "oq_class_window_check",
     "oq_matrix_from_host", "oq_matrix_to_host", "oq_matrix_rows_to_host", "oq_matrix_shape", "oq_matrix_kernel_ms", "oq_matrix_assembly_info", "oq_hex8_pair_classes", "oq_matrix_destroy", "oq_gemv",
     "oq_problem_create_fault", "oq_problem_create_viscoelastic", "oq_problem_destroy", "oq_problem_layout",
     "oq_profile_enable", "oq_profile_read", "oq_rhs_bytes",

@@ -52,8 +52,8 @@ struct ClassMvArgs {
     const int* done;              // optional device flag: integration complete, skip
     double* part;                 // [kCmParts][K][nr] partial sums of the source-group quarters (blockIdx.y)
     // diagonal kernel
-    const int *rpos, *rg_items_pos;
-    int noff, L;
+    const int *run_m0, *out_map;  // first coarse position of every run; flat y index of (run entry, row), -1: none
+    int noff, L, nout;            // padded offsets per slab, source positions per slice, K * nr
     int d1_smem;                  // general kernel: the receivers' rows of D1 are staged in shared memory
 };
 
@@ -71,6 +71,19 @@ class_gather_x_kernel(const int* __restrict__ xmap, size_t nslots, int ns, const
         const int s = __ldg(xmap + t);
 #pragma unroll
         for (int p = 0; p < PX; ++p) xg[t * PX + p] = (s >= 0 && p < P) ? x[(size_t)p * ns + s] : 0.0;
+    }
+}
+
+// the same with a flat map: xg[t] = x[map[t]] (0 where map < 0) -- the sliding-window kernel's [group][position][column]
+__global__ void __launch_bounds__(256)
+class_gather_flat_kernel(const int* __restrict__ map, size_t n, const double* x0, size_t x_stride, PeerWait pw, const int* done,
+                         double* __restrict__ xg)
+{
+    if (done && *reinterpret_cast<const volatile int*>(done)) return;
+    const double* x = x0 + consumer_parity(pw) * x_stride;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
+        const int m = __ldg(map + t);
+        xg[t] = m >= 0 ? x[m] : 0.0;
     }
 }
 
@@ -255,7 +268,7 @@ class_matvec_diag_kernel(const __grid_constant__ ClassMvArgs a)
     __syncthreads();
     if (t >= kCdConsumers) {                                    // ---- producer warp: one lane fetches group after group
         if (t == kCdConsumers) {
-            const int p0 = a.rpos[a.rg_items_pos[begin]];
+            const int p0 = a.run_m0[blockIdx.x];
             const int* d23row = a.D23 + (size_t)row * a.ns23;
             const int* order = a.sg_order + (size_t)row * a.ns23;
             for (int it = it0; it < it1; ++it) {
@@ -335,7 +348,10 @@ class_matvec_diag_kernel(const __grid_constant__ ClassMvArgs a)
 #pragma unroll
         for (int g = 0; g < G; ++g) {
             const int m = blk * G + g;
-            if (m < count) a.part[((size_t)blockIdx.y * 6 + k) * a.nr + a.rg_items_pos[begin + m]] = acc[g];
+            if (m < count) {
+                const int o = a.out_map[(size_t)(begin + m) * 6 + k];
+                if (o >= 0) a.part[(size_t)blockIdx.y * a.nout + o] = acc[g];
+            }
         }
     }
 }
@@ -379,21 +395,16 @@ static int class_matvec(const OqMatrix* A, const double* x, size_t x_stride, con
     a.nr = c.nr; a.y_in = y_in; a.y_out = y_out; a.done = done; a.part = c.part.p;
     const size_t nout = (size_t)c.K * c.nr;
     const unsigned fblocks = (unsigned)((nout + 255) / 256);
-    // 1. the forcing vector in group order (waits for the peers)
-    const int* xmap = diag ? c.dxmap.p : c.xmap.p;
-    const int xstride = diag ? kCdSlices * c.dL : c.xstride;
-    double* xg = diag ? c.dxg.p : c.xg.p;
-    const size_t nslots = (size_t)c.ns23 * xstride;
-    const unsigned gblocks = (unsigned)std::min<size_t>((nslots + 255) / 256, 148 * 8);
-    if (c.P == 6) class_gather_x_kernel<6><<<gblocks, 256, 0, st>>>(xmap, nslots, c.ns, x, x_stride, pw, done, xg);
-    else class_gather_x_kernel<1><<<gblocks, 256, 0, st>>>(xmap, nslots, c.ns, x, x_stride, pw, done, xg);
-    OQ_LAUNCHED();
-    a.xg = xg; a.xstride = xstride;
-    // 2. the product
     if (diag) {
-        a.Tm = c.Td.p; a.noff = c.noff; a.L = c.dL;
+        // 1. the forcing vector by (source group, coarse position, column) -- waits for the peers
+        const size_t n = (size_t)c.ns23 * kCdSlices * c.dL * 6;
+        class_gather_flat_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 8), 256, 0, st>>>(c.dxmap.p, n, x, x_stride, pw, done, c.dxg.p);
+        OQ_LAUNCHED();
+        // 2. the product
+        a.ts = 38; a.xg = c.dxg.p; a.xstride = kCdSlices * c.dL;
+        a.Tm = c.Td.p; a.noff = c.noff; a.L = c.dL; a.nout = (int)nout;
         a.cta_row = c.dcta_row.p; a.cta_begin = c.dcta_begin.p; a.cta_count = c.dcta_count.p;
-        a.rpos = c.rpos.p; a.rg_items_pos = c.rg_items_pos.p;
+        a.run_m0 = c.dcta_m0.p; a.out_map = c.dout_map.p;
         static size_t dsmem_set[2] = {48 * 1024, 48 * 1024};
         if (c.dblk == 8) {
             OQ_TRY(cm_set_smem(class_matvec_diag_kernel<8>, c.dsmem, dsmem_set[0]));
@@ -407,6 +418,16 @@ static int class_matvec(const OqMatrix* A, const double* x, size_t x_stride, con
         OQ_LAUNCHED();
         return 0;
     }
+    // 1. the forcing vector in group order (waits for the peers)
+    {
+        const size_t nslots = (size_t)c.ns23 * c.xstride;
+        const unsigned gblocks = (unsigned)std::min<size_t>((nslots + 255) / 256, 148 * 8);
+        if (c.P == 6) class_gather_x_kernel<6><<<gblocks, 256, 0, st>>>(c.xmap.p, nslots, c.ns, x, x_stride, pw, done, c.xg.p);
+        else class_gather_x_kernel<1><<<gblocks, 256, 0, st>>>(c.xmap.p, nslots, c.ns, x, x_stride, pw, done, c.xg.p);
+        OQ_LAUNCHED();
+        a.xg = c.xg.p; a.xstride = c.xstride;
+    }
+    // 2. the product
     a.Tm = c.Tm.p; a.csg = c.csg.p; a.d1_smem = c.d1_smem ? 1 : 0;
     a.cta_row = c.cta_row.p; a.cta_begin = c.cta_begin.p; a.cta_count = c.cta_count.p;
     static size_t smem_set[6] = {48 * 1024, 48 * 1024, 48 * 1024, 48 * 1024, 48 * 1024, 48 * 1024};

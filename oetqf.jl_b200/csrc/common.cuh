@@ -135,17 +135,18 @@ struct ClassOperand {
     size_t smem = 0;
     bool d1_smem = false;                  // the D1 rows of a CTA's receivers fit shared memory beside the stages
     double table_bytes = 0;
-    // diagonal fast path (class_matvec_diag_kernel): 6x6 operands whose x classes depend on the DIFFERENCE of integer
-    // x positions only (receivers and sources on one equidistant grid along x: the Toeplitz structure of GF.jl:31-71)
+    // sliding-window kernel (class_matvec_diag_kernel): operands whose x classes are a function of (residue, coarse
+    // position difference) -- receivers and sources on commensurate equidistant grids along x (the Toeplitz structure of
+    // GF.jl:31-71); see OffsetPlan in greens_classes.cuh
     bool diag_ok = false;
+    int dmode = 0, dQ = 1;                 // 0: 6x6 on one grid, 1: 1x6 (receivers finer), 2: 6x1 (sources finer); residues
     int dblk = kCdBlk;                     // receiver blocks of 8 per CTA run (8, or 4 on shards with few runs)
-    int npos = 0, dL = 0, noff = 0;        // x positions; source positions per slice (multiple of the window length); padded offsets
-    DevBuf<double> Td;                     // [n23][noff][ts] the table in offset order, zero padded
-    DevBuf<int> rg_items_pos;              // receivers ordered by ((y,z) class, x position); every CTA run is contiguous in position
-    DevBuf<int> rpos;                      // [nr] x position of every local receiver
-    DevBuf<int> dxmap;                     // [ns23][4 dL]: the source of a (y,z) group at an x position, -1: none
+    int npos = 0, dL = 0, noff = 0;        // coarse source positions; positions per slice (multiple of the window length); padded offsets
+    DevBuf<double> Td;                     // [n23][noff][38] the table in offset order, zero padded
+    DevBuf<int> dxmap;                     // [ns23][4 dL][6]: flat index into x of (source group, coarse position, column), -1: none
     DevBuf<double> dxg;                    // [ns23][4 dL][6]
-    DevBuf<int> dcta_row, dcta_begin, dcta_count;
+    DevBuf<int> dout_map;                  // [entries][6]: flat index into y of (coarse receiver position of a run, row), -1: none
+    DevBuf<int> dcta_row, dcta_begin, dcta_count, dcta_m0;
     int ndctas = 0;
     size_t dsmem = 0;
 };

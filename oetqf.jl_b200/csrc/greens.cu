@@ -760,6 +760,20 @@ int oq_matrix_from_toeplitz(const double* st_host, int nx, int nxi, int row_begi
     return 0;
 }
 
+// x positions of receivers and sources on their common grid + the coarse grid (origin, step) of `coarse` for the
+// sliding-window class kernel; false: no such grid (the operand keeps the general kernel)
+static bool window_grid(const std::vector<double>& xr, const std::vector<double>& xs, int coarse_side /*0 both, 1 sources, 2 receivers*/,
+                        std::vector<int>& pr, std::vector<int>& ps, long long* c0, long long* qstep)
+{
+    std::vector<double> all(xr);
+    all.insert(all.end(), xs.begin(), xs.end());
+    std::vector<int> pos;
+    if (!grid_positions(all, pos)) return false;
+    pr.assign(pos.begin(), pos.begin() + xr.size());
+    ps.assign(pos.begin() + xr.size(), pos.end());
+    return coarse_grid(coarse_side == 2 ? pr : coarse_side == 1 ? ps : pos, *c0, *qstep);
+}
+
 static int build_fault_mantle(const OqFaultMesh* mf, const OqHex8Mesh* ma, const OqQuadrature* quad, double lambda,
                               double mu, int ftype, int nrept, double buffer_ratio, int e_begin, int e_end,
                               OqMatrix** out, bool keep = false)
@@ -814,7 +828,14 @@ static int build_fault_mantle(const OqFaultMesh* mf, const OqHex8Mesh* ma, const
             rc = tm.stop(&M->table_ms);
             if (!rc && keep) {
                 M->cls.reset(new ClassOperand());
-                rc = make_class_operand(pc, table, 6, 1, nel, nf, *M->cls);
+                // receivers = mantle cells (coarse grid along x), sources = fault cells (finer): sliding window per residue
+                std::vector<double> xr(ma->cx, ma->cx + ma->n), xs(nf);
+                for (int j = 0; j < nf; ++j) xs[j] = mf->x[j % mf->nx];
+                std::vector<int> pr, ps;
+                long long c0 = 0, qstep = 1;
+                const bool grid = window_grid(xr, xs, 2, pr, ps, &c0, &qstep);
+                rc = make_class_operand(pc, table, 6, 1, nel, nf, *M->cls, grid ? pr.data() + e_begin : nullptr, grid ? ps.data() : nullptr,
+                                        2, c0, qstep);
             } else {
             if (!rc) rc = tm.start();
             if (!rc) {
@@ -945,7 +966,14 @@ static int build_mantle_fault(const OqHex8Mesh* ma, const OqFaultMesh* mf, doubl
             rc = tm.stop(&M->table_ms);
             if (!rc && keep) {
                 M->cls.reset(new ClassOperand());
-                rc = make_class_operand(pc, table, 1, 6, M->local_rows, ma->n, *M->cls);
+                // receivers = fault cells (fine grid along x), sources = mantle cells (coarse): sliding window per residue
+                std::vector<double> xr(nf), xs(ma->qx, ma->qx + ma->n);
+                for (int j = 0; j < nf; ++j) xr[j] = mf->x[j % mf->nx];
+                std::vector<int> pr, ps;
+                long long c0 = 0, qstep = 1;
+                const bool grid = window_grid(xr, xs, 1, pr, ps, &c0, &qstep);
+                rc = make_class_operand(pc, table, 1, 6, M->local_rows, ma->n, *M->cls, grid ? pr.data() + row_begin : nullptr,
+                                        grid ? ps.data() : nullptr, 1, c0, qstep);
             } else {
             if (!rc) rc = tm.start();
             if (!rc) {
@@ -1059,12 +1087,13 @@ static int build_mantle_mantle(const OqHex8Mesh* ma, const OqQuadrature* quad, d
             rc = tm.stop(&M->table_ms);
             if (!rc && keep) {
                 M->cls.reset(new ClassOperand());
-                // integer x positions of receivers (c_x) and sources (q_x) on their common grid: the diagonal fast path
-                std::vector<double> xall(2 * (size_t)ma->n);
-                for (int e = 0; e < ma->n; ++e) { xall[e] = ma->cx[e]; xall[(size_t)ma->n + e] = ma->qx[e]; }
-                std::vector<int> xidx;
-                const int npos = cluster_values(xall, 1e-12 * span_of(xall, xall), xidx);
-                rc = make_class_operand(pc, table, 6, 6, nel, ma->n, *M->cls, xidx.data() + e_begin, xidx.data() + ma->n, npos);
+                // integer x positions of receivers (c_x) and sources (q_x) on their common grid: the sliding-window kernel
+                std::vector<double> xr(ma->cx, ma->cx + ma->n), xs(ma->qx, ma->qx + ma->n);
+                std::vector<int> pr, ps;
+                long long c0 = 0, qstep = 1;
+                const bool grid = window_grid(xr, xs, 0, pr, ps, &c0, &qstep);
+                rc = make_class_operand(pc, table, 6, 6, nel, ma->n, *M->cls, grid ? pr.data() + e_begin : nullptr, grid ? ps.data() : nullptr,
+                                        0, c0, qstep);
             } else {
             if (!rc) rc = tm.start();
             if (!rc) {
@@ -1242,7 +1271,7 @@ int oq_matrix_form(const OqMatrix* a, int* form, double* device_bytes)
             const ClassOperand& c = *a->cls;
             *device_bytes = c.table_bytes + 8.0 * (double)(c.xg.n + c.dxg.n) +
                             4.0 * (double)(c.rc1.n + c.sc1.n + c.D1.n + c.D23.n + c.rc23.n + c.sc23.n + c.rg_items.n + c.sg_ptr.n +
-                                           c.sg_order.n + c.xmap.n + c.csg.n + c.dxmap.n + c.rg_items_pos.n + c.rpos.n +
+                                           c.sg_order.n + c.xmap.n + c.csg.n + c.dxmap.n + c.dout_map.n + c.dcta_m0.n +
                                            c.cta_row.n + c.cta_begin.n + c.cta_count.n + c.dcta_row.n + c.dcta_begin.n + c.dcta_count.n);
         } else *device_bytes = 8.0 * (double)a->d.n;
     }
@@ -1289,19 +1318,88 @@ int oq_class_form_plan(const OqHex8Mesh* ma, int e_begin, int e_end, long long* 
     if (!mantle_mantle_classes(ma, e_begin, e_end, pc)) return 0;
     const int nel = e_end - e_begin;
     out8[0] = pc.g1.n; out8[1] = pc.g23.n; out8[2] = pc.worthwhile ? 1 : 0;
-    std::vector<double> xall(2 * (size_t)ma->n);
-    for (int e = 0; e < ma->n; ++e) { xall[e] = ma->cx[e]; xall[(size_t)ma->n + e] = ma->qx[e]; }
-    std::vector<int> xidx;
-    const int npos = cluster_values(xall, 1e-12 * span_of(xall, xall), xidx);
-    ClassOperand c;
-    c.ns23 = pc.g23.ns;
-    std::vector<int> diag, rip, bypos, drow, dbeg, dcnt;
-    const bool ok = find_diagonals(pc, xidx.data() + e_begin, xidx.data() + ma->n, npos, nel, ma->n, c, diag, rip, bypos, drow, dbeg, dcnt);
-    out8[3] = ok ? 1 : 0; out8[4] = ok ? (long long)drow.size() : 0; out8[5] = npos;
+    std::vector<double> xr(ma->cx, ma->cx + ma->n), xs(ma->qx, ma->qx + ma->n);
+    std::vector<int> pr, ps;
+    long long c0 = 0, qstep = 1;
+    OffsetPlan pl;
+    const bool ok = window_grid(xr, xs, 0, pr, ps, &c0, &qstep) &&
+                    plan_offsets(pc, 0, pr.data() + e_begin, ps.data(), nel, ma->n, c0, qstep, 6, kCdBlk, 0, pl);
+    out8[3] = ok ? 1 : 0; out8[4] = ok ? (long long)pl.drow.size() : 0; out8[5] = ok ? pl.NS : 0;
     int max_sg = 0;
     std::vector<int> cnt(pc.g23.ns, 0);
     for (int s2 = 0; s2 < ma->n; ++s2) max_sg = std::max(max_sg, ++cnt[pc.g23.scls[s2]]);
     out8[6] = max_sg; out8[7] = pc.g23.nr;
+    return 0;
+}
+
+// Host-only self check of the sliding-window plan of a fault <-> mantle operand (tests): which = 1 mantle -> fault
+// (receivers = fault cells [begin, end)), 2 fault -> mantle (receivers = elements [begin, end)).  out6 = { plan found,
+// residues Q, runs, (receiver, source) pairs checked, pairs whose class through the plan differs from the class maps,
+// receivers not reachable through out_map }.
+int oq_class_window_check(const OqHex8Mesh* ma, const OqFaultMesh* mf, int which, int begin, int end, long long* out6)
+{
+    OQ_CHECK(ma && mf && out6 && (which == 1 || which == 2), "bad argument");
+    for (int i = 0; i < 6; ++i) out6[i] = 0;
+    const int nf = mf->nx * mf->nxi, ne = ma->n;
+    Hex8PairClasses pc;
+    std::vector<double> xr, xs;
+    int K = 1;
+    if (which == 1) {
+        OQ_CHECK(0 <= begin && begin < end && end <= nf, "row range");
+        if (!mantle_fault_classes(ma, mf, begin, end, pc)) return 0;
+        xr.resize(nf); for (int j = 0; j < nf; ++j) xr[j] = mf->x[j % mf->nx];
+        xs.assign(ma->qx, ma->qx + ne);
+    } else {
+        OQ_CHECK(0 <= begin && begin < end && end <= ne, "element range");
+        static const double c1[3] = {0, 0, 0};
+        const double lrept = 2.0 * (mf->dx * mf->nx);
+        if (!fault_mantle_classes(mf, ma, c1, 1, 2, lrept, begin, end, pc)) return 0;
+        xr.assign(ma->cx, ma->cx + ne);
+        xs.resize(nf); for (int j = 0; j < nf; ++j) xs[j] = mf->x[j % mf->nx];
+        K = 6;
+    }
+    const int nr = end - begin, ns = which == 1 ? ne : nf;
+    std::vector<int> pr, ps;
+    long long c0 = 0, qstep = 1;
+    if (!window_grid(xr, xs, which, pr, ps, &c0, &qstep)) return 0;
+    OffsetPlan pl;
+    if (!plan_offsets(pc, which, pr.data() + begin, ps.data(), nr, ns, c0, qstep, K, kCdBlk, 0, pl)) return 0;
+    const int npad = pl.NS;
+    if (!plan_offsets(pc, which, pr.data() + begin, ps.data(), nr, ns, c0, qstep, K, kCdBlk, npad, pl)) return 0;
+    out6[0] = 1; out6[1] = pl.Q; out6[2] = (long long)pl.drow.size();
+    const int nd = pl.MR + pl.NS - 1;
+    std::vector<char> seen(nr, 0);
+    long long checked = 0, bad = 0;
+    for (size_t run = 0; run < pl.drow.size(); ++run)
+        for (int m = 0; m < pl.dcnt[run]; ++m)
+            for (int k = 0; k < 6; ++k) {
+                const int o = pl.out_map[(size_t)(pl.dbeg[run] + m) * 6 + k];
+                if (o < 0) continue;
+                const int r = which == 1 ? o : o % nr;                     // K = 1: y index = r; K = 6: k*nr + r
+                if (which == 2 && o / nr != k) { ++bad; continue; }
+                seen[r] = 1;
+                if (pc.g23.rcls[r] != pl.drow[run]) { ++bad; continue; }
+                const int mp = pl.dm0[run] + m;
+                // every source through xmap
+                for (int g = 0; g < pc.g23.ns; ++g)
+                    for (int j = 0; j < npad; ++j)
+                        for (int c = 0; c < 6; ++c) {
+                            const int xm = pl.xmap[((size_t)g * npad + j) * 6 + c];
+                            if (xm < 0) continue;
+                            const int s2 = which == 1 ? xm % ns : xm;       // P = 6: c*ns + s; P = 1: s
+                            if (which == 1 && (xm / ns != c)) { ++bad; continue; }
+                            if (which == 1 && c != 0) continue;            // one check per source
+                            if (pc.g23.scls[s2] != g) { ++bad; continue; }
+                            const int slot = which == 1 ? k : c;
+                            const int want = pc.g1.D[(size_t)pc.g1.rcls[r] * pc.g1.ns + pc.g1.scls[s2]];
+                            const int got = pl.dcls[(size_t)slot * nd + (mp - j + pl.NS - 1)];
+                            ++checked;
+                            if (got != want) ++bad;
+                        }
+                if (which == 2 && k > 0) break;                             // rows of one receiver share the pairs
+            }
+    out6[3] = checked; out6[4] = bad;
+    for (int r = 0; r < nr; ++r) if (!seen[r]) ++out6[5];
     return 0;
 }
 

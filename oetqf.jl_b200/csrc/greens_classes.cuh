@@ -12,6 +12,7 @@
 // pairs, in which case the caller keeps the tiled kernels.
 #pragma once
 #include <algorithm>
+#include <climits>
 #include <cmath>
 #include <cstring>
 #include <vector>
@@ -403,75 +404,219 @@ class_table_transpose_kernel(const double* __restrict__ T, size_t ncls, int KP, 
     Tm[t] = m < KP ? T[(size_t)m * ncls + c] : 0.0;
 }
 
-// Td[c23][o][:] = Tm[c23][diag[o - pl]][:] (zeros where there is no such offset): the table in offset order
+// Td[c23][o][k][c] (38 doubles per block): the table in OFFSET order for the sliding-window kernel, zero where there
+// is no such offset / residue.  idx = o - npad + NS indexes dcls[slot][idx] (see OffsetPlan); src blocks have `ts_src`
+// doubles: mode 0 [k*6+c], mode 1 (1x6) [c] with slot = k, mode 2 (6x1) [k] with slot = c.
 __global__ void __launch_bounds__(256)
-class_table_offset_kernel(const double* __restrict__ Tm, const int* __restrict__ diag, size_t n23, int n1, int noff, int pl,
-                          int ndiag, int ts, double* __restrict__ Td)
+class_table_offset_kernel(const double* __restrict__ Tm, int ts_src, const int* __restrict__ dcls, int nd, int mode, int Q,
+                          size_t n23, int n1, int noff, int shift, double* __restrict__ Td)
 {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n23 * noff * ts) return;
-    const int m = (int)(t % ts);
-    const size_t co = t / ts;
+    if (t >= n23 * noff * 38) return;
+    const int e = (int)(t % 38);
+    const size_t co = t / 38;
     const int o = (int)(co % noff);
     const size_t c23 = co / noff;
-    const int idx = o - pl;
-    const int cls = (idx >= 0 && idx < ndiag) ? diag[idx] : -1;
-    Td[t] = cls >= 0 ? Tm[(c23 * n1 + cls) * ts + m] : 0.0;
+    double v = 0.0;
+    const int idx = o - shift;
+    if (e < 36 && idx >= 0 && idx < nd) {
+        const int k = e / 6, c = e - k * 6;
+        const int slot = mode == 1 ? k : mode == 2 ? c : 0;
+        if (slot < Q || mode == 0) {
+            const int cls = dcls[(size_t)slot * nd + idx];
+            if (cls >= 0) v = Tm[(c23 * n1 + cls) * ts_src + (mode == 0 ? e : mode == 1 ? c : k)];
+        }
+    }
+    Td[t] = v;
 }
 
 // The class form of a shard: table (class-major copy), class maps and the work list of class_matvec_kernel.
 // `pc` is restricted to the shard's receivers; `nr` local receiver units, `ns` source units.
 
-// Diagonal structure of a 6x6 operand: rpos / spos = integer x positions of the local receivers / of the sources.
-// Returns false (and leaves c.diag_ok unset) when the x classes are not a function of the position difference, when
-// a CTA run of receivers is not contiguous in position, or when two sources of a (y,z) group share a position.
-static inline bool find_diagonals(const Hex8PairClasses& pc, const int* rpos, const int* spos, int npos, int nr, int ns,
-                                  ClassOperand& c, std::vector<int>& diag, std::vector<int>& ritems_pos, std::vector<int>& bypos,
-                                  std::vector<int>& crow, std::vector<int>& cbeg, std::vector<int>& ccnt, int blk = kCdBlk)
+// ---- offset plan of the sliding-window kernel (class_matvec_diag_kernel) ---------------------------------------
+// The kernel multiplies 6x6 blocks indexed by the OFFSET between a coarse receiver position m and a coarse source
+// position j.  Three operand shapes map onto it:
+//   mode 0  mantle -> mantle (6x6): one grid, m = j = x position; block = the class block [k][p]
+//   mode 1  mantle -> fault  (1x6): sources on the coarse grid, receivers on a finer one: fine position = Q*m + rho;
+//           block row k = residue rho of the receiver, columns = the 6 unit strains
+//   mode 2  fault -> mantle  (6x1): receivers on the coarse grid, sources fine: position = Q*j + rho;
+//           block rows = the 6 stress components, column c = residue rho of the source
+// (up to 6 residues).  Everything is found numerically from integer positions on the common fine grid; `false` means the
+// x classes are not a function of (slot, m - j) or the positions are not what the window needs, and the operand keeps the
+// general kernel.
+struct OffsetPlan {
+    int mode = 0, Q = 1;                  // residues in use
+    int MR = 0, NS = 0;                   // coarse receiver positions of the shard, coarse source positions
+    std::vector<int> dcls;                // [6][MR + NS - 1]: class of (slot, m' - j' + NS - 1), -1: none
+    std::vector<int> drow, dbeg, dcnt, dm0;   // runs of <= blk*8 consecutive coarse receiver positions of one (y,z) class
+    std::vector<int> out_map;             // [entries][6]: flat index into y of (entry = coarse position of a run, row k), -1: none
+    std::vector<int> xmap;                // [ns23][npad][6]: flat index into x of (source group, coarse position, column), -1: none
+};
+
+static inline bool floor_divmod(long long t, long long q, long long& m, long long& r)
+{
+    m = t / q; r = t - m * q;
+    if (r < 0) { r += q; --m; }
+    return true;
+}
+
+// rpos / spos: integer x positions (common fine grid) of the local receivers / all sources; c0, qstep: origin and step
+// of the coarse grid in the same units (mode 0: qstep = 1)
+static inline bool plan_offsets(const Hex8PairClasses& pc, int mode, const int* rpos, const int* spos, int nr, int ns,
+                                long long c0, long long qstep, int K, int blk, int npad_for, OffsetPlan& pl)
 {
     const AxisClasses& g1 = pc.g1;
-    std::vector<int> pa(g1.nr, -1), pb(g1.ns, -1);
-    for (int r = 0; r < nr; ++r) { int& q = pa[g1.rcls[r]]; if (q < 0) q = rpos[r]; else if (q != rpos[r]) return false; }
-    for (int s = 0; s < ns; ++s) { int& q = pb[g1.scls[s]]; if (q < 0) q = spos[s]; else if (q != spos[s]) return false; }
-    diag.assign(2 * (size_t)npos - 1, -1);
-    for (int a = 0; a < g1.nr; ++a)
+    if (nr <= 0 || ns <= 0 || qstep <= 0) return false;
+    pl.mode = mode;
+    // coarse index and residue of every receiver / source
+    std::vector<long long> mr(nr), rr(nr), js(ns), rs(ns);
+    for (int r = 0; r < nr; ++r) floor_divmod((long long)rpos[r] - c0, qstep, mr[r], rr[r]);
+    for (int s2 = 0; s2 < ns; ++s2) floor_divmod((long long)spos[s2] - c0, qstep, js[s2], rs[s2]);
+    if (mode != 1) for (int r = 0; r < nr; ++r) if (rr[r] != 0) return false;        // receivers on the coarse grid
+    if (mode != 2) for (int s2 = 0; s2 < ns; ++s2) if (rs[s2] != 0) return false;    // sources on the coarse grid
+    // residues of the fine side -> slots 0..Q-1
+    std::vector<long long> resid;
+    if (mode == 1) resid.assign(rr.begin(), rr.end());
+    else if (mode == 2) resid.assign(rs.begin(), rs.end());
+    else resid.push_back(0);
+    std::sort(resid.begin(), resid.end());
+    resid.erase(std::unique(resid.begin(), resid.end()), resid.end());
+    pl.Q = (int)resid.size();
+    if (pl.Q < 1 || pl.Q > 6) return false;
+    auto slot_of = [&](long long r) { return (int)(std::lower_bound(resid.begin(), resid.end(), r) - resid.begin()); };
+    const long long mmin = *std::min_element(mr.begin(), mr.end()), mmax = *std::max_element(mr.begin(), mr.end());
+    const long long jmin = *std::min_element(js.begin(), js.end()), jmax = *std::max_element(js.begin(), js.end());
+    if (mmax - mmin > (1 << 20) || jmax - jmin > (1 << 20)) return false;
+    pl.MR = (int)(mmax - mmin + 1); pl.NS = (int)(jmax - jmin + 1);
+    const int npad = npad_for > 0 ? npad_for : pl.NS;
+    if (npad < pl.NS) return false;
+    // per x class: one (coarse index, slot)
+    std::vector<long long> am(g1.nr, LLONG_MIN), bj(g1.ns, LLONG_MIN);
+    std::vector<int> aslot(g1.nr, 0), bslot(g1.ns, 0);
+    for (int r = 0; r < nr; ++r) {
+        const int a = g1.rcls[r]; const int sl = mode == 1 ? slot_of(rr[r]) : 0;
+        if (am[a] == LLONG_MIN) { am[a] = mr[r] - mmin; aslot[a] = sl; }
+        else if (am[a] != mr[r] - mmin || aslot[a] != sl) return false;
+    }
+    for (int s2 = 0; s2 < ns; ++s2) {
+        const int b = g1.scls[s2]; const int sl = mode == 2 ? slot_of(rs[s2]) : 0;
+        if (bj[b] == LLONG_MIN) { bj[b] = js[s2] - jmin; bslot[b] = sl; }
+        else if (bj[b] != js[s2] - jmin || bslot[b] != sl) return false;
+    }
+    const int nd = pl.MR + pl.NS - 1;
+    pl.dcls.assign((size_t)6 * nd, -1);
+    for (int a = 0; a < g1.nr; ++a) {
+        if (am[a] == LLONG_MIN) continue;
         for (int b = 0; b < g1.ns; ++b) {
-            if (pa[a] < 0 || pb[b] < 0) continue;
-            int& q = diag[pa[a] - pb[b] + npos - 1];
+            if (bj[b] == LLONG_MIN) continue;
+            const int slot = mode == 1 ? aslot[a] : mode == 2 ? bslot[b] : 0;
+            int& q = pl.dcls[(size_t)slot * nd + (size_t)(am[a] - bj[b] + pl.NS - 1)];
             const int cls = g1.D[(size_t)a * g1.ns + b];
             if (q < 0) q = cls; else if (q != cls) return false;
         }
-    // receivers by ((y,z) class, position); runs of <= kCdBlk*kCdG consecutive positions
+    }
+    // receiver runs
     const int nr23 = pc.g23.nr;
     std::vector<std::vector<int>> groups(nr23);
     for (int r = 0; r < nr; ++r) groups[pc.g23.rcls[r]].push_back(r);
-    ritems_pos.clear(); crow.clear(); cbeg.clear(); ccnt.clear();
+    pl.drow.clear(); pl.dbeg.clear(); pl.dcnt.clear(); pl.dm0.clear(); pl.out_map.clear();
     const int run = blk * kCdG;
     for (int g = 0; g < nr23; ++g) {
-        std::vector<int>& m = groups[g];
-        std::sort(m.begin(), m.end(), [&](int a, int b) { return rpos[a] < rpos[b]; });
+        std::vector<int>& mem = groups[g];
+        std::sort(mem.begin(), mem.end(), [&](int a, int b) { return mr[a] != mr[b] ? mr[a] < mr[b] : rr[a] < rr[b]; });
         size_t k = 0;
-        while (k < m.size()) {
-            size_t e = k + 1;
-            while (e < m.size() && e - k < (size_t)run && rpos[m[e]] == rpos[m[e - 1]] + 1) ++e;
-            if (e < m.size() && e - k < (size_t)run && rpos[m[e]] == rpos[m[e - 1]]) return false;   // two receivers, one position
-            crow.push_back(g); cbeg.push_back((int)ritems_pos.size()); ccnt.push_back((int)(e - k));
-            for (size_t q = k; q < e; ++q) ritems_pos.push_back(m[q]);
-            k = e;
+        while (k < mem.size()) {
+            // one run: consecutive coarse positions starting at mr[mem[k]]
+            const long long m0 = mr[mem[k]];
+            const int entry0 = (int)(pl.out_map.size() / 6);
+            long long mcur = m0;
+            int count = 0;
+            while (k < mem.size() && count < run) {
+                if (mr[mem[k]] != mcur) break;
+                pl.out_map.resize(pl.out_map.size() + 6, -1);
+                int* om = &pl.out_map[pl.out_map.size() - 6];
+                while (k < mem.size() && mr[mem[k]] == mcur) {                 // the receivers of this coarse position
+                    const int r = mem[k];
+                    if (mode == 1) {
+                        const int sl = slot_of(rr[r]);
+                        if (om[sl] >= 0) return false;                         // two receivers, one position
+                        om[sl] = r;                                            // K = 1: y index = r
+                    } else {
+                        if (om[0] >= 0) return false;
+                        for (int kk = 0; kk < K; ++kk) om[kk] = kk * nr + r;
+                    }
+                    ++k;
+                }
+                ++count; ++mcur;
+            }
+            pl.drow.push_back(g); pl.dbeg.push_back(entry0); pl.dcnt.push_back(count); pl.dm0.push_back((int)(m0 - mmin));
         }
     }
-    if ((long long)crow.size() > 4LL * nr23 + 64) return false;          // positions too scattered to be worth it
-    bypos.assign((size_t)c.ns23 * npos, -1);
-    for (int s = 0; s < ns; ++s) {
-        int& q = bypos[(size_t)pc.g23.scls[s] * npos + spos[s]];
-        if (q >= 0) return false;
-        q = s;
+    if ((long long)pl.drow.size() > 4LL * nr23 + 64) return false;             // positions too scattered to be worth it
+    // sources by (group, coarse position, column)
+    const int ns23 = pc.g23.ns;
+    pl.xmap.assign((size_t)ns23 * npad * 6, -1);
+    for (int s2 = 0; s2 < ns; ++s2) {
+        int* xm = &pl.xmap[((size_t)pc.g23.scls[s2] * npad + (size_t)(js[s2] - jmin)) * 6];
+        if (mode == 2) {
+            const int sl = slot_of(rs[s2]);
+            if (xm[sl] >= 0) return false;
+            xm[sl] = s2;                                                       // P = 1: x index = s
+        } else {
+            if (xm[0] >= 0) return false;
+            for (int c = 0; c < 6; ++c) xm[c] = c * ns + s2;                   // x[p*ns + s]
+        }
     }
     return true;
 }
 
+// integer positions of coordinates on their common grid: step = smallest gap between distinct values; false when a
+// value does not sit on that grid (to 1e-6 of the step) or the grid would be absurdly long
+static inline bool grid_positions(const std::vector<double>& x, std::vector<int>& pos)
+{
+    std::vector<int> idx;
+    const int ncl = cluster_values(x, 1e-12 * span_of(x, x), idx);
+    if (ncl < 1) return false;
+    std::vector<double> val(ncl);
+    for (size_t i = 0; i < x.size(); ++i) val[idx[i]] = x[i];
+    double step = 0;
+    for (int c = 1; c < ncl; ++c) step = step == 0 ? val[c] - val[c - 1] : std::min(step, val[c] - val[c - 1]);
+    pos.assign(x.size(), 0);
+    if (ncl == 1) return true;
+    // the step of the common grid may be a fraction of the smallest gap (e.g. centres of cells 5 and 1 units long):
+    // try step / d for small d
+    for (int d = 1; d <= 4; ++d) {
+        const double h = step / d;
+        bool ok = (val[ncl - 1] - val[0]) / h < 4e6;
+        std::vector<long long> p(ncl);
+        for (int c = 0; c < ncl && ok; ++c) {
+            const double t = (val[c] - val[0]) / h;
+            p[c] = (long long)std::llround(t);
+            if (std::fabs(t - (double)p[c]) > 1e-6) ok = false;
+        }
+        if (ok) { for (size_t i = 0; i < x.size(); ++i) pos[i] = (int)p[idx[i]]; return true; }
+    }
+    return false;
+}
+
+// origin and step of an arithmetic progression of positions (the coarse grid); false if they are not one
+static inline bool coarse_grid(const std::vector<int>& pos, long long& c0, long long& qstep)
+{
+    std::vector<int> u(pos);
+    std::sort(u.begin(), u.end());
+    u.erase(std::unique(u.begin(), u.end()), u.end());
+    c0 = u[0]; qstep = 1;
+    if (u.size() == 1) return true;
+    qstep = u[1] - u[0];
+    for (size_t i = 1; i < u.size(); ++i) if (u[i] - u[i - 1] != qstep) return false;
+    return true;
+}
+
+// rpos / spos (optional): integer x positions of the local receivers / all sources on their common grid, with the
+// origin c0 and step qstep of the coarse grid (plan_offsets); mode: 0 6x6 one grid, 1 sources coarse, 2 receivers coarse
 static inline int make_class_operand(const Hex8PairClasses& pc, const DevBuf<double>& table, int K, int P, int nr, int ns,
-                                     ClassOperand& c, const int* rpos = nullptr, const int* spos = nullptr, int npos = 0)
+                                     ClassOperand& c, const int* rpos = nullptr, const int* spos = nullptr, int mode = 0,
+                                     long long c0 = 0, long long qstep = 1)
 {
     c.K = K; c.P = P; c.nr = nr; c.ns = ns;
     c.n1 = pc.g1.n; c.n23 = pc.g23.n; c.ns1 = pc.g1.ns; c.ns23 = pc.g23.ns;
@@ -575,44 +720,47 @@ static inline int make_class_operand(const Hex8PairClasses& pc, const DevBuf<dou
     }
     OQ_CHECK(c.smem <= 226 * 1024, "class form: %d x-classes of %d doubles do not fit shared memory (%zu bytes)", c.n1, c.ts, c.smem);
     c.table_bytes = (double)ncls * c.ts * sizeof(double);
-    if (K == 6 && P == 6 && rpos && spos && npos > 0 && nr > 0) {
-        std::vector<int> diag, rip, bypos, drow, dbeg, dcnt;
-        c.npos = npos;
-        c.dL = (int)round_up((size_t)(npos + kCdSlices - 1) / kCdSlices, kCdG);
-        const size_t npad = (size_t)kCdSlices * c.dL, ndp = (size_t)kCdBlk * kCdG + npad;
-        c.noff = (int)(npos - 1 + ndp);
-        c.dsmem = 2 * (ndp * c.ts + ndp / 2 + npad * 6) * sizeof(double) + (size_t)kCdSlices * kCdBlk * kCdG * 6 * sizeof(double);
-        size_t free_b = 0, total_b = 0;
-        const double td_bytes = (double)c.n23 * c.noff * c.ts * sizeof(double);
-        const bool fits = cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && td_bytes < 0.5 * (double)free_b;
-        if (fits && c.dsmem <= 226 * 1024 && find_diagonals(pc, rpos, spos, npos, nr, ns, c, diag, rip, bypos, drow, dbeg, dcnt)) {
-            if (drow.size() * 4 < 3 * 148) {    // too few runs of 64 receivers (x 4 source quarters) to fill the GPU: runs of 32
+    if (rpos && spos && nr > 0) {
+        // the sliding-window kernel, if the x classes are a function of (residue, coarse offset)
+        OffsetPlan pl;
+        bool ok = plan_offsets(pc, mode, rpos, spos, nr, ns, c0, qstep, K, kCdBlk, 0, pl);      // first pass: NS, MR
+        if (ok) {
+            c.dL = (int)round_up((size_t)(pl.NS + kCdSlices - 1) / kCdSlices, kCdG);
+            const int npad = kCdSlices * c.dL;
+            c.dblk = kCdBlk;
+            ok = plan_offsets(pc, mode, rpos, spos, nr, ns, c0, qstep, K, c.dblk, npad, pl);
+            if (ok && pl.drow.size() * 4 < 3 * 148) {     // too few runs of 64 (x 4 source quarters) to fill the GPU: runs of 32
                 c.dblk = 4;
-                find_diagonals(pc, rpos, spos, npos, nr, ns, c, diag, rip, bypos, drow, dbeg, dcnt, 4);
-                const size_t ndp4 = (size_t)4 * kCdG + npad;
-                c.dsmem = 2 * (ndp4 * c.ts + ndp4 / 2 + npad * 6) * sizeof(double) + (size_t)kCdSlices * 4 * kCdG * 6 * sizeof(double);
+                ok = plan_offsets(pc, mode, rpos, spos, nr, ns, c0, qstep, K, c.dblk, npad, pl);
             }
-            DevBuf<int> ddiag;
-            OQ_TRY(ddiag.upload(diag.data(), diag.size()));
-            OQ_TRY(c.Td.alloc((size_t)c.n23 * c.noff * c.ts));
-            const size_t tot = (size_t)c.n23 * c.noff * c.ts;
-            class_table_offset_kernel<<<(unsigned)((tot + 255) / 256), 256>>>(c.Tm.p, ddiag.p, (size_t)c.n23, c.n1, c.noff, (int)(npad - npos),
-                                                                              2 * npos - 1, c.ts, c.Td.p);
-            OQ_LAUNCHED();
-            OQ_CUDA(cudaDeviceSynchronize());
-            std::vector<int> dxmap((size_t)c.ns23 * npad, -1);
-            for (int g = 0; g < c.ns23; ++g)
-                for (int j = 0; j < npos; ++j) dxmap[(size_t)g * npad + j] = bypos[(size_t)g * npos + j];
-            OQ_TRY(c.dxmap.upload(dxmap.data(), dxmap.size()));
-            OQ_TRY(c.dxg.alloc((size_t)c.ns23 * npad * 6));
-            OQ_TRY(c.rg_items_pos.upload(rip.data(), rip.size()));
-            OQ_TRY(c.rpos.upload(rpos, nr));
-            OQ_TRY(c.dcta_row.upload(drow.data(), drow.size()));
-            OQ_TRY(c.dcta_begin.upload(dbeg.data(), dbeg.size()));
-            OQ_TRY(c.dcta_count.upload(dcnt.data(), dcnt.size()));
-            c.ndctas = (int)drow.size();
-            c.diag_ok = true;
-            c.table_bytes += td_bytes;
+            const size_t ndp = (size_t)c.dblk * kCdG + npad, ndp8 = (size_t)kCdBlk * kCdG + npad;
+            c.noff = (int)(pl.MR - 1 + ndp8);
+            c.dsmem = 2 * (ndp * 38 + ndp / 2 + (size_t)npad * 6) * sizeof(double) + (size_t)kCdSlices * c.dblk * kCdG * 6 * sizeof(double);
+            size_t free_b = 0, total_b = 0;
+            const double td_bytes = (double)c.n23 * c.noff * 38 * sizeof(double);
+            const bool fits = cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && td_bytes < 0.5 * (double)free_b;
+            if (ok && fits && c.dsmem <= 226 * 1024) {
+                const int nd = pl.MR + pl.NS - 1;
+                DevBuf<int> ddcls;
+                OQ_TRY(ddcls.upload(pl.dcls.data(), pl.dcls.size()));
+                const size_t tot = (size_t)c.n23 * c.noff * 38;
+                OQ_TRY(c.Td.alloc(tot));
+                class_table_offset_kernel<<<(unsigned)((tot + 255) / 256), 256>>>(c.Tm.p, c.ts, ddcls.p, nd, mode, pl.Q, (size_t)c.n23, c.n1,
+                                                                                  c.noff, npad - pl.NS, c.Td.p);
+                OQ_LAUNCHED();
+                OQ_CUDA(cudaDeviceSynchronize());
+                OQ_TRY(c.dxmap.upload(pl.xmap.data(), pl.xmap.size()));
+                OQ_TRY(c.dxg.alloc((size_t)c.ns23 * npad * 6));
+                OQ_TRY(c.dout_map.upload(pl.out_map.data(), pl.out_map.size()));
+                OQ_TRY(c.dcta_row.upload(pl.drow.data(), pl.drow.size()));
+                OQ_TRY(c.dcta_begin.upload(pl.dbeg.data(), pl.dbeg.size()));
+                OQ_TRY(c.dcta_count.upload(pl.dcnt.data(), pl.dcnt.size()));
+                OQ_TRY(c.dcta_m0.upload(pl.dm0.data(), pl.dm0.size()));
+                c.ndctas = (int)pl.drow.size();
+                c.npos = pl.NS; c.dmode = mode; c.dQ = pl.Q;
+                c.diag_ok = true;
+                c.table_bytes += td_bytes;
+            }
         }
     }
     OQ_CUDA(cudaDeviceSynchronize());

@@ -322,6 +322,16 @@ def class_form_plan(ma, elems=None) -> dict:
     return {k: (bool(v) if k in ("worthwhile", "diagonal") else int(v)) for k, v in zip(keys, out)}
 
 
+def class_window_check(ma, mf, which, begin=0, end=None) -> dict:
+    """Host-only self check of the sliding-window plan of gf21 (which=1) / gf12 (which=2) (oq_class_window_check)."""
+    end = (mf.nx * mf.nxi if which == 1 else len(ma)) if end is None else end
+    out = np.zeros(6, dtype=np.int64)
+    cma, cmf = ma.c_struct(), mf.c_struct()
+    _lib.check(_lib.load().oq_class_window_check(C.byref(cma), C.byref(cmf), int(which), int(begin), int(end),
+                                                 out.ctypes.data_as(C.POINTER(C.c_longlong))))
+    return dict(zip(("found", "residues", "runs", "checked", "mismatches", "unreached"), (int(v) for v in out)))
+
+
 def hex8_pair_classes(ma, mf=None, begin=0, end=None, recv=(), src=()):
     """Host-only view of the class decomposition behind device_mantle_mantle (mf=None) / device_mantle_fault
     (oq_hex8_pair_classes): (counts, rep_recv_x, rep_src_x, rep_recv_yz, rep_src_yz) for the sample pairs."""

@@ -232,3 +232,26 @@ def test_class_form_plan(oq):
     irr = oq.BEMHex8Mesh(c[0], c[1], -2e4 - c[2], c[0].copy(), c[1] - d[1] / 2, -2e4 - c[2] + d[2] / 2, d[0], d[1], d[2])
     ip = gf.class_form_plan(irr)
     assert not ip["worthwhile"] and not ip["diagonal"]
+
+
+def test_class_window_plans_of_the_fault_mantle_operands(oq):
+    """gf21 / gf12 in class form take the sliding-window kernel per residue of the finer grid (fault cells 4 or 5 to a
+    mantle cell): every (receiver, source) pair reached through the plan's maps gets the class the general maps give it,
+    every receiver is reached, on full operands and on row shards"""
+    from oetqf_b200 import gf
+    cases = [(W.FaultSpec(32e3, 8e3, 1e3, 1e3), W.BoxSpec(-16e3, -6e3, -8e3, 32e3, 12e3, -20e3, 8, 3, 4, tuple(np.cumprod(np.ones(4) * 1.3))), 4),
+             (W.FaultSpec(50 * 250.0, 8 * 250.0, 250.0, 250.0), W.BoxSpec(-6250.0, -10e3, -2e3, 12500.0, 20e3, -40e3, 10, 5, 4, ()), 5)]
+    for fs, bs, q in cases:
+        mf = oq.gen_mesh("RectOkada", fs.x, fs.xi, fs.dx, fs.dxi, fs.dip)
+        ma = oq.gen_mesh("BEMHex8Mesh", *bs.args())
+        nf, ne = mf.nx * mf.nxi, len(ma)
+        for which, n in ((1, nf), (2, ne)):
+            for b, e in ((0, n), (n // 3 + 1, 2 * n // 3 + 2)):
+                res = gf.class_window_check(ma, mf, which, b, e)
+                assert res["found"] == 1 and res["residues"] == q, (which, b, e, res)
+                assert res["mismatches"] == 0 and res["unreached"] == 0 and res["checked"] >= (e - b) * (ne if which == 1 else nf)
+    # a mantle grid that is not commensurate with the fault's: no plan (the operand keeps the general kernel)
+    fs = W.FaultSpec(32e3, 8e3, 1e3, 1e3)
+    mf = oq.gen_mesh("RectOkada", fs.x, fs.xi, fs.dx, fs.dxi, fs.dip)
+    ma = oq.gen_mesh("BEMHex8Mesh", -16e3, -6e3, -8e3, 32e3, 12e3, -20e3, 7, 3, 2, None)
+    assert gf.class_window_check(ma, mf, 1)["found"] == 0
