@@ -150,7 +150,7 @@ def main():
                                   "fp64_peak_tflops": peak / 1e12,
                                   "frac_of_fp64_peak": 2 * fma / (float(t[0]) / args.steps * 1e-3) / peak,
                                   "gf22_columns_vs_pointwise_closed_form_max_rel_err": col_err,
-                                  "note": "evaluation bound by shared-memory bandwidth: every FMA reads one table entry (cap 25 % of the DFMA peak)"}
+                                  "note": "fp64 FMA from shared-memory tables (csrc/classmat.cuh): window kernel where the grids are commensurate, general kernel (<= 25 % of the DFMA peak) otherwise"}
         print(json.dumps(line))
         if args.out:
             with open(args.out, "w") as fh:
