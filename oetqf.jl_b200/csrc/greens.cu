@@ -1068,7 +1068,7 @@ static int build_mantle_mantle(const OqHex8Mesh* ma, const OqQuadrature* quad, d
         bool built = false;
         if (mode == kHex8Auto || mode == kHex8Classes) built = mantle_mantle_classes(ma, e_begin, e_end, pc);
         const bool classes = hex8_use_classes(mode, built, pc, 36) && (!keep || pc.worthwhile);
-        if (keep && !classes) { delete M; return fail("mantle -> mantle: the cell pairs of this mesh do not fall into translation classes (keep the dense form)"); }
+        if (keep && !classes) { delete M; return fail("mantle -> mantle: the cell pairs of this mesh do not fall into translation classes worth a class form (fewer than 4 pairs per class, or a table that does not fit the free HBM): keep the dense form"); }
         DevHex8Tiles tiles;
         const bool tiled = !classes && mode != kHex8Pair;
         if (!classes && M->d.zero()) { delete M; return 1; }
