@@ -35,6 +35,8 @@ def main():
     ap.add_argument("--gf11", default="dense", choices=["dense", "fft"])
     ap.add_argument("--check-sources", type=int, default=3,
                     help="class form: check gf22 x against columns evaluated pointwise (oq_stress_vol_hex8) for this many sources")
+    ap.add_argument("--solve-steps", type=int, default=0,
+                    help="also take this many Tsit5 steps with the device-resident integrator (oq_solve) and report the time per step")
     args = ap.parse_args()
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
     torch.cuda.set_device(local)
@@ -132,6 +134,20 @@ def main():
                 want += c * col.T
         got = d22.gemv(x).reshape(6, e1 - e0)
         col_err = float(np.max(np.abs(got - want)) / np.max(np.abs(want)))
+    solve_rec = None
+    if args.solve_steps > 0:
+        loc = oq.dist.local_state(u0.x, rows, elems, kind="viscoelastic")
+        barrier()
+        t1 = time.perf_counter()
+        sol = oq.solve(prob, oq.Tsit5(), reltol=1e-6, abstol=1e-8, dt=1e-6, dtmax=0.2 * W.YEAR, maxiters=args.solve_steps,
+                       save_everystep=False, local_u0=loc)
+        barrier()
+        wall = time.perf_counter() - t1
+        steps = sol.stats["naccept"] + sol.stats["nreject"]
+        solve_rec = {"algorithm": "Tsit5 (oq_solve, state resident on the GPUs)", "steps": steps, "accepted": sol.stats["naccept"],
+                     "rhs_evaluations": sol.stats["nf"], "simulated_s": sol.stats["t"], "wall_s": wall,
+                     "ms_per_step": 1e3 * wall / max(1, steps), "retcode": sol.retcode,
+                     "finite": bool(all(np.all(np.isfinite(np.asarray(x))) for x in sol.u[-1].x))}
     forms = {k: m.form() for k, m in (("gf12", d12), ("gf21", d21), ("gf22", d22))}
     fma = sum((m.local_rows * m.cols) for m in (d12, d21, d22)) if args.form == "classes" else 0
     if rank == 0:
@@ -143,7 +159,7 @@ def main():
                 "assembly_ms_max_over_ranks": {"gf22": float(t[1]), "gf21": float(t[2]), "gf12": float(t[3])},
                 "assembly_rank0": asm, "assembly_wall_s": asm_wall,
                 "form": args.form, "gf11": args.gf11, "operands_rank0": forms,
-                "dense_equivalent_bytes_total": 8.0 * (nf * nf + 2 * 6 * ne * nf + (6 * ne) ** 2)}
+                "dense_equivalent_bytes_total": 8.0 * (nf * nf + 2 * 6 * ne * nf + (6 * ne) ** 2), "solve": solve_rec}
         if args.form == "classes":
             peak = oq.measure_fp64_peak()
             line["class_form"] = {"fma_per_eval_rank0": fma, "achieved_tflops": 2 * fma / (float(t[0]) / args.steps * 1e-3) / 1e12,
