@@ -676,16 +676,15 @@ static inline int make_class_operand(const Hex8PairClasses& pc, const DevBuf<dou
             crow.push_back(g); cbeg.push_back(b); ccnt.push_back(std::min(rb, rptr[g + 1] - b));
         }
     c.nctas = (int)crow.size();
-    // every row of D23 walks the source groups in ascending order of their class: receivers of different rows then
-    // need the same table slab at about the same time (one HBM fetch serves them all through L2)
+    // Every row of D23 walks the source groups in their natural order (the (y,z) classes of the sources, numbered as the
+    // mesh lists them).  On a structured mesh the slab a receiver row (ry, rz) needs for the source row (sy, sz) is the
+    // one of the offset ry - sy: the neighbouring receiver row needs it ONE step later, and since every row has the
+    // same number of sources per layer the lag never grows -- rows that run at the same time share their fetches through
+    // L2.  (Ordering by class id instead let the rows drift apart by hundreds of steps: L2 hit rate 6 %.)
     {
         std::vector<int> order((size_t)nr23 * c.ns23);
-        for (int g = 0; g < nr23; ++g) {
-            int* o = &order[(size_t)g * c.ns23];
-            for (int b = 0; b < c.ns23; ++b) o[b] = b;
-            const int* d = &pc.g23.D[(size_t)g * c.ns23];
-            std::stable_sort(o, o + c.ns23, [&](int a, int b) { return d[a] < d[b]; });
-        }
+        for (int g = 0; g < nr23; ++g)
+            for (int b = 0; b < c.ns23; ++b) order[(size_t)g * c.ns23 + b] = b;
         OQ_TRY(c.sg_order.upload(order.data(), order.size()));
     }
     OQ_TRY(c.rg_items.upload(ritems.data(), ritems.size()));
