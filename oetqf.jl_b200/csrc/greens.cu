@@ -1092,8 +1092,19 @@ static int build_mantle_mantle(const OqHex8Mesh* ma, const OqQuadrature* quad, d
                 std::vector<int> pr, ps;
                 long long c0 = 0, qstep = 1;
                 const bool grid = window_grid(xr, xs, 0, pr, ps, &c0, &qstep);
+                // walk order of the source (y,z) classes: by layer (q_z, dz, dy), then along y
+                std::vector<int> rep(pc.g23.ns, -1), walk(pc.g23.ns);
+                for (int e = 0; e < ma->n; ++e) if (rep[pc.g23.scls[e]] < 0) rep[pc.g23.scls[e]] = e;
+                for (int b = 0; b < pc.g23.ns; ++b) walk[b] = b;
+                std::stable_sort(walk.begin(), walk.end(), [&](int a, int b) {
+                    const int ea = rep[a], eb = rep[b];
+                    if (ma->qz[ea] != ma->qz[eb]) return ma->qz[ea] > ma->qz[eb];
+                    if (ma->dz[ea] != ma->dz[eb]) return ma->dz[ea] < ma->dz[eb];
+                    if (ma->dy[ea] != ma->dy[eb]) return ma->dy[ea] < ma->dy[eb];
+                    return ma->qy[ea] < ma->qy[eb];
+                });
                 rc = make_class_operand(pc, table, 6, 6, nel, ma->n, *M->cls, grid ? pr.data() + e_begin : nullptr, grid ? ps.data() : nullptr,
-                                        0, c0, qstep);
+                                        0, c0, qstep, &walk);
             } else {
             if (!rc) rc = tm.start();
             if (!rc) {

@@ -616,7 +616,7 @@ static inline bool coarse_grid(const std::vector<int>& pos, long long& c0, long 
 // origin c0 and step qstep of the coarse grid (plan_offsets); mode: 0 6x6 one grid, 1 sources coarse, 2 receivers coarse
 static inline int make_class_operand(const Hex8PairClasses& pc, const DevBuf<double>& table, int K, int P, int nr, int ns,
                                      ClassOperand& c, const int* rpos = nullptr, const int* spos = nullptr, int mode = 0,
-                                     long long c0 = 0, long long qstep = 1)
+                                     long long c0 = 0, long long qstep = 1, const std::vector<int>* sg_walk = nullptr)
 {
     c.K = K; c.P = P; c.nr = nr; c.ns = ns;
     c.n1 = pc.g1.n; c.n23 = pc.g23.n; c.ns1 = pc.g1.ns; c.ns23 = pc.g23.ns;
@@ -682,9 +682,13 @@ static inline int make_class_operand(const Hex8PairClasses& pc, const DevBuf<dou
     // same number of sources per layer the lag never grows -- rows that run at the same time share their fetches through
     // L2.  (Ordering by class id instead let the rows drift apart by hundreds of steps: L2 hit rate 6 %.)
     {
+        // sg_walk (optional, a permutation of the source groups that depends on the mesh alone): the order of the walk
+        // -- for the mantle sources layer by layer, along y inside a layer, so that the lag between neighbouring receiver
+        // rows is one step, not one sweep over the layers
         std::vector<int> order((size_t)nr23 * c.ns23);
+        const bool walk = sg_walk && (int)sg_walk->size() == c.ns23;
         for (int g = 0; g < nr23; ++g)
-            for (int b = 0; b < c.ns23; ++b) order[(size_t)g * c.ns23 + b] = b;
+            for (int b = 0; b < c.ns23; ++b) order[(size_t)g * c.ns23 + b] = walk ? (*sg_walk)[b] : b;
         OQ_TRY(c.sg_order.upload(order.data(), order.size()));
     }
     OQ_TRY(c.rg_items.upload(ritems.data(), ritems.size()));
